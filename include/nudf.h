@@ -1,0 +1,221 @@
+/* nudf.h -- C ABI of libnudf.so, the B200 (sm_100a) implementation of NeuralUDF's volume-rendering hot path.
+ *
+ * The reference (xxlong0/NeuralUDF) is pure PyTorch and has NO plugin / FFI layer;
+ * its "boundary" for this path is the Python surface `exp_runner_blending.py:15-19` imports.  This header is the
+ * C-ABI a drop-in replacement binds instead (INTEGRATION.md shows the ctypes stub): every entry point below cites
+ * the reference interface it replaces.  Conventions:
+ *   - all pointers are DEVICE pointers into caller-owned (torch) storages unless marked "host";
+ *   - fp32, row-major, explicit leading dimensions (ld, in floats);
+ *   - the library never allocates device memory: callers size workspaces with the *_floats() queries;
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *   - return value: 0 ok, -1 invalid argument, -2 CUDA error; nudf_last_error() has the text (thread-local).
+ */
+#ifndef NUDF_H_
+#define NUDF_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUDF_MAX_LAYERS 16
+#define NUDF_ABI_VERSION 1
+
+int nudf_abi_version(void);
+const char* nudf_last_error(void);
+/* GEMM engine for the wide (K,N in {128,256}) layers: 0 = exact-fp32 FFMA, 1 = tcgen05 3xBF16 split (default 1
+ * when built with the tensor path).  Small / odd-shaped contractions always use the FFMA engine. */
+int nudf_set_engine(int engine);
+int nudf_get_engine(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * UDFNetwork  (reference: models/fields.py:115-231; forward :192-211, gradient :219-231)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct nudf_udf_desc {
+  int32_t n_lin;      /* number of linear layers = n_layers + 1                                   */
+  int32_t d_in;       /* 3                                                                        */
+  int32_t multires;   /* positional-encoding octaves L (models/embedder.py:39-51)                 */
+  int32_t d_out;      /* 257 = 1 (udf) + feature width                                            */
+  int32_t skip_layer; /* layer whose input is cat(h, PE)/sqrt(2) (fields.py:202-203), -1 if none  */
+  float scale;        /* fields.py:193                                                            */
+  int32_t in_dim[NUDF_MAX_LAYERS];
+  int32_t out_dim[NUDF_MAX_LAYERS];
+  const float* weight_g[NUDF_MAX_LAYERS]; /* [out,1]  legacy weight_norm g  (lin{l}.weight_g)     */
+  const float* weight_v[NUDF_MAX_LAYERS]; /* [out,in] legacy weight_norm v  (lin{l}.weight_v)     */
+  const float* bias[NUDF_MAX_LAYERS];     /* [out]                          (lin{l}.bias)         */
+} nudf_udf_desc;
+
+/* floats needed for the folded weights W_l = g_l v_l/||v_l|| (rows padded to a multiple of 4 floats) */
+int64_t nudf_udf_folded_floats(const nudf_udf_desc* d);
+/* folds weight-norm once per optimiser step (replaces torch._weight_norm inside every nn.Linear call) */
+int nudf_udf_fold_weights(const nudf_udf_desc* d, float* wfold, void* stream);
+/* floats of the activation context saved by forward for `P` points (with_grad: also the reverse-sweep tensors) */
+int64_t nudf_udf_ctx_floats(const nudf_udf_desc* d, int64_t P, int with_grad);
+/* floats of the scratch needed by backward */
+int64_t nudf_udf_scratch_floats(const nudf_udf_desc* d, int64_t P);
+/* out[P, ld_out] <- cat(|y0|/scale, y[1:])   (UDFNetwork.forward, fields.py:192-211)
+ * grad[P,3]     <- d udf / d x exactly, by a reverse sweep (UDFNetwork.gradient, fields.py:219-231); may be NULL.
+ * ctx           <- saved activations (required; sized by nudf_udf_ctx_floats(d, P, grad != NULL)). */
+int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* out,
+                     int64_t ld_out, float* grad, float* ctx, void* stream);
+/* Value only (no context kept): udf[P] <- |y0|/scale.  Used by importance sampling and grid queries
+ * (udf_renderer_blending.py:731-733, 282-284; extract_mesh.py:60-73). `work` needs nudf_udf_ctx_floats(d,P,0). */
+int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* udf, float* work,
+                   void* stream);
+/* Parameter gradients for  L = <out_bar, out> + <grad_bar, grad>  (first- and second-order terms; the latter is
+ * what autograd's double backward through create_graph=True computes in the reference).  out_bar [P, ld_ob] and
+ * grad_bar [P,3] may each be NULL (= zero).  dwfold (same layout as wfold) and dbias (sum of out_dim floats) are
+ * OVERWRITTEN.  ctx must come from nudf_udf_forward with grad != NULL on the same points. */
+int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* out_bar,
+                      int64_t ld_ob, const float* grad_bar, const float* ctx, float* scratch, float* dwfold,
+                      float* dbias, void* stream);
+/* weight-norm backward: dwfold -> (dg[l] [out,1], dv[l] [out,in]) for every layer (overwrites) */
+int nudf_udf_unfold_grads(const nudf_udf_desc* d, const float* dwfold, float* const* dg, float* const* dv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ResidualRenderingNetwork, mode 'no_normal'  (reference: models/fields.py:400-495)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct nudf_color_desc {
+  int32_t n_lin;        /* n_layers + 1 (5) */
+  int32_t d_feature;    /* 256 */
+  int32_t d_hidden;     /* 128 */
+  int32_t d_out;        /* 3   */
+  int32_t n_blend;      /* blending_cand_views (10) */
+  int32_t multires_view;/* 4   */
+  const float* base_g[NUDF_MAX_LAYERS]; const float* base_v[NUDF_MAX_LAYERS]; const float* base_b[NUDF_MAX_LAYERS];
+  const float* main_g[NUDF_MAX_LAYERS]; const float* main_v[NUDF_MAX_LAYERS]; const float* main_b[NUDF_MAX_LAYERS];
+} nudf_color_desc;
+
+int64_t nudf_color_folded_floats(const nudf_color_desc* d);
+int nudf_color_fold_weights(const nudf_color_desc* d, float* wfold, void* stream);
+int64_t nudf_color_ctx_floats(const nudf_color_desc* d, int64_t P);
+int64_t nudf_color_scratch_floats(const nudf_color_desc* d, int64_t P);
+/* color_base[P,3], color[P,3], blend[P,n_blend] <- forward(points, view_dirs, feature_vectors) (fields.py:452-495).
+ * dirs is [P,3] when samples_per_ray <= 1; otherwise it is [P / samples_per_ray, 3] and row p uses
+ * dirs[p / samples_per_ray] (the reference materialises that expansion of rays_d, udf_renderer_blending.py:359-362). */
+int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float* pts, const float* dirs,
+                       int32_t samples_per_ray, const float* feat, int64_t ld_feat, int64_t P, float* color_base,
+                       float* color, float* blend, float* ctx, void* stream);
+/* grads wrt parameters (dwfold/dbias overwritten) and wrt feature_vectors (dfeat [P, ld_df] overwritten).
+ * cb_bar/c_bar [P,3], blend_bar [P,n_blend]; any may be NULL (= zero). */
+int nudf_color_backward(const nudf_color_desc* d, const float* wfold, int64_t P, const float* cb_bar,
+                        const float* c_bar, const float* blend_bar, const float* ctx, float* scratch, float* dfeat,
+                        int64_t ld_df, float* dwfold, float* dbias, void* stream);
+int nudf_color_unfold_grads(const nudf_color_desc* d, const float* dwfold, float* const* dg_base, float* const* dv_base,
+                            float* const* dg_main, float* const* dv_main, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * NeRF++ background network  (reference: models/fields.py:541-628, use_viewdirs=True)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct nudf_nerf_desc {
+  int32_t D;             /* 8   */
+  int32_t W;             /* 256 */
+  int32_t d_in;          /* 4   */
+  int32_t multires;      /* 10  */
+  int32_t multires_view; /* 4   */
+  int32_t skip;          /* skips[0] = 4: output of layer `skip` is concatenated as cat(PE, h) */
+  const float* pts_w[NUDF_MAX_LAYERS]; const float* pts_b[NUDF_MAX_LAYERS];
+  const float* views_w; const float* views_b;
+  const float* feature_w; const float* feature_b;
+  const float* alpha_w; const float* alpha_b;
+  const float* rgb_w; const float* rgb_b;
+} nudf_nerf_desc;
+
+int64_t nudf_nerf_ctx_floats(const nudf_nerf_desc* d, int64_t P);
+int64_t nudf_nerf_scratch_floats(const nudf_nerf_desc* d, int64_t P);
+/* sigma[P], rgb[P,3] <- NeRF.forward(pts4, view_dirs) (fields.py:599-628; no sigmoid on rgb) */
+int nudf_nerf_forward(const nudf_nerf_desc* d, const float* pts, const float* dirs, int32_t samples_per_ray,
+                      int64_t P, float* sigma, float* rgb, float* ctx, void* stream);
+/* parameter gradients; dparams[] order: pts_w[0], pts_b[0], ..., views_w, views_b, feature_w, feature_b, alpha_w,
+ * alpha_b, rgb_w, rgb_b  (each overwritten, same shape as the parameter). */
+int nudf_nerf_backward(const nudf_nerf_desc* d, int64_t P, const float* sigma_bar, const float* rgb_bar,
+                       const float* ctx, float* scratch, float* const* dparams, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * render_core ray kernels  (reference: models/udf_renderer_blending.py:327-584)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct nudf_render_cfg {
+  int32_t n_rays;           /* N */
+  int32_t n_samples;        /* S  (columns of z_vals entering render_core) */
+  int32_t n_outside;        /* O  (0 when no NeRF++ background is composited) */
+  float sample_dist;        /* last-interval length, :353 */
+  float cos_anneal_ratio;   /* :296-297; used only when has_cos_anneal != 0 */
+  int32_t has_cos_anneal;
+  float flip_saturation;    /* :409 */
+  float sparse_scale_factor;/* :553 */
+  int32_t use_norm_grad_for_cosine; /* :380-383 */
+  int32_t has_background_rgb; float background_rgb[3]; /* :527-528 */
+} nudf_render_cfg;
+
+/* pts[N*S,3], mid_z[N,S], dists[N,S] <- rays and z_vals (:352-362) */
+int nudf_ray_points(const float* rays_o, const float* rays_d, const float* z_vals, int32_t n_rays, int32_t n_samples,
+                    float sample_dist, float* pts, float* mid_z, float* dists, void* stream);
+
+/* per-sample / per-ray output pointers of the compositing pass; any per-sample pointer may be NULL */
+typedef struct nudf_render_out {
+  float* color_base; float* color; float* depth; float* normals;  /* [N,3] [N,3] [N,1] [N,3] */
+  float* weights;                                                 /* [N,S+O] */
+  float* weight_sum; float* weight_sum_fg_bg;                     /* [N,1] */
+  float* ray_sums;  /* [N,5]: sum relax*(|g|-1)^2, sum relax, sum near*(|g|-1)^2, sum near, sum exp(-k udf) */
+  float* gradient_mag; float* true_cos; float* vis_prob; float* alpha; float* alpha_plus; float* alpha_minus;
+  float* alpha_occ; float* raw_occ; float* inside_sphere;        /* [N,S] each */
+  float* gradients_flip;                                         /* [N,S,3] */
+} nudf_render_out;
+
+/* alpha compositing with the visibility-weighted UDF density (:364-553 minus the networks).
+ * heads: DEVICE float[3] = (inv_s, beta, gamma) after the clips of :373-377 (kept on the device so that a training
+ * step needs no host synchronisation).
+ * udf [N*S] (stride ld_udf floats between samples), grads [N*S,3], sampled colours [N*S,3] x2,
+ * bg_alpha [N,S+O] / bg_color [N,S+O,3] from render_core_outside (only columns >= S are read), may be NULL. */
+int nudf_render_composite_forward(const nudf_render_cfg* cfg, const float* heads, const float* rays_d, const float* pts,
+                                  const float* mid_z, const float* dists, const float* udf, int64_t ld_udf,
+                                  const float* grads, const float* sampled_color_base, const float* sampled_color,
+                                  const float* bg_alpha, const float* bg_color, const nudf_render_out* out,
+                                  void* stream);
+
+typedef struct nudf_render_bar {   /* upstream gradients, any may be NULL */
+  const float* color_base; const float* color; const float* depth;       /* [N,3] [N,3] [N,1] */
+  const float* weight_sum; const float* weight_sum_fg_bg;                 /* [N,1] */
+  const float* ray_sums; /* [N,5] d loss / d ray_sums (columns 1 and 3, the detached mask counts, are ignored) */
+} nudf_render_bar;
+
+/* Backward of the compositing pass.  Outputs (overwritten): udf_bar [N*S], grads_bar [N*S,3], scb_bar/sc_bar
+ * [N*S,3], bg_alpha_bar [N,S+O] / bg_color_bar [N,S+O,3] (may be NULL), scalar_bar[N,3] = per-ray partial
+ * d/d(inv_s, beta, gamma) (caller sums over rays). */
+int nudf_render_composite_backward(const nudf_render_cfg* cfg, const float* heads, const float* rays_d, const float* pts,
+                                   const float* mid_z, const float* dists, const float* udf, int64_t ld_udf,
+                                   const float* grads, const float* sampled_color_base, const float* sampled_color,
+                                   const float* bg_alpha, const float* bg_color, const nudf_render_bar* bar,
+                                   float* udf_bar, float* grads_bar, float* scb_bar,
+                                   float* sc_bar, float* bg_alpha_bar, float* bg_color_bar, float* scalar_bar,
+                                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * hierarchical sampling  (reference: models/udf_renderer_blending.py:66-104, 197-290, 723-755, 834-866)
+ * ------------------------------------------------------------------------------------------------------------ */
+/* One up-sampling round: new_z[N,m] (and optionally the searchsorted indices inds[N,m], int64) from z[N,n], udf[N,n].
+ * mode 0 = up_sample_unbias (:197-272), 1 = up_sample_no_occ_aware (:834-866).  Scans are accumulated in fp64 and
+ * rounded to fp32 per element, like torch's CPU cumsum/cumprod, so that indices are reproducible.
+ * u_lin: DEVICE float[m] = torch.linspace(0.5/m, 1-0.5/m, m) (:76), supplied by the caller so that its rounding is
+ * exactly torch's. */
+int nudf_up_sample(int32_t mode, const float* rays_o, const float* rays_d, const float* z, const float* udf,
+                   int32_t n_rays, int32_t n, int32_t m, float sample_dist, float inv_s, float beta, float gamma,
+                   const float* u_lin, float* new_z, int64_t* inds, void* stream);
+/* sample_pdf(det=True) alone (:66-104): bins [N,n], weights [N,n-1] -> samples [N,m], inds [N,m] */
+int nudf_sample_pdf(const float* bins, const float* weights, int32_t n_rays, int32_t n, int32_t m, const float* u_lin,
+                    float* samples, int64_t* inds, void* stream);
+/* cat_z_vals merge (:274-290): z_out[N,n+m] sorted union, udf_out gathered likewise (udf/new_udf/udf_out may be
+ * NULL for the `last` round).  new_pts[N*m,3] <- o + d*new_z (points to evaluate before the merge), optional. */
+int nudf_merge_z(const float* z, const float* new_z, const float* udf, const float* new_udf, int32_t n_rays, int32_t n,
+                 int32_t m, float* z_out, float* udf_out, void* stream);
+int nudf_points_on_rays(const float* rays_o, const float* rays_d, const float* z, int32_t n_rays, int32_t n,
+                        float* pts, void* stream);
+/* NeRF++ inverted-sphere inputs and alpha (:161-184): pts4[N*n,4], then alpha = 1-exp(-relu(sigma) dists) */
+int nudf_outside_points(const float* rays_o, const float* rays_d, const float* z, int32_t n_rays, int32_t n,
+                        int32_t col0, float sample_dist, float* pts4, float* dists, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUDF_H_ */

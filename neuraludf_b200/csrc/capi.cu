@@ -1,0 +1,45 @@
+// Library-level entry points of libnudf.so: error reporting, ABI version, engine selection.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/nudf.h"
+#include "common.cuh"
+
+namespace nudf {
+
+static thread_local char g_err[512] = "";
+static int g_engine = -1;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int get_engine() {
+  if (g_engine < 0) {
+    const char* e = getenv("NUDF_ENGINE");
+    g_engine = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_engine;
+}
+
+}  // namespace nudf
+
+extern "C" {
+
+int nudf_abi_version(void) { return NUDF_ABI_VERSION; }
+const char* nudf_last_error(void) { return nudf::g_err; }
+int nudf_set_engine(int engine) {
+  if (engine != 0 && engine != 1) {
+    nudf::set_error("nudf_set_engine: engine must be 0 (fp32 FFMA) or 1 (tcgen05 3xBF16)");
+    return -1;
+  }
+  nudf::g_engine = engine;
+  return 0;
+}
+int nudf_get_engine(void) { return nudf::get_engine(); }
+
+}  // extern "C"

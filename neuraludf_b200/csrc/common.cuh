@@ -1,0 +1,74 @@
+// Shared helpers for the nudf sm_100a kernels.
+// Math helpers marked NUDF_HD are compiled for the host as well (tests/host/ builds them with g++ to check
+// the per-sample formulas against the oracle on the CPU dev box, where no GPU exists).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NUDF_HD __host__ __device__ __forceinline__
+#else
+#define NUDF_HD inline
+#endif
+
+#define NUDF_MAX_LAYERS 16
+#define NUDF_SQRT1_2 0.70710678118654752440f
+
+namespace nudf {
+
+// nn.Softplus(beta=100, threshold=20)  (reference models/fields.py:180)
+NUDF_HD float softplus100(float z) {
+  float bz = 100.0f * z;
+  return bz > 20.0f ? z : log1pf(expf(bz)) * 0.01f;
+}
+// sigma(100 z) recovered from a = softplus100(z); exactly 1 in the linear regime (torch's softplus backward).
+NUDF_HD float sig_from_softplus(float a) {
+  float ba = 100.0f * a;
+  return ba > 20.0f ? 1.0f : -expm1f(-ba);
+}
+NUDF_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+NUDF_HD float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+}  // namespace nudf
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+namespace nudf {
+
+void set_error(const char* fmt, ...);
+
+#define NUDF_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      nudf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+#define NUDF_LAUNCH_OK()                                                                \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      nudf::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+#define NUDF_REQUIRE(cond, msg)                                                         \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      nudf::set_error("%s:%d: requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+      return -1;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace nudf
+#endif

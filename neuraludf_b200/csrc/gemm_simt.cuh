@@ -1,0 +1,294 @@
+// Exact-fp32 SIMT GEMM with fused epilogues (FFMA path).
+//
+// Role in the design (DESIGN.md section "kernels"): this is the bit-faithful fp32 engine used for (a) every
+// contraction that is too small or too oddly shaped for the tcgen05 path (K = 39/30/3, N = 1/3/13), (b) the
+// parity anchor the tensor-core path is validated against on the GPU.  C = epi(A * B) with the contraction
+// dimension K; operand layouts are chosen per call:
+//     A(m,k) = A_KC ? A[m*lda + k] : A[k*lda + m]
+//     B(k,n) = B_KC ? B[n*ldb + k] : B[k*ldb + n]
+// so  X W^T (forward / tangent chains)  is <true,true>,   dY W (reverse / backward chains) is <true,false>,
+// and dY^T X (weight gradients, contraction over points, split over gridDim.z with atomics) is <false,false>.
+#pragma once
+#include "common.cuh"
+
+namespace nudf {
+
+constexpr int GS_BM = 128, GS_BN = 128, GS_BK = 8, GS_PAD = 4, GS_THREADS = 256;
+
+template <bool KC>
+__device__ __forceinline__ void gs_load_tile(const float* __restrict__ src, int64_t ld, int64_t mn0, int64_t mn_total,
+                                             int k0, int k_end, float (*dst)[GS_BM + GS_PAD], int tid, bool vec_ok) {
+  if (KC) {
+    // K contiguous in memory: each thread fetches 4 consecutive k of one row, stores transposed.
+    int r = tid >> 1;
+    int kq = (tid & 1) * 4;
+    int64_t row = mn0 + r;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < mn_total) {
+      const float* p = src + row * ld + (k0 + kq);
+      if (vec_ok && (k0 + kq + 3) < k_end) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k0 + kq + j < k_end) v[j] = p[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[kq + j][r] = v[j];
+  } else {
+    // M/N contiguous in memory: each thread fetches 4 consecutive m (or n) of one k.
+    int k = tid >> 5;
+    int q = (tid & 31) * 4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 + k < k_end) {
+      const float* p = src + (int64_t)(k0 + k) * ld + (mn0 + q);
+      if (vec_ok && (mn0 + q + 3) < mn_total) {
+        t = *reinterpret_cast<const float4*>(p);
+      } else {
+        if (mn0 + q + 0 < mn_total) t.x = p[0];
+        if (mn0 + q + 1 < mn_total) t.y = p[1];
+        if (mn0 + q + 2 < mn_total) t.z = p[2];
+        if (mn0 + q + 3 < mn_total) t.w = p[3];
+      }
+    }
+    *reinterpret_cast<float4*>(&dst[k][q]) = t;
+  }
+}
+
+template <bool A_KC, bool B_KC, class Epi>
+__global__ void __launch_bounds__(GS_THREADS)
+gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t M, int N,
+                 int64_t K, int64_t k_chunk, Epi epi) {
+  __shared__ __align__(16) float As[2][GS_BK][GS_BM + GS_PAD];
+  __shared__ __align__(16) float Bs[2][GS_BK][GS_BN + GS_PAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * GS_BM;
+  const int n0 = blockIdx.y * GS_BN;
+  // contraction range of this CTA (split-K over gridDim.z; K may exceed 2^31 only through M, which it never does)
+  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke64 = (kb + k_chunk < K) ? kb + k_chunk : K;
+  const float* Ab = A_KC ? A + kb : A + kb * lda;
+  const float* Bb = B_KC ? B + kb : B + kb * ldb;
+  const int k_end = (int)(ke64 - kb);
+  const bool a_vec = ((lda & 3) == 0) && aligned16(Ab) && (A_KC || true);
+  const bool b_vec = ((ldb & 3) == 0) && aligned16(Bb);
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int n_tiles = (k_end + GS_BK - 1) / GS_BK;
+  if (n_tiles > 0) {
+    gs_load_tile<A_KC>(Ab, lda, m0, M, 0, k_end, As[0], tid, a_vec);
+    gs_load_tile<B_KC>(Bb, ldb, n0, N, 0, k_end, Bs[0], tid, b_vec);
+  }
+  __syncthreads();
+  for (int t = 0; t < n_tiles; ++t) {
+    const int cur = t & 1;
+    if (t + 1 < n_tiles) {
+      gs_load_tile<A_KC>(Ab, lda, m0, M, (t + 1) * GS_BK, k_end, As[cur ^ 1], tid, a_vec);
+      gs_load_tile<B_KC>(Bb, ldb, n0, N, (t + 1) * GS_BK, k_end, Bs[cur ^ 1], tid, b_vec);
+    }
+#pragma unroll
+    for (int k = 0; k < GS_BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= M) continue;
+#pragma unroll
+    for (int jg = 0; jg < 2; ++jg) {
+      int col = n0 + jg * 64 + tx * 4;
+      int nv = N - col;
+      if (nv <= 0) continue;
+      float v[4] = {acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]};
+      epi(row, col, v, nv < 4 ? nv : 4);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogues.  Each receives 4 consecutive columns of one row (nv of them valid).
+// ---------------------------------------------------------------------------------------------------------------
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS100 = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ void ld4(const float* __restrict__ base, int64_t ld, int64_t row, int col, int nv, float out[4]) {
+  const float* p = base + row * ld + col;
+  if (nv == 4 && ((ld & 3) == 0) && ((col & 3) == 0) && aligned16(base)) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = j < nv ? p[j] : 0.f;
+  }
+}
+__device__ __forceinline__ void st4(float* __restrict__ base, int64_t ld, int64_t row, int col, int nv, const float v[4]) {
+  float* p = base + row * ld + col;
+  if (nv == 4 && ((ld & 3) == 0) && ((col & 3) == 0) && aligned16(base)) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) p[j] = v[j];
+  }
+}
+
+// C[row, col] = act(acc + bias[col]) * post_scale
+struct EpiAct {
+  float* C; int64_t ldc; const float* bias; int act; float post_scale;
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = acc[j] + ((bias != nullptr && j < nv) ? bias[col + j] : 0.f);
+      if (act == ACT_RELU) x = fmaxf(x, 0.f);
+      else if (act == ACT_SOFTPLUS100) x = softplus100(x);
+      else if (act == ACT_SIGMOID) x = sigmoidf_(x);
+      v[j] = x * post_scale;
+    }
+    st4(C, ldc, row, col, nv, v);
+  }
+};
+
+// C[row, col] += acc   (split-K partial sums of weight gradients)
+struct EpiAtomicAdd {
+  float* C; int64_t ldc;
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) atomicAdd(C + row * ldc + col + j, acc[j]);
+  }
+};
+
+// Reverse sweep (grad_x udf): acc = G = d udf / d A[l].  Converts it into D_{l-1} = G * s * sigma(100 z_{l-1});
+// skip-concatenated columns (>= n_main) are routed to the positional-encoding gradient buffer.
+struct EpiRev {
+  int n_main; float post_scale;
+  const float* Anext; int64_t lda; float a_unscale;   // stored activation of layer l-1 (= A[l], first n_main cols)
+  float* Dprev; int64_t ldd;
+  float* Gpe; int64_t ldg;                             // [P, d_pe] or null
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nv) break;
+      int c = col + j;
+      float g = acc[j] * post_scale;
+      if (c < n_main) {
+        float a = Anext[row * lda + c] * a_unscale;
+        Dprev[row * ldd + c] = g * sig_from_softplus(a);
+      } else if (Gpe != nullptr) {
+        Gpe[row * ldg + (c - n_main)] = g;
+      }
+    }
+  }
+};
+
+// Last reverse GEMM (layer 0): Ge = acc + Gpe
+struct EpiRevFinal {
+  float* Ge; int64_t ldge; const float* Gpe; int64_t ldg;
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nv) break;
+      float g = acc[j];
+      if (Gpe != nullptr) g += Gpe[row * ldg + col + j];
+      Ge[row * ldge + col + j] = g;
+    }
+  }
+};
+
+// Tangent chain: acc = Zdot_l.  Q_l = Zdot * D_l * 100 (1 - S_l);  Adot_{l+1} = S_l * Zdot * post_scale.
+struct EpiTan {
+  const float* Anext; int64_t lda; float a_unscale;
+  const float* D; int64_t ldd;
+  float* Q; int64_t ldq;
+  float* AdotNext; int64_t ldn; float post_scale;
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+    float a[4], d[4], q[4], n[4];
+    ld4(Anext, lda, row, col, nv, a);
+    ld4(D, ldd, row, col, nv, d);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float s = sig_from_softplus(a[j] * a_unscale);
+      q[j] = acc[j] * d[j] * (100.0f * (1.0f - s));
+      n[j] = s * acc[j] * post_scale;
+    }
+    st4(Q, ldq, row, col, nv, q);
+    st4(AdotNext, ldn, row, col, nv, n);
+  }
+};
+
+// Backward chain: acc = Abar wrt A[l].  Zbar_{l-1} = Abar * post_scale * S_{l-1} + Q_{l-1} (in place over Q).
+struct EpiBwd {
+  int n_main; float post_scale;
+  const float* Anext; int64_t lda; float a_unscale;
+  float* QZ; int64_t ldq;
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nv) break;
+      int c = col + j;
+      if (c >= n_main) break;
+      float s = sig_from_softplus(Anext[row * lda + c] * a_unscale);
+      float* q = QZ + row * ldq + c;
+      *q = acc[j] * post_scale * s + *q;
+    }
+  }
+};
+
+// ReLU-MLP backward: dZ_prev[row, c - col_lo] = acc * (Yprev > 0) for c in [col_lo, col_hi); optional accumulate.
+struct EpiReluBwd {
+  int col_lo, col_hi;
+  const float* Yprev; int64_t ldy;   // post-ReLU output of the previous layer (null: no activation)
+  float* dZ; int64_t ldz; int accumulate;
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nv) break;
+      int c = col + j;
+      if (c < col_lo || c >= col_hi) continue;
+      int cc = c - col_lo;
+      float* p = dZ + row * ldz + cc;
+      float g = accumulate ? (*p + acc[j]) : acc[j];
+      if (Yprev != nullptr && !(Yprev[row * ldy + cc] > 0.f)) g = 0.f;   // mask applies to the accumulated sum
+      *p = g;
+    }
+  }
+};
+
+template <bool A_KC, bool B_KC, class Epi>
+static inline int gemm_simt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int64_t K,
+                            const Epi& epi, cudaStream_t st, int split_k = 1) {
+  if (M <= 0 || N <= 0) return 0;
+  int64_t k_chunk = K;
+  if (split_k > 1) {
+    k_chunk = round_up(cdiv(K, split_k), GS_BK);
+    split_k = (int)cdiv(K, k_chunk);
+  } else {
+    split_k = 1;
+  }
+  dim3 grid((unsigned)cdiv(M, GS_BM), (unsigned)cdiv(N, GS_BN), (unsigned)split_k);
+  gemm_simt_kernel<A_KC, B_KC, Epi><<<grid, GS_THREADS, 0, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace nudf

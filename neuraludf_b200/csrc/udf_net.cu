@@ -1,0 +1,547 @@
+// UDFNetwork on B200: forward value chain, exact input-gradient (reverse sweep), and the first+second order
+// parameter gradients (tangent chain + backward chain + weight-gradient contractions).
+// Reference semantics: models/fields.py:115-231 (forward :192-211, gradient :219-231); maths: SURVEY.md App. A and
+// tests/proto/udf_pipeline.py (the torch prototype of exactly this sequence, checked against autograd).
+#include "../../include/nudf.h"
+#include "common.cuh"
+#include "gemm_engine.cuh"
+
+namespace nudf {
+
+struct UdfPlan {
+  int n_lin, d_in, L, d_pe, d_out, skip;
+  float scale;
+  int in_dim[NUDF_MAX_LAYERS], out_dim[NUDF_MAX_LAYERS];
+  int64_t w_off[NUDF_MAX_LAYERS], w_ld[NUDF_MAX_LAYERS], w_total;
+  int64_t b_off[NUDF_MAX_LAYERS], b_total;
+  int pe_ld, y_ld;
+  int a_ld[NUDF_MAX_LAYERS];    // ld of A[l] (input of layer l), l >= 1
+  int o_ld[NUDF_MAX_LAYERS];    // ld of D[l] / Q[l] (out_dim rounded)
+  int max_ld;
+};
+
+static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
+  NUDF_REQUIRE(d != nullptr, "null desc");
+  NUDF_REQUIRE(d->n_lin >= 2 && d->n_lin <= NUDF_MAX_LAYERS, "n_lin out of range");
+  NUDF_REQUIRE(d->d_in == 3, "d_in must be 3");
+  NUDF_REQUIRE(d->multires >= 0 && d->multires <= 16, "multires out of range");
+  p->n_lin = d->n_lin; p->d_in = d->d_in; p->L = d->multires; p->d_out = d->d_out; p->skip = d->skip_layer;
+  p->scale = d->scale;
+  p->d_pe = d->d_in * (1 + 2 * d->multires);
+  NUDF_REQUIRE(p->skip < 0 || (p->skip >= 1 && p->skip <= p->n_lin - 1), "skip_layer out of range");
+  int64_t off = 0, boff = 0;
+  p->max_ld = 0;
+  for (int l = 0; l < p->n_lin; ++l) {
+    p->in_dim[l] = d->in_dim[l]; p->out_dim[l] = d->out_dim[l];
+    NUDF_REQUIRE(p->in_dim[l] > 0 && p->out_dim[l] > 0, "bad layer dims");
+    p->w_ld[l] = round_up(p->in_dim[l], 4);
+    p->w_off[l] = off; off += (int64_t)p->out_dim[l] * p->w_ld[l];
+    off = round_up(off, 4);
+    p->b_off[l] = boff; boff += p->out_dim[l];
+    p->a_ld[l] = (int)round_up(p->in_dim[l], 4);
+    p->o_ld[l] = (int)round_up(p->out_dim[l], 4);
+    if (p->a_ld[l] > p->max_ld) p->max_ld = p->a_ld[l];
+    if (p->o_ld[l] > p->max_ld) p->max_ld = p->o_ld[l];
+  }
+  p->w_total = off; p->b_total = boff;
+  NUDF_REQUIRE(p->in_dim[0] == p->d_pe, "in_dim[0] must equal the positional-encoding width");
+  NUDF_REQUIRE(p->out_dim[p->n_lin - 1] == p->d_out, "last layer width must equal d_out");
+  for (int l = 1; l < p->n_lin; ++l) {
+    int expect = p->out_dim[l - 1] + (l == p->skip ? p->d_pe : 0);
+    NUDF_REQUIRE(p->in_dim[l] == expect, "layer dims are not chained consistently");
+  }
+  p->pe_ld = (int)round_up(p->d_pe, 4);
+  p->y_ld = (int)round_up(p->d_out, 4);
+  return 0;
+}
+
+// ---- context / scratch layout (all offsets in floats; every block starts 16B-aligned) -------------------------
+struct UdfCtx {
+  int64_t e0, a[NUDF_MAX_LAYERS], y, sgn, d[NUDF_MAX_LAYERS], gpe, ge, total;
+};
+static void ctx_layout(const UdfPlan& p, int64_t P, int with_grad, UdfCtx* c) {
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
+  c->e0 = take(P * p.pe_ld);
+  for (int l = 1; l < p.n_lin; ++l) c->a[l] = take(P * p.a_ld[l]);
+  c->y = take(P * p.y_ld);
+  c->sgn = take(P);
+  if (with_grad) {
+    for (int l = 0; l < p.n_lin - 1; ++l) c->d[l] = take(P * p.o_ld[l]);
+    c->gpe = take(P * p.pe_ld);
+    c->ge = take(P * p.pe_ld);
+  }
+  c->total = off;
+}
+struct UdfScratch {
+  int64_t edot, adot[2], q[NUDF_MAX_LAYERS], zlast, total;
+};
+static void scratch_layout(const UdfPlan& p, int64_t P, UdfScratch* s) {
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
+  s->edot = take(P * p.pe_ld);
+  s->adot[0] = take(P * p.max_ld);
+  s->adot[1] = take(P * p.max_ld);
+  for (int l = 0; l < p.n_lin - 1; ++l) s->q[l] = take(P * p.o_ld[l]);
+  s->zlast = take(P * p.y_ld);
+  s->total = off;
+}
+
+// ---- element-wise kernels ---------------------------------------------------------------------------------------
+
+// W = g * v / ||v||  per output row (legacy weight_norm, dim=0); rows padded with zeros up to ld.
+__global__ void fold_kernel(const float* __restrict__ g, const float* __restrict__ v, int out, int in, int64_t ld,
+                            float* __restrict__ w) {
+  int row = blockIdx.x;
+  if (row >= out) return;
+  const float* vr = v + (int64_t)row * in;
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < in; k += blockDim.x) ss += vr[k] * vr[k];
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  float s = g[row] / sqrtf(red[0]);
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) w[(int64_t)row * ld + k] = k < in ? vr[k] * s : 0.f;
+}
+
+// dW -> dg = <dW, v>/||v|| ; dv = g/||v|| (dW - dg v/||v||)
+__global__ void unfold_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ dw,
+                              int out, int in, int64_t ld, float* __restrict__ dg, float* __restrict__ dv) {
+  int row = blockIdx.x;
+  if (row >= out) return;
+  const float* vr = v + (int64_t)row * in;
+  const float* dr = dw + (int64_t)row * ld;
+  float ss = 0.f, dot = 0.f;
+  for (int k = threadIdx.x; k < in; k += blockDim.x) { ss += vr[k] * vr[k]; dot += vr[k] * dr[k]; }
+  __shared__ float red[2][32];
+  for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t0 = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.f;
+    float t1 = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+    if (threadIdx.x == 0) { red[0][0] = t0; red[1][0] = t1; }
+  }
+  __syncthreads();
+  float n = sqrtf(red[0][0]);
+  float dgv = red[1][0] / n;          // <dW, v/||v||>
+  if (threadIdx.x == 0) dg[row] = dgv;
+  float gn = g[row] / n;
+  for (int k = threadIdx.x; k < in; k += blockDim.x) dv[(int64_t)row * in + k] = gn * (dr[k] - dgv * vr[k] / n);
+}
+
+// E0 = PE(x*scale) [P, pe_ld]; optionally also E0/sqrt2 into the skip columns of A[skip].
+__global__ void pe_forward_kernel(const float* __restrict__ pts, int64_t P, int L, float scale, float* __restrict__ e0,
+                                  int pe_ld, float* __restrict__ askip, int askip_ld, int askip_col) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float x[3] = {pts[i * 3 + 0] * scale, pts[i * 3 + 1] * scale, pts[i * 3 + 2] * scale};
+  float* e = e0 + i * pe_ld;
+  float* a = askip ? askip + i * askip_ld + askip_col : nullptr;
+  int d_pe = 3 * (1 + 2 * L);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { e[c] = x[c]; if (a) a[c] = x[c] * NUDF_SQRT1_2; }
+  float f = 1.0f;
+  for (int k = 0; k < L; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      e[3 + 6 * k + c] = s; e[3 + 6 * k + 3 + c] = co;
+      if (a) { a[3 + 6 * k + c] = s * NUDF_SQRT1_2; a[3 + 6 * k + 3 + c] = co * NUDF_SQRT1_2; }
+    }
+    f *= 2.0f;
+  }
+  for (int c = d_pe; c < pe_ld; ++c) e[c] = 0.f;
+}
+
+// out = cat(|y0|/scale, y[1:]); sgn = sign(y0)
+__global__ void udf_finalize_kernel(const float* __restrict__ y, int y_ld, int d_out, int64_t P, float inv_scale,
+                                    float* __restrict__ out, int64_t ld_out, float* __restrict__ sgn) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t row = idx / d_out;
+  int c = (int)(idx - row * d_out);
+  if (row >= P) return;
+  float v = y[row * y_ld + c];
+  if (c == 0) {
+    if (sgn) sgn[row] = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
+    v = fabsf(v) * inv_scale;
+  }
+  if (out) out[row * ld_out + c] = v;
+}
+__global__ void udf_value_only_kernel(const float* __restrict__ y, int y_ld, int64_t P, float inv_scale, float* __restrict__ udf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) udf[i] = fabsf(y[i * y_ld]) * inv_scale;
+}
+
+// Reverse-sweep seed: G = (sgn/scale) W_last[0,:]  -> D[n_lin-2] (and Gpe when the last layer is the skip layer).
+__global__ void rev_init_kernel(const float* __restrict__ sgn, const float* __restrict__ wlast_row0, int in_last,
+                                float inv_scale, int64_t P, EpiRev epi) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int cols4 = (in_last + 3) / 4;
+  int64_t row = idx / cols4;
+  int c = (int)(idx - row * cols4) * 4;
+  if (row >= P) return;
+  float s = sgn[row] * inv_scale;
+  float v[4];
+  int nv = in_last - c < 4 ? in_last - c : 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = j < nv ? s * wlast_row0[c + j] : 0.f;
+  epi(row, c, v, nv);
+}
+
+// grad_x = scale * J_e(x)^T Ge
+__global__ void pe_vjp_kernel(const float* __restrict__ pts, const float* __restrict__ ge, int pe_ld, int64_t P, int L,
+                              float scale, float* __restrict__ grad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float* g = ge + i * pe_ld;
+  float f = 1.0f;
+  float acc[3] = {g[0], g[1], g[2]};
+  float x[3] = {pts[i * 3 + 0] * scale, pts[i * 3 + 1] * scale, pts[i * 3 + 2] * scale};
+  for (int k = 0; k < L; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      acc[c] += f * (co * g[3 + 6 * k + c] - s * g[3 + 6 * k + 3 + c]);
+    }
+    f *= 2.0f;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) grad[i * 3 + c] = acc[c] * scale;
+}
+
+// Edot = scale * J_e(x) gbar  [P, pe_ld]
+__global__ void pe_jvp_kernel(const float* __restrict__ pts, const float* __restrict__ gbar, int64_t P, int L, float scale,
+                              float* __restrict__ edot, int pe_ld) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float* e = edot + i * pe_ld;
+  float x[3] = {pts[i * 3 + 0] * scale, pts[i * 3 + 1] * scale, pts[i * 3 + 2] * scale};
+  float v[3] = {gbar[i * 3 + 0] * scale, gbar[i * 3 + 1] * scale, gbar[i * 3 + 2] * scale};
+  int d_pe = 3 * (1 + 2 * L);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) e[c] = v[c];
+  float f = 1.0f;
+  for (int k = 0; k < L; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      e[3 + 6 * k + c] = f * co * v[c];
+      e[3 + 6 * k + 3 + c] = -f * s * v[c];
+    }
+    f *= 2.0f;
+  }
+  for (int c = d_pe; c < pe_ld; ++c) e[c] = 0.f;
+}
+
+// dst[:, col0 + c] = src[:, c] * scale   for c < ncols
+__global__ void copy_cols_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int col0,
+                                 int ncols, int64_t P, float scale) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t row = idx / ncols;
+  int c = (int)(idx - row * ncols);
+  if (row >= P) return;
+  dst[row * ldd + col0 + c] = src[row * lds + c] * scale;
+}
+
+// out[c] (+)= sum_rows w[row] * X[row, c]   (w may be null = 1).  grid: (col tiles of 32, row chunks)
+__global__ void weighted_colsum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, float wscale,
+                                       int64_t P, int N, int64_t rows_per_block, float* __restrict__ out) {
+  int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  int ry = threadIdx.x >> 5;  // 0..7
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < P ? r0 + rows_per_block : P;
+  float acc = 0.f;
+  if (c < N)
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += (w ? w[r] * wscale : 1.f) * X[r * ldx + c];
+  __shared__ float red[8][33];
+  red[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    atomicAdd(out + c, t);
+  }
+}
+
+int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st) {
+  if (P <= 0 || N <= 0) return 0;
+  int64_t rpb = 512;
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(P, rpb));
+  weighted_colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, w, wscale, P, N, rpb, out);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+// Zlast[:,0] = sgn * ob[:,0] / scale ; Zlast[:,1:] = ob[:,1:]
+__global__ void zlast_kernel(const float* __restrict__ ob, int64_t ld_ob, const float* __restrict__ sgn, float inv_scale,
+                             int d_out, int y_ld, int64_t P, float* __restrict__ z) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t row = idx / y_ld;
+  int c = (int)(idx - row * y_ld);
+  if (row >= P) return;
+  float v = 0.f;
+  if (c < d_out) {
+    v = ob[row * ld_ob + c];
+    if (c == 0) v *= sgn[row] * inv_scale;
+  }
+  z[row * y_ld + c] = v;
+}
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)cdiv(n, t); }
+
+// ---- host orchestration -----------------------------------------------------------------------------------------
+
+static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cudaStream_t st) {
+  for (int l = 0; l < p.n_lin; ++l) {
+    fold_kernel<<<p.out_dim[l], 128, 0, st>>>(d->weight_g[l], d->weight_v[l], p.out_dim[l], p.in_dim[l], p.w_ld[l],
+                                               wfold + p.w_off[l]);
+    NUDF_LAUNCH_OK();
+  }
+  return 0;
+}
+
+static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P,
+                       float* ctx, const UdfCtx& c, cudaStream_t st) {
+  float* e0 = ctx + c.e0;
+  float* askip = nullptr; int askip_ld = 0, askip_col = 0;
+  if (p.skip >= 1) { askip = ctx + c.a[p.skip]; askip_ld = p.a_ld[p.skip]; askip_col = p.out_dim[p.skip - 1]; }
+  pe_forward_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, P, p.L, p.scale, e0, p.pe_ld, askip, askip_ld, askip_col);
+  NUDF_LAUNCH_OK();
+  for (int l = 0; l < p.n_lin; ++l) {
+    const float* A = l == 0 ? e0 : ctx + c.a[l];
+    int64_t lda = l == 0 ? p.pe_ld : p.a_ld[l];
+    const float* W = wfold + p.w_off[l];
+    int rc;
+    if (l < p.n_lin - 1) {
+      EpiAct epi{ctx + c.a[l + 1], p.a_ld[l + 1], d->bias[l], ACT_SOFTPLUS100, (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f};
+      rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st);
+    } else {
+      EpiAct epi{ctx + c.y, p.y_ld, d->bias[l], ACT_NONE, 1.0f};
+      rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st);
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int reverse_chain(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, float* ctx, const UdfCtx& c,
+                         float* grad, cudaStream_t st) {
+  const int last = p.n_lin - 1;
+  auto make_rev = [&](int l) {  // epilogue that turns G (wrt A[l]) into D[l-1]
+    EpiRev e;
+    e.n_main = p.out_dim[l - 1];
+    e.post_scale = (l == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+    e.Anext = ctx + c.a[l]; e.lda = p.a_ld[l]; e.a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
+    e.Dprev = ctx + c.d[l - 1]; e.ldd = p.o_ld[l - 1];
+    e.Gpe = (l == p.skip) ? ctx + c.gpe : nullptr; e.ldg = p.pe_ld;
+    return e;
+  };
+  {
+    EpiRev e = make_rev(last);
+    int cols4 = (p.in_dim[last] + 3) / 4;
+    rev_init_kernel<<<nblk(P * cols4, 256), 256, 0, st>>>(ctx + c.sgn, wfold + p.w_off[last], p.in_dim[last],
+                                                          1.0f / p.scale, P, e);
+    NUDF_LAUNCH_OK();
+  }
+  for (int l = last - 1; l >= 1; --l) {
+    EpiRev e = make_rev(l);
+    int rc = gemm_nn(ctx + c.d[l], p.o_ld[l], wfold + p.w_off[l], p.w_ld[l], P, p.in_dim[l], p.out_dim[l], e, st);
+    if (rc) return rc;
+  }
+  {
+    EpiRevFinal e{ctx + c.ge, p.pe_ld, p.skip >= 1 ? ctx + c.gpe : nullptr, p.pe_ld};
+    int rc = gemm_nn(ctx + c.d[0], p.o_ld[0], wfold + p.w_off[0], p.w_ld[0], P, p.in_dim[0], p.out_dim[0], e, st);
+    if (rc) return rc;
+  }
+  pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace nudf
+
+using namespace nudf;
+
+extern "C" {
+
+int64_t nudf_udf_folded_floats(const nudf_udf_desc* d) {
+  UdfPlan p;
+  if (make_plan(d, &p)) return -1;
+  return p.w_total;
+}
+
+int nudf_udf_fold_weights(const nudf_udf_desc* d, float* wfold, void* stream) {
+  UdfPlan p;
+  if (int rc = make_plan(d, &p)) return rc;
+  NUDF_REQUIRE(wfold != nullptr, "null wfold");
+  cudaStream_t st = (cudaStream_t)stream;
+  return fold_all(p, d, wfold, st);
+}
+
+int64_t nudf_udf_ctx_floats(const nudf_udf_desc* d, int64_t P, int with_grad) {
+  UdfPlan p;
+  if (make_plan(d, &p)) return -1;
+  UdfCtx c;
+  ctx_layout(p, P, with_grad, &c);
+  return c.total;
+}
+
+int64_t nudf_udf_scratch_floats(const nudf_udf_desc* d, int64_t P) {
+  UdfPlan p;
+  if (make_plan(d, &p)) return -1;
+  UdfScratch s;
+  scratch_layout(p, P, &s);
+  return s.total;
+}
+
+int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* out, int64_t ld_out,
+                     float* grad, float* ctx, void* stream) {
+  UdfPlan p;
+  if (int rc = make_plan(d, &p)) return rc;
+  NUDF_REQUIRE(wfold && pts && ctx, "null pointer");
+  NUDF_REQUIRE(out == nullptr || ld_out >= p.d_out, "ld_out too small");
+  if (P <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  UdfCtx c;
+  ctx_layout(p, P, grad != nullptr, &c);
+  if (int rc = value_chain(p, d, wfold, pts, P, ctx, c, st)) return rc;
+  udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
+                                                              ctx + c.sgn);
+  NUDF_LAUNCH_OK();
+  if (grad) return reverse_chain(p, wfold, pts, P, ctx, c, grad, st);
+  return 0;
+}
+
+int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* udf, float* work,
+                   void* stream) {
+  UdfPlan p;
+  if (int rc = make_plan(d, &p)) return rc;
+  NUDF_REQUIRE(wfold && pts && work && udf, "null pointer");
+  if (P <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  UdfCtx c;
+  ctx_layout(p, P, 0, &c);
+  // value-only: the last layer needs only its row 0 (the udf head); the 256 feature rows are skipped.
+  UdfPlan pv = p;
+  pv.out_dim[p.n_lin - 1] = 1;
+  nudf_udf_desc dv = *d;
+  if (int rc = value_chain(pv, &dv, wfold, pts, P, work, c, st)) return rc;
+  udf_value_only_kernel<<<nblk(P, 256), 256, 0, st>>>(work + c.y, p.y_ld, P, 1.0f / p.scale, udf);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* out_bar,
+                      int64_t ld_ob, const float* grad_bar, const float* ctx_c, float* scratch, float* dwfold,
+                      float* dbias, void* stream) {
+  UdfPlan p;
+  if (int rc = make_plan(d, &p)) return rc;
+  NUDF_REQUIRE(wfold && pts && ctx_c && scratch && dwfold && dbias, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  NUDF_CUDA_OK(cudaMemsetAsync(dwfold, 0, sizeof(float) * p.w_total, st));
+  NUDF_CUDA_OK(cudaMemsetAsync(dbias, 0, sizeof(float) * p.b_total, st));
+  if (P <= 0) return 0;
+  float* ctx = const_cast<float*>(ctx_c);  // read-only use
+  UdfCtx c;
+  ctx_layout(p, P, 1, &c);
+  UdfScratch s;
+  scratch_layout(p, P, &s);
+  const int last = p.n_lin - 1;
+  const int split = (int)cdiv(P, 2048);
+
+  // ---- tangent chain (second-order terms) ----
+  if (grad_bar) {
+    float* edot = scratch + s.edot;
+    pe_jvp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, grad_bar, P, p.L, p.scale, edot, p.pe_ld);
+    NUDF_LAUNCH_OK();
+    const float* adot = edot;
+    int64_t ld_adot = p.pe_ld;
+    for (int l = 0; l < last; ++l) {
+      // dW_l += D_l^T Adot_l
+      EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
+      if (int rc = gemm_tn(ctx + c.d[l], p.o_ld[l], adot, ld_adot, p.out_dim[l], p.in_dim[l], P, ew, st, split)) return rc;
+      float* nxt = scratch + s.adot[l & 1];
+      int64_t ld_nxt = p.a_ld[l + 1];
+      EpiTan et;
+      et.Anext = ctx + c.a[l + 1]; et.lda = p.a_ld[l + 1];
+      et.a_unscale = (l + 1 == p.skip) ? 1.41421356237309504880f : 1.0f;
+      et.D = ctx + c.d[l]; et.ldd = p.o_ld[l];
+      et.Q = scratch + s.q[l]; et.ldq = p.o_ld[l];
+      et.AdotNext = nxt; et.ldn = ld_nxt; et.post_scale = (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+      if (int rc = gemm_nt(adot, ld_adot, wfold + p.w_off[l], p.w_ld[l], P, p.out_dim[l], p.in_dim[l], et, st))
+        return rc;
+      if (l + 1 == p.skip) {
+        copy_cols_kernel<<<nblk(P * p.d_pe, 256), 256, 0, st>>>(edot, p.pe_ld, nxt, ld_nxt, p.out_dim[l], p.d_pe, P,
+                                                                 NUDF_SQRT1_2);
+        NUDF_LAUNCH_OK();
+      }
+      adot = nxt; ld_adot = ld_nxt;
+    }
+    // g_last = W_last^T d_last with d_last = (sgn/scale) e_0  =>  dW_last[0,:] += sum_p (sgn/scale) Adot_last
+    if (int rc = colsum(adot, ld_adot, ctx + c.sgn, 1.0f / p.scale, P, p.in_dim[last], dwfold + p.w_off[last], st)) return rc;
+  }
+
+  // ---- backward chain ----
+  const bool has_q = grad_bar != nullptr;
+  if (!has_q)
+    for (int l = 0; l < last; ++l)
+      NUDF_CUDA_OK(cudaMemsetAsync(scratch + s.q[l], 0, sizeof(float) * P * p.o_ld[l], st));
+  float* zl = scratch + s.zlast;
+  if (out_bar) {
+    zlast_kernel<<<nblk(P * p.y_ld, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, p.d_out, p.y_ld, P, zl);
+    NUDF_LAUNCH_OK();
+    EpiAtomicAdd ew{dwfold + p.w_off[last], p.w_ld[last]};
+    if (int rc = gemm_tn(zl, p.y_ld, ctx + c.a[last], p.a_ld[last], p.out_dim[last], p.in_dim[last], P, ew, st, split)) return rc;
+    if (int rc = colsum(zl, p.y_ld, nullptr, 1.f, P, p.out_dim[last], dbias + p.b_off[last], st)) return rc;
+    EpiBwd eb;
+    eb.n_main = p.out_dim[last - 1]; eb.post_scale = (last == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+    eb.Anext = ctx + c.a[last]; eb.lda = p.a_ld[last]; eb.a_unscale = (last == p.skip) ? 1.41421356237309504880f : 1.0f;
+    eb.QZ = scratch + s.q[last - 1]; eb.ldq = p.o_ld[last - 1];
+    if (int rc = gemm_nn(zl, p.y_ld, wfold + p.w_off[last], p.w_ld[last], P, p.in_dim[last], p.out_dim[last], eb, st))
+      return rc;
+  }
+  for (int l = last - 1; l >= 0; --l) {
+    const float* zb = scratch + s.q[l];  // now holds Zbar_l
+    const float* A = l == 0 ? ctx + c.e0 : ctx + c.a[l];
+    int64_t lda = l == 0 ? p.pe_ld : p.a_ld[l];
+    EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
+    if (int rc = gemm_tn(zb, p.o_ld[l], A, lda, p.out_dim[l], p.in_dim[l], P, ew, st, split)) return rc;
+    if (int rc = colsum(zb, p.o_ld[l], nullptr, 1.f, P, p.out_dim[l], dbias + p.b_off[l], st)) return rc;
+    if (l > 0) {
+      EpiBwd eb;
+      eb.n_main = p.out_dim[l - 1]; eb.post_scale = (l == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+      eb.Anext = ctx + c.a[l]; eb.lda = p.a_ld[l]; eb.a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
+      eb.QZ = scratch + s.q[l - 1]; eb.ldq = p.o_ld[l - 1];
+      if (int rc = gemm_nn(zb, p.o_ld[l], wfold + p.w_off[l], p.w_ld[l], P, p.in_dim[l], p.out_dim[l], eb, st))
+        return rc;
+    }
+  }
+  return 0;
+}
+
+int nudf_udf_unfold_grads(const nudf_udf_desc* d, const float* dwfold, float* const* dg, float* const* dv, void* stream) {
+  UdfPlan p;
+  if (int rc = make_plan(d, &p)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < p.n_lin; ++l) {
+    unfold_kernel<<<p.out_dim[l], 128, 0, st>>>(d->weight_g[l], d->weight_v[l], dwfold + p.w_off[l], p.out_dim[l],
+                                                 p.in_dim[l], p.w_ld[l], dg[l], dv[l]);
+    NUDF_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -508,6 +508,62 @@ def render_core_outside(nerf_fn, o, d, z, sample_dist, n_outside):
 # a13: render_core, models/udf_renderer_blending.py:327-584 (blending inputs = None) --------------
 # ----------------------------------------------------------------------------------------------
 
+def composite(d, pts, mid, dists, udf, grads, scb, sc_, inv_s, beta, gamma, cos_anneal_ratio=None,
+              flip_saturation=0.0, background_rgb=None, background_alpha=None, background_sampled_color=None,
+              sparse_scale_factor=25000.0, use_norm_grad_for_cosine=False):
+    """Everything of render_core after the networks (:370-553): udf [N,S], grads [N,S,3], sampled colours
+    [N,S,3] x2, scalar heads already clipped.  Differentiable w.r.t. all floating inputs."""
+    n_rays, n = udf.shape
+    dirs = d[:, None, :].expand(n_rays, n, 3)
+    g_mag = torch.linalg.norm(grads, ord=2, dim=-1, keepdim=True)
+    g_norm = grads / (g_mag + 1e-5)
+    true_cos = (dirs * (g_norm if use_norm_grad_for_cosine else grads)).sum(-1)
+    with torch.no_grad():
+        flip = -torch.sign((dirs * g_norm).sum(-1, keepdim=True))
+        flip[flip == 0] = 1
+    raw_occ = logistic_density(udf, beta, 1.0, 1.0)
+    alpha_occ = 1.0 - torch.exp(-F.relu(raw_occ) * gamma * dists)
+    vm = (true_cos < 0.01).to(udf.dtype)
+    vm = torch.cat([vm[:, 1:], torch.ones_like(vm[:, :1])], dim=-1)
+    vis_prob = exclusive_cumprod((1.0 - alpha_occ + flip_saturation * vm).clip(0, 1) + 1e-7).clip(0, 1)
+    a_plus = neus_alpha(udf, -true_cos.abs(), dists, inv_s, cos_anneal_ratio)
+    a_minus = neus_alpha(-udf, -true_cos.abs(), dists, inv_s, cos_anneal_ratio)
+    alpha = a_plus * vis_prob + a_minus * (1 - vis_prob)
+    pn = torch.linalg.norm(pts.reshape(n_rays, n, 3), ord=2, dim=-1)
+    inside = (pn < 1.0).to(udf.dtype)
+    relax = (pn < 1.2).to(udf.dtype)
+    near_surface = (udf < 0.05).to(udf.dtype).detach()
+    alpha_fg = alpha
+    cb, c = scb, sc_
+    if background_alpha is not None:
+        alpha = torch.cat([alpha, background_alpha[:, n:]], dim=-1)
+        cb = torch.cat([cb, background_sampled_color[:, n:]], dim=1)
+        c = torch.cat([c, background_sampled_color[:, n:]], dim=1)
+    weights = alpha * exclusive_cumprod(1.0 - alpha + 1e-7)
+    wsum = weights.sum(dim=-1, keepdim=True)
+    color_base = (cb * weights[:, :, None]).sum(dim=1)
+    color = (c * weights[:, :, None]).sum(dim=1)
+    depth = (mid * weights[:, :n]).sum(dim=1, keepdim=True)
+    if background_rgb is not None:
+        color = color + background_rgb * (1.0 - wsum)
+    ge = (torch.linalg.norm(grads, ord=2, dim=-1) - 1.0) ** 2
+    gradient_error = (relax * ge).sum() / (relax.sum() + 1e-5)
+    gradient_error_ns = (near_surface * ge).sum() / (near_surface.sum() + 1e-5)
+    g_flip = flip * grads
+    sparse_error = torch.exp(-sparse_scale_factor * udf).sum(dim=1).mean()
+    return {
+        "color_base": color_base, "color": color, "weights": weights, "depth": depth,
+        "gradient_error": gradient_error, "gradient_error_near_surface": gradient_error_ns,
+        "normals": (g_flip * weights[:, :n, None]).sum(dim=1), "gradients": grads,
+        "gradients_flip": g_flip, "inside_sphere": inside, "udf": udf,
+        "gradient_mag": g_mag.reshape(n_rays, n), "true_cos": true_cos,
+        "vis_prob": vis_prob, "alpha": alpha_fg, "alpha_plus": a_plus, "alpha_minus": a_minus,
+        "mid_z_vals": mid, "dists": dists, "sparse_error": sparse_error, "alpha_occ": alpha_occ,
+        "raw_occ": raw_occ, "sampled_color_base": scb, "sampled_color": sc_,
+        "weight_sum": weights[:, :n].sum(dim=-1, keepdim=True), "weight_sum_fg_bg": wsum,
+    }
+
+
 def render_core(udf_p, udf_c, col_p, col_c, sc, o, d, z, sample_dist, cos_anneal_ratio=None,
                 background_rgb=None, background_alpha=None, background_sampled_color=None,
                 flip_saturation=0.0, sparse_scale_factor=25000.0, use_norm_grad_for_cosine=False,
@@ -526,63 +582,20 @@ def render_core(udf_p, udf_c, col_p, col_c, sc, o, d, z, sample_dist, cos_anneal
         # the reference re-runs the forward inside gradient(); the values are identical
         grads = torch.autograd.grad(udf, pts_g, torch.ones_like(udf), create_graph=True,
                                     retain_graph=True)[0]
-    g_mag = torch.linalg.norm(grads, ord=2, dim=-1, keepdim=True)
-    g_norm = grads / (g_mag + 1e-5)
     inv_s, beta, gamma = scalar_heads(sc, beta_min)
-    inv_s_e = inv_s.reshape(1, 1).expand(n_rays * n, 1)
-    true_cos = (dirs * (g_norm if use_norm_grad_for_cosine else grads)).sum(-1, keepdim=True)
-    with torch.no_grad():
-        flip = -torch.sign((dirs * g_norm).sum(-1, keepdim=True))
-        flip[flip == 0] = 1
-    raw_occ = logistic_density(udf, beta, 1.0, 1.0).reshape(n_rays, n)
-    alpha_occ = 1.0 - torch.exp(-F.relu(raw_occ) * gamma * dists)
-    vm = (true_cos < 0.01).to(z.dtype).reshape(n_rays, n)
-    vm = torch.cat([vm[:, 1:], torch.ones_like(vm[:, :1])], dim=-1)
-    vis_prob = exclusive_cumprod((1.0 - alpha_occ + flip_saturation * vm).clip(0, 1) + 1e-7).clip(0, 1)
-    a_plus = neus_alpha(udf, -true_cos.abs(), dists.reshape(-1, 1), inv_s_e, cos_anneal_ratio).reshape(n_rays, n)
-    a_minus = neus_alpha(-udf, -true_cos.abs(), dists.reshape(-1, 1), inv_s_e, cos_anneal_ratio).reshape(n_rays, n)
-    alpha = a_plus * vis_prob + a_minus * (1 - vis_prob)
-    udf2 = udf.reshape(n_rays, n)
-
     cb, c, blend = color_mlp(col_p, col_c, pts_g, dirs, feat)
-    cb = cb.reshape(n_rays, n, 3)
-    c = c.reshape(n_rays, n, 3)
-
-    pn = torch.linalg.norm(pts, ord=2, dim=-1).reshape(n_rays, n)
-    inside = (pn < 1.0).to(z.dtype)
-    relax = (pn < 1.2).to(z.dtype)
-    near_surface = (udf2 < 0.05).to(z.dtype).detach()
-
-    alpha_fg = alpha
-    if background_alpha is not None:
-        alpha = torch.cat([alpha, background_alpha[:, n:]], dim=-1)
-        cb = torch.cat([cb, background_sampled_color[:, n:]], dim=1)
-        c = torch.cat([c, background_sampled_color[:, n:]], dim=1)
-    weights = alpha * exclusive_cumprod(1.0 - alpha + 1e-7)
-    wsum = weights.sum(dim=-1, keepdim=True)
-    color_base = (cb * weights[:, :, None]).sum(dim=1)
-    color = (c * weights[:, :, None]).sum(dim=1)
-    depth = (mid * weights[:, :n]).sum(dim=1, keepdim=True)
-    if background_rgb is not None:
-        color = color + background_rgb * (1.0 - wsum)
-    ge = (torch.linalg.norm(grads.reshape(n_rays, n, 3), ord=2, dim=-1) - 1.0) ** 2
-    gradient_error = (relax * ge).sum() / (relax.sum() + 1e-5)
-    gradient_error_ns = (near_surface * ge).sum() / (near_surface.sum() + 1e-5)
-    g3 = grads.reshape(n_rays, n, 3)
-    g_flip = flip.reshape(n_rays, n, 1) * g3
-    sparse_error = torch.exp(-sparse_scale_factor * udf2).sum(dim=1).mean()
-    return {
-        "color_base": color_base, "color": color, "weights": weights,
-        "s_val": 1.0 / inv_s_e, "beta": 1.0 / beta, "gamma": gamma, "depth": depth,
-        "gradient_error": gradient_error, "gradient_error_near_surface": gradient_error_ns,
-        "normals": (g_flip * weights[:, :n, None]).sum(dim=1), "gradients": g3,
-        "gradients_flip": g_flip, "inside_sphere": inside, "udf": udf2,
-        "gradient_mag": g_mag.reshape(n_rays, n), "true_cos": true_cos.reshape(n_rays, n),
-        "vis_prob": vis_prob, "alpha": alpha_fg, "alpha_plus": a_plus, "alpha_minus": a_minus,
-        "mid_z_vals": mid, "dists": dists, "sparse_error": sparse_error, "alpha_occ": alpha_occ,
-        "raw_occ": raw_occ, "blending_weights": blend.reshape(n_rays, n, -1),
-        "sampled_color_base": cb[:, :n], "sampled_color": c[:, :n],
-    }
+    ret = composite(d, pts, mid, dists, udf.reshape(n_rays, n), grads.reshape(n_rays, n, 3),
+                    cb.reshape(n_rays, n, 3), c.reshape(n_rays, n, 3), inv_s, beta, gamma,
+                    cos_anneal_ratio=cos_anneal_ratio, flip_saturation=flip_saturation,
+                    background_rgb=background_rgb, background_alpha=background_alpha,
+                    background_sampled_color=background_sampled_color,
+                    sparse_scale_factor=sparse_scale_factor,
+                    use_norm_grad_for_cosine=use_norm_grad_for_cosine)
+    ret["s_val"] = 1.0 / inv_s.reshape(1, 1).expand(n_rays * n, 1)
+    ret["beta"] = 1.0 / beta
+    ret["gamma"] = gamma
+    ret["blending_weights"] = blend.reshape(n_rays, n, -1)
+    return ret
 
 
 # ----------------------------------------------------------------------------------------------
@@ -626,8 +639,6 @@ def render(udf_p, udf_c, col_p, col_c, nerf_p, nerf_c, sc, o, d, near, far, n_sa
                       flip_saturation=flip_saturation, **kw)
     n = z.shape[1]
     ret["z_vals"] = z
-    ret["weight_sum"] = ret["weights"][:, :n].sum(dim=-1, keepdim=True)
-    ret["weight_sum_fg_bg"] = ret["weights"].sum(dim=-1, keepdim=True)
     ret["variance"] = ret["s_val"]
     return ret
 
