@@ -28,6 +28,12 @@ const char* nudf_last_error(void);
  * when built with the tensor path).  Small / odd-shaped contractions always use the FFMA engine. */
 int nudf_set_engine(int engine);
 int nudf_get_engine(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+int64_t nudf_launch_count(void);
+/* One fused dense layer Y[M,N] = act(X[M,K] W[N,K]^T + bias), act: 0 none, 1 relu, 2 softplus(beta=100), 3 sigmoid.
+ * The building block of every network below (an nn.Linear + activation of the reference, e.g. fields.py:205-208). */
+int nudf_dense_forward(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* Y, int64_t ldy,
+                       int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * UDFNetwork  (reference: models/fields.py:115-231; forward :192-211, gradient :219-231)

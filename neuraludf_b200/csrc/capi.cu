@@ -10,6 +10,8 @@ namespace nudf {
 
 static thread_local char g_err[512] = "";
 static int g_engine = -1;
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -41,5 +43,6 @@ int nudf_set_engine(int engine) {
   return 0;
 }
 int nudf_get_engine(void) { return nudf::get_engine(); }
+int64_t nudf_launch_count(void) { return (int64_t)__atomic_load_n(&nudf::g_launches, __ATOMIC_RELAXED); }
 
 }  // extern "C"

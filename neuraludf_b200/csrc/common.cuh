@@ -38,6 +38,7 @@ NUDF_HD float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), 
 namespace nudf {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define NUDF_CUDA_OK(expr)                                                              \
   do {                                                                                  \
@@ -50,6 +51,7 @@ void set_error(const char* fmt, ...);
 
 #define NUDF_LAUNCH_OK()                                                                \
   do {                                                                                  \
+    nudf::count_launch();                                                               \
     cudaError_t _e = cudaGetLastError();                                                \
     if (_e != cudaSuccess) {                                                            \
       nudf::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -207,6 +207,17 @@ using namespace nudf;
 
 extern "C" {
 
+// One dense layer Y = act(X W^T + b): the primitive every network above is built from, exported for micro-benchmarks
+// (bench.py times the dominant 256x256 layer through it) and for callers that want a single fused layer.
+int nudf_dense_forward(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* Y, int64_t ldy,
+                       int64_t M, int32_t N, int32_t K, int32_t act, void* stream) {
+  NUDF_REQUIRE(X && W && Y, "null pointer");
+  NUDF_REQUIRE(act >= 0 && act <= 3, "act must be 0 (none), 1 (relu), 2 (softplus beta=100), 3 (sigmoid)");
+  NUDF_REQUIRE(ldx >= K && ldw >= K && ldy >= N, "leading dimension too small");
+  EpiAct e{Y, ldy, bias, act, 1.0f};
+  return gemm_nt(X, ldx, W, ldw, M, N, K, e, (cudaStream_t)stream);
+}
+
 int64_t nudf_color_folded_floats(const nudf_color_desc* d) {
   ColorPlan p;
   if (color_plan(d, &p)) return -1;

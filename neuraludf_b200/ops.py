@@ -1,0 +1,539 @@
+"""torch.autograd.Function wrappers over the libnudf C-ABI.
+
+PyTorch is plumbing here: it owns the device buffers (parameters, activations, workspaces), the stream and the
+autograd graph between the three kernel groups (UDF net -> colour net -> compositing).  All arithmetic is in
+libnudf.so; there is no eager fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("neuraludf_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path"
+                               % t.device)
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UDF network
+# ---------------------------------------------------------------------------------------------------------------
+class UdfHandle:
+    """Per-module state: C descriptor, folded-weight buffer (re-folded whenever a parameter changed)."""
+
+    def __init__(self, layers, d_in, multires, d_out, skip_layer, scale):
+        # layers: list of modules with .weight_g [out,1], .weight_v [out,in], .bias [out]
+        self.layers = layers
+        self.meta = (d_in, multires, d_out, skip_layer, float(scale))
+        self._key = None
+        self.desc = None
+        self.wfold = None
+
+    def params(self):
+        ps = []
+        for m in self.layers:
+            ps += [m.weight_g, m.weight_v, m.bias]
+        return ps
+
+    def refresh(self):
+        ps = self.params()
+        _require_cuda(*ps)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key == self._key:
+            return
+        d = L.UdfDesc()
+        d.n_lin = len(self.layers)
+        d.d_in, d.multires, d.d_out, d.skip_layer, d.scale = self.meta
+        for l, m in enumerate(self.layers):
+            for p in (m.weight_g, m.weight_v, m.bias):
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("UDFNetwork parameters must be contiguous float32")
+            d.out_dim[l], d.in_dim[l] = m.weight_v.shape
+            d.weight_g[l] = m.weight_g.data_ptr()
+            d.weight_v[l] = m.weight_v.data_ptr()
+            d.bias[l] = m.bias.data_ptr()
+        lib = L.lib()
+        n = lib.nudf_udf_folded_floats(ctypes.byref(d))
+        if n < 0:
+            L.check(-1, "nudf_udf_folded_floats")
+        dev = ps[0].device
+        if self.wfold is None or self.wfold.numel() != n or self.wfold.device != dev:
+            self.wfold = torch.empty(n, dtype=torch.float32, device=dev)
+        L.check(lib.nudf_udf_fold_weights(ctypes.byref(d), L.ptr(self.wfold), L.stream_ptr()), "nudf_udf_fold_weights")
+        self.desc = d
+        self._key = key
+
+
+class _UdfFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, handle, with_grad, *params):
+        lib = L.lib()
+        handle.refresh()
+        pts = _f32c(pts)
+        _require_cuda(pts)
+        P = pts.shape[0]
+        d_out = handle.meta[2]
+        out = torch.empty(P, d_out, dtype=torch.float32, device=pts.device)
+        grad = torch.empty(P, 3, dtype=torch.float32, device=pts.device) if with_grad else None
+        nctx = lib.nudf_udf_ctx_floats(ctypes.byref(handle.desc), P, 1 if with_grad else 0)
+        buf = torch.empty(max(nctx, 1), dtype=torch.float32, device=pts.device)
+        L.check(lib.nudf_udf_forward(ctypes.byref(handle.desc), L.ptr(handle.wfold), L.ptr(pts), P, L.ptr(out), d_out,
+                                     L.ptr(grad), L.ptr(buf), L.stream_ptr()), "nudf_udf_forward")
+        ctx.handle, ctx.with_grad, ctx.P = handle, with_grad, P
+        ctx.save_for_backward(pts, buf)
+        ctx.key = handle._key
+        if with_grad:
+            return out, grad
+        return out, torch.empty(0, device=pts.device)
+
+    @staticmethod
+    def backward(ctx, out_bar, grad_bar):
+        lib = L.lib()
+        h = ctx.handle
+        pts, buf = ctx.saved_tensors
+        if h._key != ctx.key:
+            raise RuntimeError("UDFNetwork parameters were modified between forward and backward")
+        P = ctx.P
+        if not ctx.with_grad:
+            grad_bar = None
+        out_bar = _f32c(out_bar)
+        grad_bar = _f32c(grad_bar)
+        dev = pts.device
+        nscr = lib.nudf_udf_scratch_floats(ctypes.byref(h.desc), P)
+        scratch = torch.empty(max(nscr, 1), dtype=torch.float32, device=dev)
+        dw = torch.empty_like(h.wfold)
+        nb = sum(int(m.bias.numel()) for m in h.layers)
+        db = torch.empty(nb, dtype=torch.float32, device=dev)
+        L.check(lib.nudf_udf_backward(ctypes.byref(h.desc), L.ptr(h.wfold), L.ptr(pts), P, L.ptr(out_bar),
+                                      out_bar.shape[1] if out_bar is not None else 0, L.ptr(grad_bar), L.ptr(buf),
+                                      L.ptr(scratch), L.ptr(dw), L.ptr(db), L.stream_ptr()), "nudf_udf_backward")
+        dgs = [torch.empty_like(m.weight_g) for m in h.layers]
+        dvs = [torch.empty_like(m.weight_v) for m in h.layers]
+        L.check(lib.nudf_udf_unfold_grads(ctypes.byref(h.desc), L.ptr(dw), _ptr_array(dgs), _ptr_array(dvs),
+                                          L.stream_ptr()), "nudf_udf_unfold_grads")
+        grads = []
+        off = 0
+        for l, m in enumerate(h.layers):
+            n = m.bias.numel()
+            grads += [dgs[l], dvs[l], db[off:off + n].clone()]
+            off += n
+        return (None, None, None) + tuple(grads)
+
+
+def udf_forward(handle, pts, with_grad):
+    """(out [P,d_out], grad [P,3] or None); differentiable w.r.t. the module parameters (not w.r.t. pts)."""
+    out, grad = _UdfFunction.apply(pts, handle, with_grad, *handle.params())
+    return out, (grad if with_grad else None)
+
+
+def udf_value(handle, pts):
+    """udf [P] without autograd and without keeping activations (sampling / grid queries)."""
+    lib = L.lib()
+    handle.refresh()
+    pts = _f32c(pts)
+    _require_cuda(pts)
+    P = pts.shape[0]
+    udf = torch.empty(P, dtype=torch.float32, device=pts.device)
+    n = lib.nudf_udf_ctx_floats(ctypes.byref(handle.desc), P, 0)
+    work = torch.empty(max(n, 1), dtype=torch.float32, device=pts.device)
+    L.check(lib.nudf_udf_value(ctypes.byref(handle.desc), L.ptr(handle.wfold), L.ptr(pts), P, L.ptr(udf), L.ptr(work),
+                               L.stream_ptr()), "nudf_udf_value")
+    return udf
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# colour network
+# ---------------------------------------------------------------------------------------------------------------
+class ColorHandle:
+    def __init__(self, base_layers, main_layers, d_feature, d_hidden, d_out, n_blend, multires_view):
+        self.base, self.main = base_layers, main_layers
+        self.meta = (d_feature, d_hidden, d_out, n_blend, multires_view)
+        self._key = None
+        self.desc = None
+        self.wfold = None
+
+    def params(self):
+        ps = []
+        for m in list(self.main) + list(self.base):
+            ps += [m.weight_g, m.weight_v, m.bias]
+        return ps
+
+    def refresh(self):
+        ps = self.params()
+        _require_cuda(*ps)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key == self._key:
+            return
+        d = L.ColorDesc()
+        d.n_lin = len(self.base)
+        d.d_feature, d.d_hidden, d.d_out, d.n_blend, d.multires_view = self.meta
+        for l, m in enumerate(self.base):
+            d.base_g[l], d.base_v[l], d.base_b[l] = m.weight_g.data_ptr(), m.weight_v.data_ptr(), m.bias.data_ptr()
+        for l, m in enumerate(self.main):
+            d.main_g[l], d.main_v[l], d.main_b[l] = m.weight_g.data_ptr(), m.weight_v.data_ptr(), m.bias.data_ptr()
+        lib = L.lib()
+        n = lib.nudf_color_folded_floats(ctypes.byref(d))
+        if n < 0:
+            L.check(-1, "nudf_color_folded_floats")
+        dev = ps[0].device
+        if self.wfold is None or self.wfold.numel() != n or self.wfold.device != dev:
+            self.wfold = torch.empty(n, dtype=torch.float32, device=dev)
+        L.check(lib.nudf_color_fold_weights(ctypes.byref(d), L.ptr(self.wfold), L.stream_ptr()), "nudf_color_fold_weights")
+        self.desc = d
+        self._key = key
+
+
+class _ColorFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, dirs, feat, handle, samples_per_ray, *params):
+        lib = L.lib()
+        handle.refresh()
+        pts, dirs = _f32c(pts), _f32c(dirs)
+        if feat.dtype != torch.float32 or feat.stride(-1) != 1:
+            feat = _f32c(feat)
+        _require_cuda(pts, dirs, feat)
+        P = pts.shape[0]
+        d_feature, d_hidden, d_out, n_blend, _ = handle.meta
+        dev = pts.device
+        cb = torch.empty(P, d_out, dtype=torch.float32, device=dev)
+        c = torch.empty(P, d_out, dtype=torch.float32, device=dev)
+        bl = torch.empty(P, n_blend, dtype=torch.float32, device=dev)
+        n = lib.nudf_color_ctx_floats(ctypes.byref(handle.desc), P)
+        buf = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        L.check(lib.nudf_color_forward(ctypes.byref(handle.desc), L.ptr(handle.wfold), L.ptr(pts), L.ptr(dirs),
+                                       int(samples_per_ray), L.ptr(feat), feat.stride(0), P, L.ptr(cb), L.ptr(c),
+                                       L.ptr(bl), L.ptr(buf), L.stream_ptr()), "nudf_color_forward")
+        ctx.handle, ctx.P, ctx.key = handle, P, handle._key
+        ctx.save_for_backward(buf)
+        return cb, c, bl
+
+    @staticmethod
+    def backward(ctx, cb_bar, c_bar, bl_bar):
+        lib = L.lib()
+        h = ctx.handle
+        (buf,) = ctx.saved_tensors
+        if h._key != ctx.key:
+            raise RuntimeError("colour-network parameters were modified between forward and backward")
+        P = ctx.P
+        dev = buf.device
+        cb_bar, c_bar, bl_bar = _f32c(cb_bar), _f32c(c_bar), _f32c(bl_bar)
+        d_feature = h.meta[0]
+        nscr = lib.nudf_color_scratch_floats(ctypes.byref(h.desc), P)
+        scratch = torch.empty(max(nscr, 1), dtype=torch.float32, device=dev)
+        dfeat = torch.empty(P, d_feature, dtype=torch.float32, device=dev)
+        dw = torch.empty_like(h.wfold)
+        nb = sum(int(m.bias.numel()) for m in list(h.base) + list(h.main))
+        db = torch.empty(nb, dtype=torch.float32, device=dev)
+        L.check(lib.nudf_color_backward(ctypes.byref(h.desc), L.ptr(h.wfold), P, L.ptr(cb_bar), L.ptr(c_bar),
+                                        L.ptr(bl_bar), L.ptr(buf), L.ptr(scratch), L.ptr(dfeat), d_feature, L.ptr(dw),
+                                        L.ptr(db), L.stream_ptr()), "nudf_color_backward")
+        dgb = [torch.empty_like(m.weight_g) for m in h.base]
+        dvb = [torch.empty_like(m.weight_v) for m in h.base]
+        dgm = [torch.empty_like(m.weight_g) for m in h.main]
+        dvm = [torch.empty_like(m.weight_v) for m in h.main]
+        L.check(lib.nudf_color_unfold_grads(ctypes.byref(h.desc), L.ptr(dw), _ptr_array(dgb), _ptr_array(dvb),
+                                            _ptr_array(dgm), _ptr_array(dvm), L.stream_ptr()), "nudf_color_unfold_grads")
+        # bias layout in the library: base layers first, then main layers
+        off = 0
+        bb, bm = [], []
+        for m in h.base:
+            n = m.bias.numel(); bb.append(db[off:off + n].clone()); off += n
+        for m in h.main:
+            n = m.bias.numel(); bm.append(db[off:off + n].clone()); off += n
+        grads = []
+        for l in range(len(h.main)):
+            grads += [dgm[l], dvm[l], bm[l]]
+        for l in range(len(h.base)):
+            grads += [dgb[l], dvb[l], bb[l]]
+        return (None, None, dfeat, None, None) + tuple(grads)
+
+
+def color_forward(handle, pts, dirs, feat, samples_per_ray=0):
+    return _ColorFunction.apply(pts, dirs, feat, handle, samples_per_ray, *handle.params())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# NeRF++ background network
+# ---------------------------------------------------------------------------------------------------------------
+class NerfHandle:
+    def __init__(self, module, D, W, d_in, multires, multires_view, skip):
+        self.m = module
+        self.meta = (D, W, d_in, multires, multires_view, skip)
+
+    def params(self):
+        m = self.m
+        ps = []
+        for lin in m.pts_linears:
+            ps += [lin.weight, lin.bias]
+        for lin in (m.views_linears[0], m.feature_linear, m.alpha_linear, m.rgb_linear):
+            ps += [lin.weight, lin.bias]
+        return ps
+
+    def desc(self):
+        m = self.m
+        d = L.NerfDesc()
+        d.D, d.W, d.d_in, d.multires, d.multires_view, d.skip = self.meta
+        for i, lin in enumerate(m.pts_linears):
+            d.pts_w[i], d.pts_b[i] = lin.weight.data_ptr(), lin.bias.data_ptr()
+        d.views_w, d.views_b = m.views_linears[0].weight.data_ptr(), m.views_linears[0].bias.data_ptr()
+        d.feature_w, d.feature_b = m.feature_linear.weight.data_ptr(), m.feature_linear.bias.data_ptr()
+        d.alpha_w, d.alpha_b = m.alpha_linear.weight.data_ptr(), m.alpha_linear.bias.data_ptr()
+        d.rgb_w, d.rgb_b = m.rgb_linear.weight.data_ptr(), m.rgb_linear.bias.data_ptr()
+        return d
+
+
+class _NerfFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, dirs, handle, samples_per_ray, *params):
+        lib = L.lib()
+        _require_cuda(pts, dirs, *params)
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("NeRF parameters must be contiguous float32")
+        pts, dirs = _f32c(pts), _f32c(dirs)
+        P = pts.shape[0]
+        dev = pts.device
+        d = handle.desc()
+        sigma = torch.empty(P, 1, dtype=torch.float32, device=dev)
+        rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        n = lib.nudf_nerf_ctx_floats(ctypes.byref(d), P)
+        buf = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        L.check(lib.nudf_nerf_forward(ctypes.byref(d), L.ptr(pts), L.ptr(dirs), int(samples_per_ray), P, L.ptr(sigma),
+                                      L.ptr(rgb), L.ptr(buf), L.stream_ptr()), "nudf_nerf_forward")
+        ctx.handle, ctx.P = handle, P
+        ctx.versions = tuple(p._version for p in params)
+        ctx.save_for_backward(buf, *params)
+        return sigma, rgb
+
+    @staticmethod
+    def backward(ctx, sigma_bar, rgb_bar):
+        lib = L.lib()
+        buf = ctx.saved_tensors[0]
+        params = ctx.saved_tensors[1:]
+        P = ctx.P
+        dev = buf.device
+        d = ctx.handle.desc()
+        sigma_bar, rgb_bar = _f32c(sigma_bar), _f32c(rgb_bar)
+        n = lib.nudf_nerf_scratch_floats(ctypes.byref(d), P)
+        scratch = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        grads = [torch.empty_like(p) for p in params]
+        L.check(lib.nudf_nerf_backward(ctypes.byref(d), P, L.ptr(sigma_bar), L.ptr(rgb_bar), L.ptr(buf), L.ptr(scratch),
+                                       _ptr_array(grads), L.stream_ptr()), "nudf_nerf_backward")
+        return (None, None, None, None) + tuple(grads)
+
+
+def nerf_forward(handle, pts, dirs, samples_per_ray=0):
+    return _NerfFunction.apply(pts, dirs, handle, samples_per_ray, *handle.params())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ray geometry + compositing
+# ---------------------------------------------------------------------------------------------------------------
+def ray_points(rays_o, rays_d, z_vals, sample_dist):
+    lib = L.lib()
+    rays_o, rays_d, z_vals = _f32c(rays_o), _f32c(rays_d), _f32c(z_vals)
+    _require_cuda(rays_o, rays_d, z_vals)
+    N, S = z_vals.shape
+    dev = z_vals.device
+    pts = torch.empty(N * S, 3, dtype=torch.float32, device=dev)
+    mid = torch.empty(N, S, dtype=torch.float32, device=dev)
+    dists = torch.empty(N, S, dtype=torch.float32, device=dev)
+    L.check(lib.nudf_ray_points(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z_vals), N, S, float(sample_dist), L.ptr(pts),
+                                L.ptr(mid), L.ptr(dists), L.stream_ptr()), "nudf_ray_points")
+    return pts, mid, dists
+
+
+DIAG_KEYS = ["gradient_mag", "true_cos", "vis_prob", "alpha", "alpha_plus", "alpha_minus", "alpha_occ", "raw_occ",
+             "inside_sphere"]
+
+
+def _make_cfg(N, S, O, sample_dist, cos_anneal_ratio, flip_saturation, sparse_scale_factor, use_norm, background_rgb):
+    cfg = L.RenderCfg()
+    cfg.n_rays, cfg.n_samples, cfg.n_outside = N, S, O
+    cfg.sample_dist = float(sample_dist)
+    cfg.has_cos_anneal = 0 if cos_anneal_ratio is None else 1
+    cfg.cos_anneal_ratio = 0.0 if cos_anneal_ratio is None else float(cos_anneal_ratio)
+    cfg.flip_saturation = float(flip_saturation)
+    cfg.sparse_scale_factor = float(sparse_scale_factor)
+    cfg.use_norm_grad_for_cosine = 1 if use_norm else 0
+    cfg.has_background_rgb = 0
+    if background_rgb is not None:
+        cfg.has_background_rgb = 1
+        vals = [float(v) for v in torch.as_tensor(background_rgb).reshape(-1).tolist()]
+        if len(vals) == 1:
+            vals = vals * 3
+        for i in range(3):
+            cfg.background_rgb[i] = vals[i]
+    return cfg
+
+
+class _CompositeFunction(torch.autograd.Function):
+    """differentiable inputs: udf [P], grads [P,3], scb [P,3], sc [P,3], bg_alpha [N,S+O], bg_color [N,S+O,3], heads [3]"""
+
+    @staticmethod
+    def forward(ctx, udf, grads, scb, sc, bg_alpha, bg_color, heads, geom, cfg, want_diag):
+        lib = L.lib()
+        rays_d, pts, mid, dists = geom
+        N, S, O = cfg.n_rays, cfg.n_samples, cfg.n_outside
+        dev = grads.device
+        if udf.dtype != torch.float32:
+            udf = udf.float()
+        ld_udf = udf.stride(0) if udf.dim() >= 1 and udf.numel() > 1 else 1
+        grads, scb, sc, heads = _f32c(grads), _f32c(scb), _f32c(sc), _f32c(heads)
+        bg_alpha, bg_color = _f32c(bg_alpha), _f32c(bg_color)
+        _require_cuda(udf, grads, scb, sc, heads, rays_d, pts, mid, dists)
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        outs = {"color_base": f(N, 3), "color": f(N, 3), "depth": f(N, 1), "normals": f(N, 3), "weights": f(N, S + O),
+                "weight_sum": f(N, 1), "weight_sum_fg_bg": f(N, 1), "ray_sums": f(N, 5)}
+        if want_diag:
+            for k in DIAG_KEYS:
+                outs[k] = f(N, S)
+            outs["gradients_flip"] = f(N, S, 3)
+        ro = L.RenderOut()
+        for k in L.RENDER_OUT_FIELDS:
+            setattr(ro, k, outs[k].data_ptr() if k in outs else None)
+        L.check(lib.nudf_render_composite_forward(ctypes.byref(cfg), L.ptr(heads), L.ptr(rays_d), L.ptr(pts), L.ptr(mid),
+                                                  L.ptr(dists), L.ptr(udf), ld_udf, L.ptr(grads), L.ptr(scb), L.ptr(sc),
+                                                  L.ptr(bg_alpha), L.ptr(bg_color), ctypes.byref(ro), L.stream_ptr()),
+                "nudf_render_composite_forward")
+        ctx.cfg, ctx.geom, ctx.ld_udf = cfg, geom, ld_udf
+        ctx.has_bg = bg_alpha is not None
+        ctx.save_for_backward(udf, grads, scb, sc, bg_alpha, bg_color, heads)
+        diff = ("color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "ray_sums")
+        nondiff = [outs[k] for k in outs if k not in diff]
+        ctx.mark_non_differentiable(*nondiff)
+        ctx.n_extra = len(nondiff)
+        ctx.extra_keys = [k for k in outs if k not in diff]
+        return tuple(outs[k] for k in diff) + tuple(nondiff)
+
+    @staticmethod
+    def backward(ctx, cb_bar, c_bar, depth_bar, ws_bar, wsa_bar, rs_bar, *unused):
+        lib = L.lib()
+        udf, grads, scb, sc, bg_alpha, bg_color, heads = ctx.saved_tensors
+        cfg = ctx.cfg
+        rays_d, pts, mid, dists = ctx.geom
+        N, S, O = cfg.n_rays, cfg.n_samples, cfg.n_outside
+        dev = grads.device
+        P = N * S
+        bar = L.RenderBar()
+        keep = []
+        for name, t in (("color_base", cb_bar), ("color", c_bar), ("depth", depth_bar), ("weight_sum", ws_bar),
+                        ("weight_sum_fg_bg", wsa_bar), ("ray_sums", rs_bar)):
+            t = _f32c(t)
+            keep.append(t)
+            setattr(bar, name, None if t is None else t.data_ptr())
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        udf_bar, grads_bar, scb_bar, sc_bar = f(P), f(P, 3), f(P, 3), f(P, 3)
+        bga_bar = f(N, S + O) if ctx.has_bg else None
+        bgc_bar = f(N, S + O, 3) if ctx.has_bg else None
+        if bgc_bar is not None:
+            bgc_bar[:, :S].zero_()
+        scal = f(N, 3)
+        L.check(lib.nudf_render_composite_backward(ctypes.byref(cfg), L.ptr(heads), L.ptr(rays_d), L.ptr(pts), L.ptr(mid),
+                                                   L.ptr(dists), L.ptr(udf), ctx.ld_udf, L.ptr(grads), L.ptr(scb),
+                                                   L.ptr(sc), L.ptr(bg_alpha), L.ptr(bg_color), ctypes.byref(bar),
+                                                   L.ptr(udf_bar), L.ptr(grads_bar), L.ptr(scb_bar), L.ptr(sc_bar),
+                                                   L.ptr(bga_bar), L.ptr(bgc_bar), L.ptr(scal), L.stream_ptr()),
+                "nudf_render_composite_backward")
+        # udf came in as a (possibly strided) [P] view
+        return (udf_bar.reshape(udf.shape), grads_bar, scb_bar, sc_bar, bga_bar, bgc_bar, scal.sum(dim=0),
+                None, None, None)
+
+
+def composite(udf, grads, scb, sc, bg_alpha, bg_color, heads, geom, cfg, want_diag=True):
+    res = _CompositeFunction.apply(udf, grads, scb, sc, bg_alpha, bg_color, heads, geom, cfg, want_diag)
+    names = ["color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "ray_sums", "normals", "weights"]
+    if want_diag:
+        names += DIAG_KEYS + ["gradients_flip"]
+    return dict(zip(names, res))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sampling
+# ---------------------------------------------------------------------------------------------------------------
+_U_CACHE = {}
+
+
+def _u_lin(m, device):
+    key = (m, str(device))
+    if key not in _U_CACHE:
+        # computed by torch's CPU linspace (the reference's arithmetic, udf_renderer_blending.py:76), then uploaded
+        _U_CACHE[key] = torch.linspace(0.0 + 0.5 / m, 1.0 - 0.5 / m, steps=m, device="cpu").to(device)
+    return _U_CACHE[key]
+
+
+def up_sample(mode, rays_o, rays_d, z, udf, sample_dist, m, inv_s, beta, gamma, return_inds=False):
+    lib = L.lib()
+    rays_o, rays_d, z, udf = _f32c(rays_o), _f32c(rays_d), _f32c(z), _f32c(udf)
+    _require_cuda(rays_o, rays_d, z, udf)
+    N, n = z.shape
+    new_z = torch.empty(N, m, dtype=torch.float32, device=z.device)
+    inds = torch.empty(N, m, dtype=torch.int64, device=z.device) if return_inds else None
+    L.check(lib.nudf_up_sample(int(mode), L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(udf), N, n, m, float(sample_dist),
+                               float(inv_s), float(beta), float(gamma), L.ptr(_u_lin(m, z.device)), L.ptr(new_z),
+                               L.ptr(inds), L.stream_ptr()), "nudf_up_sample")
+    return (new_z, inds) if return_inds else new_z
+
+
+def sample_pdf(bins, weights, m, return_inds=False):
+    lib = L.lib()
+    bins, weights = _f32c(bins), _f32c(weights)
+    _require_cuda(bins, weights)
+    N, n = bins.shape
+    samples = torch.empty(N, m, dtype=torch.float32, device=bins.device)
+    inds = torch.empty(N, m, dtype=torch.int64, device=bins.device) if return_inds else None
+    L.check(lib.nudf_sample_pdf(L.ptr(bins), L.ptr(weights), N, n, m, L.ptr(_u_lin(m, bins.device)), L.ptr(samples),
+                                L.ptr(inds), L.stream_ptr()), "nudf_sample_pdf")
+    return (samples, inds) if return_inds else samples
+
+
+def merge_z(z, new_z, udf=None, new_udf=None):
+    lib = L.lib()
+    z, new_z, udf, new_udf = _f32c(z), _f32c(new_z), _f32c(udf), _f32c(new_udf)
+    N, n = z.shape
+    m = new_z.shape[1]
+    z_out = torch.empty(N, n + m, dtype=torch.float32, device=z.device)
+    udf_out = torch.empty(N, n + m, dtype=torch.float32, device=z.device) if udf is not None else None
+    L.check(lib.nudf_merge_z(L.ptr(z), L.ptr(new_z), L.ptr(udf), L.ptr(new_udf), N, n, m, L.ptr(z_out), L.ptr(udf_out),
+                             L.stream_ptr()), "nudf_merge_z")
+    return z_out, udf_out
+
+
+def points_on_rays(rays_o, rays_d, z):
+    lib = L.lib()
+    rays_o, rays_d, z = _f32c(rays_o), _f32c(rays_d), _f32c(z)
+    N, n = z.shape
+    pts = torch.empty(N * n, 3, dtype=torch.float32, device=z.device)
+    L.check(lib.nudf_points_on_rays(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), N, n, L.ptr(pts), L.stream_ptr()),
+            "nudf_points_on_rays")
+    return pts
+
+
+def outside_points(rays_o, rays_d, z, col0, sample_dist):
+    lib = L.lib()
+    rays_o, rays_d, z = _f32c(rays_o), _f32c(rays_d), _f32c(z)
+    N, n = z.shape
+    m = n - col0
+    pts4 = torch.empty(N * m, 4, dtype=torch.float32, device=z.device)
+    dists = torch.empty(N, m, dtype=torch.float32, device=z.device)
+    L.check(lib.nudf_outside_points(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), N, n, col0, float(sample_dist), L.ptr(pts4),
+                                    L.ptr(dists), L.stream_ptr()), "nudf_outside_points")
+    return pts4, dists
