@@ -28,6 +28,21 @@ const char* nudf_last_error(void);
  * when built with the tensor path).  Small / odd-shaped contractions always use the FFMA engine. */
 int nudf_set_engine(int engine);
 int nudf_get_engine(void);
+/* Which contraction chains may use the tensor engine (bit mask; default 62 = everything but the forward value chain,
+ * whose udf head feeds exp(-25000 u) and needs fp32-grade accuracy): 1 forward value, 2 reverse sweep (grad_x udf),
+ * 4 tangent, 8 backward, 16 weight gradients, 32 colour network, 64 NeRF. */
+int nudf_set_tc_mask(int mask);
+int nudf_get_tc_mask(void);
+/* --- tensor engine building blocks (unit-tested on their own) ---
+ * weight image: bf16 hi/lo split of B(n,k) in UMMA shared-memory order; `transposed` selects B(n,k) = W[k*ldw+n]. */
+int64_t nudf_tc_image_elems(int32_t N, int32_t K);
+int nudf_tc_prepare_weights(const float* W, int64_t ldw, int32_t N, int32_t K, int32_t transposed, uint16_t* img,
+                            void* stream);
+int nudf_dense_forward_tc(const float* X, int64_t ldx, const uint16_t* img, const float* bias, float* Y, int64_t ldy,
+                          int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* dW[n_out, n_in] += dZ[P, n_out]^T X[P, n_in]  (engine 0: fp32 FFMA, 1: tcgen05) */
+int nudf_wgrad(const float* dZ, int64_t ldz, const float* X, int64_t ldx, int32_t n_out, int32_t n_in, int64_t P,
+               float* dW, int64_t ldw, int32_t engine, void* stream);
 /* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 int64_t nudf_launch_count(void);
 /* One fused dense layer Y[M,N] = act(X[M,K] W[N,K]^T + bias), act: 0 none, 1 relu, 2 softplus(beta=100), 3 sigmoid.

@@ -20,6 +20,17 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// NUDF_TC_MASK: which chains may run on the tensor engine (bits: 1 fwd value, 2 reverse sweep, 4 tangent, 8 backward,
+// 16 weight gradients, 32 colour net, 64 NeRF).  Default: everything except the forward value chain.
+static int g_tc_mask = -1;
+int tc_mask() {
+  if (g_tc_mask < 0) {
+    const char* e = getenv("NUDF_TC_MASK");
+    g_tc_mask = e ? atoi(e) : (2 | 4 | 8 | 16 | 32);
+  }
+  return g_tc_mask;
+}
+
 int get_engine() {
   if (g_engine < 0) {
     const char* e = getenv("NUDF_ENGINE");
@@ -43,6 +54,8 @@ int nudf_set_engine(int engine) {
   return 0;
 }
 int nudf_get_engine(void) { return nudf::get_engine(); }
+int nudf_set_tc_mask(int mask) { nudf::g_tc_mask = mask & 127; return 0; }
+int nudf_get_tc_mask(void) { return nudf::tc_mask(); }
 int64_t nudf_launch_count(void) { return (int64_t)__atomic_load_n(&nudf::g_launches, __ATOMIC_RELAXED); }
 
 }  // extern "C"

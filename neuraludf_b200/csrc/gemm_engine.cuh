@@ -1,37 +1,42 @@
 // Engine dispatch: every dense contraction of the hot path goes through gemm_nt / gemm_nn / gemm_tn.
 //   engine 0: exact-fp32 FFMA kernel (gemm_simt.cuh) -- always used for small / odd shapes;
-//   engine 1: tcgen05 3xBF16-split tensor-core kernel (gemm_tc.cuh) for the wide layers, when the caller
-//             supplies the pre-split weight image (TcW) produced at fold time.
+//   engine 1: tcgen05 3xBF16-split tensor-core kernels (gemm_tc.cuh) when the caller supplies the pre-split weight
+//             image built at fold time (gemm_nt / gemm_nn) or for the weight-gradient contraction (gemm_tn).
+// Which chains may use the tensor engine is a bit mask (NUDF_TC_MASK, see tc_mask()): the forward value chain needs
+// fp32-grade accuracy (udf feeds exp(-25000 u) and sigmoid(400 u)), the other chains tolerate the 3xBF16 split.
 #pragma once
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace nudf {
 
-// Pre-split bf16 (hi, lo) weight images in UMMA shared-memory order (see gemm_tc.cuh); null pointers = absent.
-struct TcW {
-  const uint16_t* nt_img;  // operand for X * W^T   (K = in  contiguous)
-  const uint16_t* nn_img;  // operand for dY * W    (K = out contiguous, i.e. W^T image)
-  int n_pad_nt, k_pad_nt, n_pad_nn, k_pad_nn;
-};
+enum TcChain { TC_FWD = 1, TC_REV = 2, TC_TAN = 4, TC_BWD = 8, TC_WGRAD = 16, TC_COLOR = 32, TC_NERF = 64 };
 
 int get_engine();
+int tc_mask();
+static inline bool tc_on(int chain) { return get_engine() == 1 && (tc_mask() & chain) != 0; }
 
 template <class Epi>
 static inline int gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int N, int64_t K,
-                          const Epi& epi, cudaStream_t st, const TcW* tw = nullptr) {
-  (void)tw;
+                          const Epi& epi, cudaStream_t st, const uint16_t* img = nullptr, int chain = 0) {
+  if (img != nullptr && tc_on(chain) && K >= 32 && N >= 16)
+    return tc::gemm_w(A, lda, M, N, (int)K, img, epi, st);
   return gemm_simt<true, true, Epi>(A, lda, W, ldw, M, N, K, epi, st, 1);
 }
 template <class Epi>
 static inline int gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int N, int64_t K,
-                          const Epi& epi, cudaStream_t st, const TcW* tw = nullptr) {
-  (void)tw;
+                          const Epi& epi, cudaStream_t st, const uint16_t* img = nullptr, int chain = 0) {
+  if (img != nullptr && tc_on(chain) && K >= 32 && N >= 16)
+    return tc::gemm_w(A, lda, M, N, (int)K, img, epi, st);
   return gemm_simt<true, false, Epi>(A, lda, W, ldw, M, N, K, epi, st, 1);
 }
 // C[M x N] += A[K x M]^T B[K x N]   (contraction over points)
 template <class Epi>
 static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K,
-                          const Epi& epi, cudaStream_t st, int split_k) {
+                          const Epi& epi, cudaStream_t st, int split_k, int chain = TC_WGRAD) {
+  if (tc_on(chain) && M >= 32 && N >= 32 && K >= 128) {
+    int splits = (int)cdiv(K, 1024);          // 16 slices of 64 points per CTA
+    return tc::gemm_tn(A, lda, B, ldb, M, N, K, epi, st, splits);
+  }
   return gemm_simt<false, false, Epi>(A, lda, B, ldb, M, N, K, epi, st, split_k);
 }
 

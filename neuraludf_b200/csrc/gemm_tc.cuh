@@ -1,0 +1,471 @@
+// tcgen05 tensor-core GEMM engine for sm_100a with an fp32-grade 3xBF16 operand split.
+//
+//   D[128 x N] (fp32, TMEM)  =  sum over K slices of   A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (kind::f16, bf16 inputs)
+//
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the three products keep ~16 mantissa bits of each operand, which is
+// what the parity tolerance needs (plain BF16/TF32 operands do not: SURVEY.md section 0, fact 3).
+//
+// Structure of one CTA (192 threads, one 128-row output tile, 2-stage smem ring, K sliced by 64):
+//   warps 0-3  producers: stage the fp32 A tile from global memory, split it to bf16 hi/lo and write it into the UMMA
+//              K-major SWIZZLE_128B shared-memory layout; after the last slice the same warps run the epilogue
+//              (tcgen05.ld of the accumulator -> fused epilogue functor -> global);
+//   warp 4     MMA issuer: one elected lane issues tcgen05.mma (M=128, N<=256, K=16) and tcgen05.commit;
+//              the warp also owns the TMEM allocation;
+//   warp 5     weight loader: one lane issues cp.async.bulk (TMA engine, UBLKCP) of the pre-split, pre-swizzled weight
+//              slice image (built once per optimiser step by tc_prep_weights_kernel) with mbarrier complete_tx.
+// The weight-gradient variant (gemm_tn) stages BOTH operands from fp32 activations with an on-the-fly transpose
+// (contraction over points) and accumulates split-K partial tiles with red.global.add.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gemm_simt.cuh"
+
+namespace nudf {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 2;
+constexpr int NPROD = 128;
+constexpr int THREADS = 192;
+constexpr int A_HALF_BYTES = BM * BK * 2;   // 16 KB: one of (hi, lo)
+
+__host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
+__host__ __device__ inline int pad64(int k) { return (k + 63) & ~63; }
+// byte offset of element (row, k) inside a [rows x 64] bf16 K-major SWIZZLE_128B tile (tile base 1024-aligned)
+__host__ __device__ inline uint32_t sw128(uint32_t row, uint32_t k) {
+  return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ (row & 7u)) & 7u) << 4) + ((k & 7u) << 1);
+}
+
+// ---- weight image --------------------------------------------------------------------------------------------------
+// For operand B(n, k), n < N, k < K:  n-tiles of 256 rows (last one padded to a multiple of 16), k-slices of 64.
+// Image order: [n_tile][k_slice][hi | lo][tile rows x 128 B, SWIZZLE_128B K-major].  Units below: uint16 elements.
+__host__ __device__ inline int n_tiles(int N) { return (N + 255) / 256; }
+__host__ __device__ inline int tile_rows(int N, int t) { int r = N - 256 * t; return pad16(r < 256 ? r : 256); }
+__host__ __device__ inline int64_t tile_elems(int N, int K, int t) { return (int64_t)(pad64(K) / 64) * 2 * tile_rows(N, t) * 64; }
+__host__ __device__ inline int64_t tile_offset(int N, int K, int t) {
+  int64_t o = 0;
+  for (int i = 0; i < t; ++i) o += tile_elems(N, K, i);
+  return o;
+}
+__host__ __device__ inline int64_t image_elems(int N, int K) { return tile_offset(N, K, n_tiles(N)); }
+
+// transposed == 0: B(n,k) = W[n*ldw + k]   (X W^T)      transposed == 1: B(n,k) = W[k*ldw + n]   (dY W)
+static __global__ void tc_prep_weights_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int transposed,
+                                       uint16_t* __restrict__ img) {
+  const int Kp = pad64(K);
+  const int nt = n_tiles(N);
+  int64_t total = 0;
+  for (int t = 0; t < nt; ++t) total += (int64_t)tile_rows(N, t) * Kp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = idx;
+    int t = 0;
+    while (rem >= (int64_t)tile_rows(N, t) * Kp) { rem -= (int64_t)tile_rows(N, t) * Kp; ++t; }
+    const int rows = tile_rows(N, t);
+    const int nl = (int)(rem / Kp), k = (int)(rem - (int64_t)nl * Kp);
+    const int n = t * 256 + nl;
+    float x = 0.f;
+    if (n < N && k < K) x = transposed ? W[(int64_t)k * ldw + n] : W[(int64_t)n * ldw + k];
+    __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    const int s = k >> 6, kl = k & 63;
+    uint16_t* base = img + tile_offset(N, K, t) + (int64_t)s * 2 * rows * 64;
+    const uint32_t off = sw128((uint32_t)nl, (uint32_t)kl) >> 1;
+    base[off] = __bfloat16_as_ushort(hi);
+    base[(int64_t)rows * 64 + off] = __bfloat16_as_ushort(lo);
+  }
+}
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  while (!mbar_try_wait(addr, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tensor core operand fetch)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor: start address, LBO = 16 B (ignored for swizzled K-major), SBO = 1024 B
+// (8 rows x 128 B), version 1 (sm_100), layout type 2 (SWIZZLE_128B).  See cute/arch/mma_sm100_desc.hpp.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void split4(const float x[4], uint2& hi, uint2& lo) {
+  float h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
+    l[j] = x[j] - h[j];
+  }
+  hi = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+  lo = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+}
+
+// Stage a [128 x 64] slice of row-major fp32 A (K contiguous) as bf16 hi/lo K-major SW128 tiles.
+__device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int k0, int K,
+                                               uint8_t* sa_hi, uint8_t* sa_lo, int tid, bool vec_ok) {
+  const int c = tid & 15;            // float4 chunk along k
+  const int rsub = tid >> 4;         // 0..7
+#pragma unroll 4
+  for (int pass = 0; pass < 16; ++pass) {
+    const int r = pass * 8 + rsub;
+    const int64_t row = m0 + r;
+    const int k = k0 + c * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < M) {
+      const float* p = A + row * lda + k;
+      if (vec_ok && k + 3 < K) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k + j < K) x[j] = p[j];
+      }
+    }
+    uint2 hi, lo;
+    split4(x, hi, lo);
+    const uint32_t off = sw128((uint32_t)r, (uint32_t)(c * 4));
+    *reinterpret_cast<uint2*>(sa_hi + off) = hi;
+    *reinterpret_cast<uint2*>(sa_lo + off) = lo;
+  }
+}
+
+// Stage a [rows x 64] K-major tile of  T(m, k) = X[(k0 + k) * ld + m0 + m]  (on-the-fly transpose; contraction index k
+// runs over points).  Lane mapping chosen so that the 32-bit shared stores of a warp hit 32 distinct banks.
+__device__ __forceinline__ void stage_transposed(const float* __restrict__ X, int64_t ld, int m0, int m_total, int64_t k0,
+                                                 int64_t k_end, int rows, uint8_t* s_hi, uint8_t* s_lo, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int rsub = lane & 7, kq = lane >> 3;
+  for (int rb = warp; rb * 8 < rows; rb += 4) {
+    const int r = rb * 8 + rsub;
+    const int m = m0 + r;
+#pragma unroll 4
+    for (int q = 0; q < 8; ++q) {
+      const int kk = 4 * q + kq;            // pair index: k = 2kk, 2kk+1
+      const int64_t ka = k0 + 2 * kk;
+      float x0 = 0.f, x1 = 0.f;
+      if (m < m_total) {
+        if (ka < k_end) x0 = X[ka * ld + m];
+        if (ka + 1 < k_end) x1 = X[(ka + 1) * ld + m];
+      }
+      float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
+      const uint32_t off = sw128((uint32_t)r, (uint32_t)(2 * kk));
+      *reinterpret_cast<uint32_t*>(s_hi + off) = pack_bf16(h0, h1);
+      *reinterpret_cast<uint32_t*>(s_lo + off) = pack_bf16(x0 - h0, x1 - h1);
+    }
+  }
+}
+
+struct SmemCtl {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full;
+  uint32_t tmem_addr;
+};
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : 256u)); }
+
+// issue the 3-product MMA group for one 64-wide K slice
+__device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                            bool first_slice) {
+#pragma unroll
+  for (int j = 0; j < BK / 16; ++j) {
+    const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
+    const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
+    mma_bf16(tmem_d, dal, dbh, idesc, (first_slice && j == 0) ? 0u : 1u);
+    mma_bf16(tmem_d, dah, dbl, idesc, 1u);
+    mma_bf16(tmem_d, dah, dbh, idesc, 1u);
+  }
+}
+
+template <class Epi>
+__device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int lane, int64_t row, int64_t M, int col_base, int n_pad,
+                                             int n_valid_end, const Epi& epi) {
+  for (int c0 = 0; c0 < n_pad; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    if (row < M) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = col_base + c0 + 4 * j;
+        int nv = n_valid_end - col;
+        if (nv > 0) epi(row, col, &v[4 * j], nv < 4 ? nv : 4);
+      }
+    }
+  }
+  (void)lane;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C[M x N] = epi( A[M x K] * B^T ),  B given as a pre-split weight image.  grid = (ceil(M/128), n_tiles(N)).
+// ---------------------------------------------------------------------------------------------------------------
+template <class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = blockIdx.y;
+  const int rows_b = tile_rows(N, t);                       // padded N of this tile (multiple of 16)
+  const int n_slices = pad64(K) / 64;
+  const uint32_t b_half_bytes = (uint32_t)rows_b * 128u;
+  const uint32_t stage_bytes = 2u * A_HALF_BYTES + 2u * b_half_bytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + STAGES * stage_bytes);
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const uint16_t* img_t = img + tile_offset(N, K, t);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], NPROD + 1); mbar_init(&ctl->empty[s], 1); }
+    mbar_init(&ctl->tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = ctl->tmem_addr;
+
+  if (warp < 4) {
+    const bool vec_ok = ((lda & 3) == 0) && aligned16(A);
+    for (int ks = 0; ks < n_slices; ++ks) {
+      const int s = ks & 1, u = ks >> 1;
+      if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
+      uint8_t* st = smem + s * stage_bytes;
+      stage_a_direct(A, lda, m0, M, ks * BK, K, st, st + A_HALF_BYTES, tid, vec_ok);
+      fence_proxy_async();
+      mbar_arrive(&ctl->full[s]);
+    }
+    // epilogue
+    mbar_wait(&ctl->tmem_full, 0);
+    tcgen05_fence_after();
+    run_epilogue(tmem_base, warp, lane, m0 + tid, M, t * 256, rows_b, N, epi);
+    tcgen05_fence_before();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc((uint32_t)rows_b);
+      for (int ks = 0; ks < n_slices; ++ks) {
+        const int s = ks & 1, u = ks >> 1;
+        mbar_wait(&ctl->full[s], (uint32_t)(u & 1));
+        tcgen05_fence_after();
+        const uint32_t st = smem_u32(smem + s * stage_bytes);
+        issue_slice(tmem_base, st, st + A_HALF_BYTES, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, idesc, ks == 0);
+        mma_commit(&ctl->empty[s]);
+      }
+      mma_commit(&ctl->tmem_full);
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      for (int ks = 0; ks < n_slices; ++ks) {
+        const int s = ks & 1, u = ks >> 1;
+        if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
+        uint8_t* st = smem + s * stage_bytes + 2 * A_HALF_BYTES;
+        mbar_arrive_expect_tx(&ctl->full[s], 2u * b_half_bytes);
+        bulk_g2s(st, img_t + (int64_t)ks * 2 * rows_b * 64, 2u * b_half_bytes, &ctl->full[s]);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols_for(rows_b));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C[M x N] += A[K x M]^T B[K x N]  (weight gradients; contraction over points, split over gridDim.z).
+// grid = (ceil(M/128), ceil(N/256), splits).  Epi is applied to the partial tile (EpiAtomicAdd).
+// ---------------------------------------------------------------------------------------------------------------
+template <class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int M, int N, int64_t K,
+               int64_t k_chunk, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * 256;
+  int rows_b = N - n0; rows_b = pad16(rows_b < 256 ? rows_b : 256);
+  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke = (kb + k_chunk < K) ? kb + k_chunk : K;
+  const int n_slices = (int)((ke - kb + BK - 1) / BK);
+  const uint32_t b_half_bytes = (uint32_t)rows_b * 128u;
+  const uint32_t stage_bytes = 2u * A_HALF_BYTES + 2u * b_half_bytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + STAGES * stage_bytes);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], NPROD); mbar_init(&ctl->empty[s], 1); }
+    mbar_init(&ctl->tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = ctl->tmem_addr;
+
+  if (warp < 4) {
+    for (int ks = 0; ks < n_slices; ++ks) {
+      const int s = ks & 1, u = ks >> 1;
+      if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
+      uint8_t* st = smem + s * stage_bytes;
+      const int64_t k0 = kb + (int64_t)ks * BK;
+      stage_transposed(A, lda, m0, M, k0, ke, BM, st, st + A_HALF_BYTES, tid);
+      stage_transposed(B, ldb, n0, N, k0, ke, rows_b, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, tid);
+      fence_proxy_async();
+      mbar_arrive(&ctl->full[s]);
+    }
+    if (n_slices > 0) {
+      mbar_wait(&ctl->tmem_full, 0);
+      tcgen05_fence_after();
+      run_epilogue(tmem_base, warp, lane, (int64_t)m0 + tid, (int64_t)M, n0, rows_b, N, epi);
+      tcgen05_fence_before();
+    }
+  } else if (warp == 4) {
+    if (lane == 0 && n_slices > 0) {
+      const uint32_t idesc = make_idesc((uint32_t)rows_b);
+      for (int ks = 0; ks < n_slices; ++ks) {
+        const int s = ks & 1, u = ks >> 1;
+        mbar_wait(&ctl->full[s], (uint32_t)(u & 1));
+        tcgen05_fence_after();
+        const uint32_t st = smem_u32(smem + s * stage_bytes);
+        issue_slice(tmem_base, st, st + A_HALF_BYTES, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, idesc, ks == 0);
+        mma_commit(&ctl->empty[s]);
+      }
+      mma_commit(&ctl->tmem_full);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols_for(rows_b));
+  }
+}
+
+inline size_t smem_bytes_for(int rows_b) {
+  return (size_t)STAGES * (2 * A_HALF_BYTES + 2 * (size_t)rows_b * 128) + sizeof(SmemCtl) + 1024 + 64;
+}
+
+template <class Epi>
+static inline int gemm_w(const float* A, int64_t lda, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  const int rows_max = tile_rows(N, 0);
+  const size_t smem = smem_bytes_for(rows_max);
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_w_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)cdiv(M, BM), (unsigned)n_tiles(N));
+  gemm_w_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+template <class Epi>
+static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K, const Epi& epi,
+                          cudaStream_t st, int split_k) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int64_t k_chunk = round_up(cdiv(K, split_k < 1 ? 1 : split_k), BK);
+  int splits = (int)cdiv(K, k_chunk);
+  const size_t smem = smem_bytes_for(pad16(N < 256 ? N : 256));
+  static bool attr_set = false;
+  if (!attr_set) {
+    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, 256), (unsigned)splits);
+  gemm_tn_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+static inline int prep_weights(const float* W, int64_t ldw, int N, int K, int transposed, uint16_t* img, cudaStream_t st) {
+  int64_t total = 0;
+  for (int t = 0; t < n_tiles(N); ++t) total += (int64_t)tile_rows(N, t) * pad64(K);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  tc_prep_weights_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K, transposed, img);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace nudf

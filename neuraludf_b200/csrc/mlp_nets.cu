@@ -100,6 +100,7 @@ struct ColorPlan {
   int dims_b[NUDF_MAX_LAYERS + 1], dims_m[NUDF_MAX_LAYERS + 1];
   int64_t wb_off[NUDF_MAX_LAYERS], wm_off[NUDF_MAX_LAYERS], wb_ld[NUDF_MAX_LAYERS], wm_ld[NUDF_MAX_LAYERS], w_total;
   int64_t bb_off[NUDF_MAX_LAYERS], bm_off[NUDF_MAX_LAYERS], b_total;
+  int64_t ib_nt[NUDF_MAX_LAYERS], ib_nn[NUDF_MAX_LAYERS], im_nt[NUDF_MAX_LAYERS], im_nn[NUDF_MAX_LAYERS], img_total;
   int ld_xb, ld_xm, ld_ym, c_cb, c_hid;
 };
 
@@ -127,6 +128,14 @@ static int color_plan(const nudf_color_desc* d, ColorPlan* p) {
     p->bm_off[l] = boff; boff += p->dims_m[l + 1];
   }
   p->w_total = off; p->b_total = boff;
+  int64_t ioff = 0;
+  for (int l = 0; l < p->n_lin; ++l) {
+    p->ib_nt[l] = ioff; ioff += tc::image_elems(p->dims_b[l + 1], p->dims_b[l]);
+    p->ib_nn[l] = ioff; ioff += tc::image_elems(p->dims_b[l], p->dims_b[l + 1]);
+    p->im_nt[l] = ioff; ioff += tc::image_elems(p->dims_m[l + 1], p->dims_m[l]);
+    p->im_nn[l] = ioff; ioff += tc::image_elems(p->dims_m[l], p->dims_m[l + 1]);
+  }
+  p->img_total = round_up(ioff, 8);
   p->ld_xb = (int)round_up(3 + p->F, 4);
   p->ld_xm = (int)round_up(p->dims_m[0], 4);
   p->ld_ym = (int)round_up(p->d_out + p->n_blend, 4);
@@ -221,7 +230,7 @@ int nudf_dense_forward(const float* X, int64_t ldx, const float* W, int64_t ldw,
 int64_t nudf_color_folded_floats(const nudf_color_desc* d) {
   ColorPlan p;
   if (color_plan(d, &p)) return -1;
-  return p.w_total;
+  return p.w_total + p.img_total / 2;
 }
 
 int nudf_color_fold_weights(const nudf_color_desc* d, float* wfold, void* stream) {
@@ -235,6 +244,15 @@ int nudf_color_fold_weights(const nudf_color_desc* d, float* wfold, void* stream
     fold_kernel2<<<p.dims_m[l + 1], 128, 0, st>>>(d->main_g[l], d->main_v[l], p.dims_m[l + 1], p.dims_m[l], p.wm_ld[l],
                                                    wfold + p.wm_off[l]);
     NUDF_LAUNCH_OK();
+  }
+  if (get_engine() == 1) {
+    uint16_t* img = reinterpret_cast<uint16_t*>(wfold + p.w_total);
+    for (int l = 0; l < p.n_lin; ++l) {
+      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l + 1], p.dims_b[l], 0, img + p.ib_nt[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l], p.dims_b[l + 1], 1, img + p.ib_nn[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l + 1], p.dims_m[l], 0, img + p.im_nt[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l], p.dims_m[l + 1], 1, img + p.im_nn[l], st)) return rc;
+    }
   }
   return 0;
 }
@@ -273,6 +291,7 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
   ew_pe_kernel<<<ew_blocks(P, 128), 128, 0, st>>>(dirs, 3, p.Lv, spr, P, xm, p.ld_xm, 0, nullptr, 0, 0);
   NUDF_LAUNCH_OK();
   const int nl = p.n_lin;
+  const uint16_t* cimg = reinterpret_cast<const uint16_t*>(wfold + p.w_total);
   // base stack
   for (int l = 0; l < nl; ++l) {
     const float* X = l == 0 ? xb : (l == nl - 1 ? xm + p.c_hid : ctx + c.hb[l]);
@@ -282,7 +301,8 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     if (l < nl - 2) { e.C = ctx + c.hb[l + 1]; e.ldc = p.H; e.act = ACT_RELU; }
     else if (l == nl - 2) { e.C = xm + p.c_hid; e.ldc = p.ld_xm; e.act = ACT_RELU; }      // x_hidden (fields.py:472-473)
     else { e.C = xm + p.c_cb; e.ldc = p.ld_xm; e.act = ACT_SIGMOID; }                      // color_base (:475-476)
-    if (int rc = gemm_nt(X, ldx, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l + 1], p.dims_b[l], e, st)) return rc;
+    if (int rc = gemm_nt(X, ldx, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l + 1], p.dims_b[l], e, st,
+                         cimg + p.ib_nt[l], TC_COLOR)) return rc;
   }
   if (color_base) {
     ew_copy_cols_kernel<<<ew_blocks(P * p.d_out, 256), 256, 0, st>>>(xm + p.c_cb, p.ld_xm, color_base, p.d_out, 0, p.d_out, P, 1.f);
@@ -296,7 +316,8 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     e.bias = d->main_b[l]; e.post_scale = 1.0f;
     if (l < nl - 1) { e.C = ctx + c.hm[l + 1]; e.ldc = p.H; e.act = ACT_RELU; }
     else { e.C = ctx + c.ym; e.ldc = p.ld_ym; e.act = ACT_NONE; }
-    if (int rc = gemm_nt(X, ldx, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l + 1], p.dims_m[l], e, st)) return rc;
+    if (int rc = gemm_nt(X, ldx, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l + 1], p.dims_m[l], e, st,
+                         cimg + p.im_nt[l], TC_COLOR)) return rc;
   }
   color_head_kernel<<<ew_blocks(P * (p.d_out + p.n_blend), 256), 256, 0, st>>>(ctx + c.ym, p.ld_ym, p.d_out, p.n_blend, P,
                                                                               color, ctx + c.cs, 4, blend);
@@ -320,6 +341,7 @@ int nudf_color_backward(const nudf_color_desc* d, const float* wfold, int64_t P,
   ColorScratch s;
   color_scratch_layout(p, P, &s);
   const int nl = p.n_lin;
+  const uint16_t* cimg = reinterpret_cast<const uint16_t*>(wfold + p.w_total);
   float* xm = ctx + c.xm;
   float* dym = scratch + s.dym;
   sigmoid_head_bwd_kernel<<<ew_blocks(P * p.ld_ym, 256), 256, 0, st>>>(c_bar, p.d_out, nullptr, 0, ctx + c.cs, 4, p.d_out,
@@ -336,10 +358,12 @@ int nudf_color_backward(const nudf_color_desc* d, const float* wfold, int64_t P,
     float* out = scratch + s.buf[flip];
     if (l >= 1) {
       EpiReluBwd e{0, p.H, ctx + c.hm[l], p.H, out, p.H, 0};
-      if (int rc = gemm_nn(dz, ldz, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l], p.dims_m[l + 1], e, st)) return rc;
+      if (int rc = gemm_nn(dz, ldz, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l], p.dims_m[l + 1], e, st,
+                           cimg + p.im_nn[l], TC_COLOR)) return rc;
     } else {
       EpiColorMainIn e{p.c_cb, p.c_hid, p.dims_m[0], scratch + s.dcbx, 4, xm + p.c_hid, p.ld_xm, out, p.H};
-      if (int rc = gemm_nn(dz, ldz, wfold + p.wm_off[0], p.wm_ld[0], P, p.dims_m[0], p.dims_m[1], e, st)) return rc;
+      if (int rc = gemm_nn(dz, ldz, wfold + p.wm_off[0], p.wm_ld[0], P, p.dims_m[0], p.dims_m[1], e, st,
+                           cimg + p.im_nn[0], TC_COLOR)) return rc;
     }
     dz = out; ldz = p.H; flip ^= 1;
   }
@@ -366,11 +390,13 @@ int nudf_color_backward(const nudf_color_desc* d, const float* wfold, int64_t P,
     if (l >= 1) {
       float* out = scratch + s.buf[flip];
       EpiReluBwd e{0, p.H, ctx + c.hb[l], p.H, out, p.H, 0};
-      if (int rc = gemm_nn(dz, ldz, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l], p.dims_b[l + 1], e, st)) return rc;
+      if (int rc = gemm_nn(dz, ldz, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l], p.dims_b[l + 1], e, st,
+                           cimg + p.ib_nn[l], TC_COLOR)) return rc;
       dz = out; flip ^= 1;
     } else if (dfeat) {
       EpiReluBwd e{3, 3 + p.F, nullptr, 0, dfeat, ld_df, 0};
-      if (int rc = gemm_nn(dz, ldz, wfold + p.wb_off[0], p.wb_ld[0], P, p.dims_b[0], p.dims_b[1], e, st)) return rc;
+      if (int rc = gemm_nn(dz, ldz, wfold + p.wb_off[0], p.wb_ld[0], P, p.dims_b[0], p.dims_b[1], e, st,
+                           cimg + p.ib_nn[0], TC_COLOR)) return rc;
     }
   }
   return 0;

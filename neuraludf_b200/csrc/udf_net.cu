@@ -14,6 +14,7 @@ struct UdfPlan {
   int in_dim[NUDF_MAX_LAYERS], out_dim[NUDF_MAX_LAYERS];
   int64_t w_off[NUDF_MAX_LAYERS], w_ld[NUDF_MAX_LAYERS], w_total;
   int64_t b_off[NUDF_MAX_LAYERS], b_total;
+  int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_total;   // uint16 offsets of the bf16 hi/lo weight images
   int pe_ld, y_ld;
   int a_ld[NUDF_MAX_LAYERS];    // ld of A[l] (input of layer l), l >= 1
   int o_ld[NUDF_MAX_LAYERS];    // ld of D[l] / Q[l] (out_dim rounded)
@@ -44,6 +45,12 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
     if (p->o_ld[l] > p->max_ld) p->max_ld = p->o_ld[l];
   }
   p->w_total = off; p->b_total = boff;
+  int64_t ioff = 0;
+  for (int l = 0; l < p->n_lin; ++l) {
+    p->img_nt[l] = ioff; ioff += tc::image_elems(p->out_dim[l], p->in_dim[l]);   // operand of X W^T  (N = out, K = in)
+    p->img_nn[l] = ioff; ioff += tc::image_elems(p->in_dim[l], p->out_dim[l]);   // operand of dY W   (N = in,  K = out)
+  }
+  p->img_total = round_up(ioff, 8);
   NUDF_REQUIRE(p->in_dim[0] == p->d_pe, "in_dim[0] must equal the positional-encoding width");
   NUDF_REQUIRE(p->out_dim[p->n_lin - 1] == p->d_out, "last layer width must equal d_out");
   for (int l = 1; l < p->n_lin; ++l) {
@@ -310,7 +317,17 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
                                                wfold + p.w_off[l]);
     NUDF_LAUNCH_OK();
   }
+  if (get_engine() == 1) {
+    uint16_t* img = reinterpret_cast<uint16_t*>(wfold + p.w_total);
+    for (int l = 0; l < p.n_lin; ++l) {
+      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, img + p.img_nt[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.in_dim[l], p.out_dim[l], 1, img + p.img_nn[l], st)) return rc;
+    }
+  }
   return 0;
+}
+static inline const uint16_t* img_base(const UdfPlan& p, const float* wfold) {
+  return reinterpret_cast<const uint16_t*>(wfold + p.w_total);
 }
 
 static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P,
@@ -327,8 +344,9 @@ static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wf
     int rc;
     if (l < p.n_lin - 1) {
       EpiAct epi{ctx + c.a[l + 1], p.a_ld[l + 1], d->bias[l], ACT_SOFTPLUS100, (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f};
-      rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st);
+      rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st, img_base(p, wfold) + p.img_nt[l], TC_FWD);
     } else {
+      // the last layer always runs on the exact-fp32 engine: its row 0 is the udf head
       EpiAct epi{ctx + c.y, p.y_ld, d->bias[l], ACT_NONE, 1.0f};
       rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st);
     }
@@ -358,12 +376,14 @@ static int reverse_chain(const UdfPlan& p, const float* wfold, const float* pts,
   }
   for (int l = last - 1; l >= 1; --l) {
     EpiRev e = make_rev(l);
-    int rc = gemm_nn(ctx + c.d[l], p.o_ld[l], wfold + p.w_off[l], p.w_ld[l], P, p.in_dim[l], p.out_dim[l], e, st);
+    int rc = gemm_nn(ctx + c.d[l], p.o_ld[l], wfold + p.w_off[l], p.w_ld[l], P, p.in_dim[l], p.out_dim[l], e, st,
+                     img_base(p, wfold) + p.img_nn[l], TC_REV);
     if (rc) return rc;
   }
   {
     EpiRevFinal e{ctx + c.ge, p.pe_ld, p.skip >= 1 ? ctx + c.gpe : nullptr, p.pe_ld};
-    int rc = gemm_nn(ctx + c.d[0], p.o_ld[0], wfold + p.w_off[0], p.w_ld[0], P, p.in_dim[0], p.out_dim[0], e, st);
+    int rc = gemm_nn(ctx + c.d[0], p.o_ld[0], wfold + p.w_off[0], p.w_ld[0], P, p.in_dim[0], p.out_dim[0], e, st,
+                     img_base(p, wfold) + p.img_nn[0], TC_REV);
     if (rc) return rc;
   }
   pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad);
@@ -380,7 +400,7 @@ extern "C" {
 int64_t nudf_udf_folded_floats(const nudf_udf_desc* d) {
   UdfPlan p;
   if (make_plan(d, &p)) return -1;
-  return p.w_total;
+  return p.w_total + p.img_total / 2;   // fp32 folded weights, then the bf16 hi/lo images (2 per float)
 }
 
 int nudf_udf_fold_weights(const nudf_udf_desc* d, float* wfold, void* stream) {
@@ -481,7 +501,8 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
       et.D = ctx + c.d[l]; et.ldd = p.o_ld[l];
       et.Q = scratch + s.q[l]; et.ldq = p.o_ld[l];
       et.AdotNext = nxt; et.ldn = ld_nxt; et.post_scale = (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
-      if (int rc = gemm_nt(adot, ld_adot, wfold + p.w_off[l], p.w_ld[l], P, p.out_dim[l], p.in_dim[l], et, st))
+      if (int rc = gemm_nt(adot, ld_adot, wfold + p.w_off[l], p.w_ld[l], P, p.out_dim[l], p.in_dim[l], et, st,
+                           img_base(p, wfold) + p.img_nt[l], TC_TAN))
         return rc;
       if (l + 1 == p.skip) {
         copy_cols_kernel<<<nblk(P * p.d_pe, 256), 256, 0, st>>>(edot, p.pe_ld, nxt, ld_nxt, p.out_dim[l], p.d_pe, P,
@@ -510,7 +531,8 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
     eb.n_main = p.out_dim[last - 1]; eb.post_scale = (last == p.skip) ? NUDF_SQRT1_2 : 1.0f;
     eb.Anext = ctx + c.a[last]; eb.lda = p.a_ld[last]; eb.a_unscale = (last == p.skip) ? 1.41421356237309504880f : 1.0f;
     eb.QZ = scratch + s.q[last - 1]; eb.ldq = p.o_ld[last - 1];
-    if (int rc = gemm_nn(zl, p.y_ld, wfold + p.w_off[last], p.w_ld[last], P, p.in_dim[last], p.out_dim[last], eb, st))
+    if (int rc = gemm_nn(zl, p.y_ld, wfold + p.w_off[last], p.w_ld[last], P, p.in_dim[last], p.out_dim[last], eb, st,
+                         img_base(p, wfold) + p.img_nn[last], TC_BWD))
       return rc;
   }
   for (int l = last - 1; l >= 0; --l) {
@@ -525,7 +547,8 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
       eb.n_main = p.out_dim[l - 1]; eb.post_scale = (l == p.skip) ? NUDF_SQRT1_2 : 1.0f;
       eb.Anext = ctx + c.a[l]; eb.lda = p.a_ld[l]; eb.a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
       eb.QZ = scratch + s.q[l - 1]; eb.ldq = p.o_ld[l - 1];
-      if (int rc = gemm_nn(zb, p.o_ld[l], wfold + p.w_off[l], p.w_ld[l], P, p.in_dim[l], p.out_dim[l], eb, st))
+      if (int rc = gemm_nn(zb, p.o_ld[l], wfold + p.w_off[l], p.w_ld[l], P, p.in_dim[l], p.out_dim[l], eb, st,
+                           img_base(p, wfold) + p.img_nn[l], TC_BWD))
         return rc;
     }
   }

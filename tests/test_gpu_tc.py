@@ -1,0 +1,130 @@
+"""GPU unit tests of the tcgen05 (3xBF16 split) GEMM engine against fp64 matmuls, and end-to-end accuracy of the
+renderer with the tensor engine enabled on the chains selected by the default mask."""
+import ctypes
+
+import pytest
+import torch
+
+from tests.gpu_util import build_modules, err_inf, parity, report, scale_inf
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _lib():
+    from neuraludf_b200 import _lib as L
+    return L, L.lib()
+
+
+def _image(W, N, K, transposed):
+    L, lib = _lib()
+    n = lib.nudf_tc_image_elems(N, K)
+    img = torch.zeros(n, dtype=torch.int16, device=DEV)
+    L.check(lib.nudf_tc_prepare_weights(L.ptr(W), W.stride(0), N, K, transposed, L.ptr(img), L.stream_ptr()), "prep")
+    return img
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (300, 256, 256), (1000, 217, 256), (130, 128, 158), (128, 16, 39),
+                                   (515, 257, 256), (4096, 256, 259), (77, 128, 64)])
+def test_dense_forward_tc_vs_fp64(M, N, K):
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn(M, K, generator=g, dtype=torch.float64)
+    W = torch.randn(N, K, generator=g, dtype=torch.float64) / K ** 0.5
+    b = torch.randn(N, generator=g, dtype=torch.float64)
+    ref = X @ W.t() + b
+    Xd, Wd, bd = X.float().to(DEV).contiguous(), W.float().to(DEV).contiguous(), b.float().to(DEV)
+    img = _image(Wd, N, K, 0)
+    Y = torch.full((M, N), float("nan"), device=DEV)
+    L.check(lib.nudf_dense_forward_tc(L.ptr(Xd), K, L.ptr(img), L.ptr(bd), L.ptr(Y), N, M, N, K, 0, L.stream_ptr()), "dense_tc")
+    torch.cuda.synchronize()
+    e = err_inf(Y, ref) / scale_inf(ref)
+    # fp32 engine for comparison
+    Y0 = torch.empty(M, N, device=DEV)
+    L.check(lib.nudf_dense_forward(L.ptr(Xd), K, L.ptr(Wd), K, L.ptr(bd), L.ptr(Y0), N, M, N, K, 0, L.stream_ptr()), "dense")
+    e0 = err_inf(Y0, ref) / scale_inf(ref)
+    report("tc.dense[%d,%d,%d]" % (M, N, K), rel_tc=e, rel_fp32=e0)
+    assert torch.isfinite(Y).all()
+    assert e < 5e-5, e
+    # transposed image: Y2 = X2 @ W  (X2 [M,N], contraction over N)
+    X2 = torch.randn(M, N, generator=g, dtype=torch.float64)
+    ref2 = X2 @ W
+    img2 = _image(Wd, K, N, 1)
+    Y2 = torch.full((M, K), float("nan"), device=DEV)
+    X2d = X2.float().to(DEV).contiguous()
+    L.check(lib.nudf_dense_forward_tc(L.ptr(X2d), N, L.ptr(img2), None, L.ptr(Y2), K, M, K, N, 0, L.stream_ptr()), "dense_tc_nn")
+    e2 = err_inf(Y2, ref2) / scale_inf(ref2)
+    report("tc.dense_nn[%d,%d,%d]" % (M, N, K), rel_tc=e2)
+    assert e2 < 5e-5, e2
+
+
+@pytest.mark.parametrize("P,n_out,n_in", [(1024, 256, 256), (5000, 217, 256), (3000, 128, 259), (700, 257, 256), (4096, 256, 39)])
+def test_wgrad_tc_vs_fp64(P, n_out, n_in):
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(P + n_out)
+    dZ = torch.randn(P, n_out, generator=g, dtype=torch.float64)
+    X = torch.randn(P, n_in, generator=g, dtype=torch.float64)
+    ref = dZ.t() @ X
+    dZd, Xd = dZ.float().to(DEV).contiguous(), X.float().to(DEV).contiguous()
+    for engine in (1, 0):
+        dW = torch.zeros(n_out, n_in, device=DEV)
+        L.check(lib.nudf_wgrad(L.ptr(dZd), n_out, L.ptr(Xd), n_in, n_out, n_in, P, L.ptr(dW), n_in, engine, L.stream_ptr()), "wgrad")
+        e = err_inf(dW, ref) / scale_inf(ref)
+        report("tc.wgrad[%d,%d,%d].engine%d" % (P, n_out, n_in, engine), rel=e)
+        assert e < 5e-5, (engine, e)
+
+
+@pytest.mark.parametrize("mask", [0, 2, 62, 63])
+def test_render_core_accuracy_by_tc_mask(golden, mask):
+    """How far each choice of tensor-engine chains moves render_core from the fp64 reference (reported; the default
+    mask must stay within the parity bounds, the all-chains mask 63 is informational)."""
+    from neuraludf_b200.models.udf_renderer_blending import UDFRendererBlending
+    L, lib = _lib()
+    old_engine, old_mask = lib.nudf_get_engine(), lib.nudf_get_tc_mask()
+    lib.nudf_set_engine(1)
+    lib.nudf_set_tc_mask(mask)
+    try:
+        g = golden
+        udf, col, nerf, var, beta = build_modules(g, DEV)
+        ren = UDFRendererBlending(nerf, udf, var, col, beta, n_samples=64, n_importance=0, n_outside=0, up_sample_steps=1,
+                                  perturb=0.0)
+        o, d = g.t("rays_o").to(DEV), g.t("rays_d").to(DEV)
+        near, far = g.t("near").to(DEV), g.t("far").to(DEV)
+        S = 128
+        z = (near + (far - near) * torch.linspace(0.0, 1.0, S, device=DEV)[None, :]).contiguous()
+        sd = ((far - near) / S).mean().item()
+        ret = ren.render_core(o, d, z, sd, udf, var, col, beta_network=beta, cos_anneal_ratio=0.5, flip_saturation=0.3)
+        tgt = torch.full((64, 3), 0.4, device=DEV)
+        loss = ((ret["color"] - tgt).abs().mean() + 0.01 * (ret["color_base"] - tgt).abs().mean()
+                + 0.1 * ret["gradient_error"] + 1e-3 * ret["sparse_error"] + 0.05 * ret["gradient_error_near_surface"]
+                + 0.1 * ((ret["weight_sum"][:, 0] - 0.5) ** 2).mean())
+        loss.backward()
+        from oracle.make_golden import GRAD_STRIDE
+        stats = {}
+        for k in ("udf", "gradients", "color", "color_base", "depth", "weights", "alpha", "sparse_error", "gradient_error"):
+            r64, r32 = g.t("rc_%s_f64" % k), g.t("rc_%s_f32" % k)
+            stats[k] = err_inf(ret[k].reshape(r64.shape), r64) / scale_inf(r64)
+            stats[k + "_refnoise"] = err_inf(r32, r64) / scale_inf(r64)
+        worst = 0.0
+        for mn, m in (("udf", udf), ("color", col)):
+            for pn, p in m.named_parameters():
+                key = "rc_grad.%s.%s_f64" % (mn, pn)
+                ref = g.t(key) if g.has(key) else g.t(key + "_sub")
+                new = p.grad.cpu() if g.has(key) else p.grad.reshape(-1)[::GRAD_STRIDE].cpu()
+                worst = max(worst, err_inf(new, ref) / scale_inf(ref))
+        stats["dparam_worst"] = worst
+        report("tc.render_core.mask%d" % mask, **stats)
+        assert all(v == v for v in stats.values())
+        if mask in (0, 2, 62):
+            assert stats["dparam_worst"] < 5e-3
+            for k in ("color", "depth", "weights", "alpha"):
+                assert stats[k] <= max(2e-4, 2.5 * stats[k + "_refnoise"]), (k, stats[k])
+    finally:
+        lib.nudf_set_engine(old_engine)
+        lib.nudf_set_tc_mask(old_mask)
