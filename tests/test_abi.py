@@ -79,3 +79,15 @@ def test_golden_scene_loads_into_modules(golden):
     from tests.gpu_util import build_modules
     build_modules(golden, device="cpu")
     build_modules(golden, device="cpu", udf_name="udf_small")
+
+
+def test_launcher_shadows_the_reference_module_names():
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from neuraludf_b200.launch import install_shadow_modules; "
+            "install_shadow_modules(); from models.fields import UDFNetwork, ResidualRenderingNetwork, NeRF, "
+            "SingleVarianceNetwork, BetaNetwork, SDFNetwork; from models.udf_renderer_blending import "
+            "UDFRendererBlending, extract_fields, extract_gradient_fields, sample_pdf; from models.embedder import "
+            "get_embedder; import models.fields as f; assert 'neuraludf_b200' in f.__file__; print('ok')" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
