@@ -197,30 +197,45 @@ def run_ours(args):
         pk = peaks()
         samples = world * N_RAYS * N_SAMPLES * args.steps
         value = samples / (ms * 1e-3)
-        # ---- dominant kernel alone: one 256x256 dense layer (softplus epilogue) over the step's 65 536 points ----
+        # ---- dominant kernels alone: one 256x256 dense layer (softplus epilogue) over the step's 65 536 points, on each
+        #      engine, and the matching weight-gradient contraction; L2 flushed between timed launches ----
+        import ctypes
         P = N_RAYS * N_SAMPLES
         X = torch.randn(P, 256, device=dev) * 0.1
         W = torch.randn(256, 256, device=dev) * 0.06
         b = torch.zeros(256, device=dev)
         Y = torch.empty(P, 256, device=dev)
+        dW = torch.zeros(256, 256, device=dev)
         flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-        st = torch.cuda.current_stream().cuda_stream
-        import ctypes
-        call = lambda: lib.nudf_dense_forward(_lib.ptr(X), 256, _lib.ptr(W), 256, _lib.ptr(b), _lib.ptr(Y), 256, P, 256,
-                                               256, 2, ctypes.c_void_p(st))
-        for _ in range(3):
-            call()
-        tk = 0.0
-        reps = 10
-        for _ in range(reps):
-            flush.zero_()                              # evict L2 between timed launches
-            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); call(); bb.record()
-            torch.cuda.synchronize()
-            tk += a.elapsed_time(bb)
-        tk /= reps
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        imgs = {}
+        for npl in (2, 3):
+            im = torch.zeros(lib.nudf_tc_image_elems(256, 256, npl), dtype=torch.int16, device=dev)
+            lib.nudf_tc_prepare_weights(_lib.ptr(W), 256, 256, 256, 0, npl, _lib.ptr(im), st)
+            imgs[npl] = im
+        calls = {
+            "dense_fp32_ffma": lambda: lib.nudf_dense_forward(_lib.ptr(X), 256, _lib.ptr(W), 256, _lib.ptr(b), _lib.ptr(Y), 256, P, 256, 256, 2, st),
+            "dense_tcgen05_3xbf16": lambda: lib.nudf_dense_forward_tc(_lib.ptr(X), 256, _lib.ptr(imgs[2]), 2, _lib.ptr(b), _lib.ptr(Y), 256, P, 256, 256, 2, st),
+            "dense_tcgen05_6xbf16": lambda: lib.nudf_dense_forward_tc(_lib.ptr(X), 256, _lib.ptr(imgs[3]), 3, _lib.ptr(b), _lib.ptr(Y), 256, P, 256, 256, 2, st),
+            "wgrad_tcgen05_3xbf16": lambda: lib.nudf_wgrad(_lib.ptr(Y), 256, _lib.ptr(X), 256, 256, 256, P, _lib.ptr(dW), 256, 1, st),
+            "wgrad_fp32_ffma": lambda: lib.nudf_wgrad(_lib.ptr(Y), 256, _lib.ptr(X), 256, 256, 256, P, _lib.ptr(dW), 256, 0, st),
+        }
         kflops = 2.0 * P * 256 * 256
-        ach = kflops / (tk * 1e-3) / 1e12
+        ktimes = {}
+        for name, call in calls.items():
+            for _ in range(3):
+                call()
+            tk = 0.0
+            reps = 10
+            for _ in range(reps):
+                flush.zero_()                          # evict L2 between timed launches
+                a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); call(); bb.record()
+                torch.cuda.synchronize()
+                tk += a.elapsed_time(bb)
+            ktimes[name] = {"us": tk / reps * 1e3, "algorithmic_tflops": kflops / (tk / reps * 1e-3) / 1e12}
+        dom = "dense_tcgen05_3xbf16" if lib.nudf_get_engine() == 1 else "dense_fp32_ffma"
+        ach = ktimes[dom]["algorithmic_tflops"]
         engine = lib.nudf_get_engine()
         cpu = cpu_baseline(steps=2, warmup=1, n_rays=256)
         out = {
@@ -240,7 +255,8 @@ def run_ours(args):
             "e2e": {"value": world * N_RAYS * N_SAMPLES * args.steps / (ms_e2e * 1e-3), "unit": "ray-samples/s",
                     "h2d_bytes_per_step": int((ho.numel() + hd.numel() + hz.numel()) * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "dense 65536x256x256 + bias + softplus epilogue (UDF hidden layer)",
+            "kernels": ktimes,
+            "roofline": {"bound": "tensor", "kernel": dom + ": dense 65536x256x256 + bias + softplus epilogue (UDF hidden layer)",
                          "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
                          "traffic": None, "peak_source": pk["source"] + ", bf16 burst",
                          "note": "algorithmic FLOPs (2MNK); the tensor engine executes 3x that (3xBF16 split)"},

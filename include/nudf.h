@@ -35,11 +35,12 @@ int nudf_set_tc_mask(int mask);
 int nudf_get_tc_mask(void);
 /* --- tensor engine building blocks (unit-tested on their own) ---
  * weight image: bf16 hi/lo split of B(n,k) in UMMA shared-memory order; `transposed` selects B(n,k) = W[k*ldw+n]. */
-int64_t nudf_tc_image_elems(int32_t N, int32_t K);
-int nudf_tc_prepare_weights(const float* W, int64_t ldw, int32_t N, int32_t K, int32_t transposed, uint16_t* img,
-                            void* stream);
-int nudf_dense_forward_tc(const float* X, int64_t ldx, const uint16_t* img, const float* bias, float* Y, int64_t ldy,
-                          int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* planes: 2 = hi/lo (3 products, ~4e-6 vs fp64), 3 = hi/mid/lo (6 products, fp32-grade; used by the value chain) */
+int64_t nudf_tc_image_elems(int32_t N, int32_t K, int32_t planes);
+int nudf_tc_prepare_weights(const float* W, int64_t ldw, int32_t N, int32_t K, int32_t transposed, int32_t planes,
+                            uint16_t* img, void* stream);
+int nudf_dense_forward_tc(const float* X, int64_t ldx, const uint16_t* img, int32_t planes, const float* bias, float* Y,
+                          int64_t ldy, int64_t M, int32_t N, int32_t K, int32_t act, void* stream);
 /* dW[n_out, n_in] += dZ[P, n_out]^T X[P, n_in]  (engine 0: fp32 FFMA, 1: tcgen05) */
 int nudf_wgrad(const float* dZ, int64_t ldz, const float* X, int64_t ldx, int32_t n_out, int32_t n_in, int64_t P,
                float* dW, int64_t ldw, int32_t engine, void* stream);

@@ -69,11 +69,12 @@ _SIGNATURES = {
     "nudf_launch_count": (ctypes.c_int64, []),
     "nudf_set_tc_mask": (ctypes.c_int, [ctypes.c_int]),
     "nudf_get_tc_mask": (ctypes.c_int, []),
-    "nudf_tc_image_elems": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32]),
+    "nudf_tc_image_elems": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "nudf_tc_prepare_weights": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
-                                               c_void_p, c_void_p]),
-    "nudf_dense_forward_tc": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p, ctypes.c_int64,
-                                             ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_void_p]),
+                                               ctypes.c_int32, c_void_p, c_void_p]),
+    "nudf_dense_forward_tc": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int32, c_void_p, c_void_p,
+                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                             c_void_p]),
     "nudf_wgrad": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                   ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int32, c_void_p]),
     "nudf_dense_forward": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p, c_void_p,

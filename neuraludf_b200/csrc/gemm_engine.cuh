@@ -17,16 +17,16 @@ static inline bool tc_on(int chain) { return get_engine() == 1 && (tc_mask() & c
 
 template <class Epi>
 static inline int gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int N, int64_t K,
-                          const Epi& epi, cudaStream_t st, const uint16_t* img = nullptr, int chain = 0) {
+                          const Epi& epi, cudaStream_t st, const uint16_t* img = nullptr, int chain = 0, int planes = 2) {
   if (img != nullptr && tc_on(chain) && K >= 32 && N >= 16)
-    return tc::gemm_w(A, lda, M, N, (int)K, img, epi, st);
+    return planes == 3 ? tc::gemm_w<3>(A, lda, M, N, (int)K, img, epi, st) : tc::gemm_w<2>(A, lda, M, N, (int)K, img, epi, st);
   return gemm_simt<true, true, Epi>(A, lda, W, ldw, M, N, K, epi, st, 1);
 }
 template <class Epi>
 static inline int gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int N, int64_t K,
                           const Epi& epi, cudaStream_t st, const uint16_t* img = nullptr, int chain = 0) {
   if (img != nullptr && tc_on(chain) && K >= 32 && N >= 16)
-    return tc::gemm_w(A, lda, M, N, (int)K, img, epi, st);
+    return tc::gemm_w<2>(A, lda, M, N, (int)K, img, epi, st);
   return gemm_simt<true, false, Epi>(A, lda, W, ldw, M, N, K, epi, st, 1);
 }
 // C[M x N] += A[K x M]^T B[K x N]   (contraction over points)

@@ -15,33 +15,32 @@ namespace nudf {
 
 constexpr int GS_BM = 128, GS_BN = 128, GS_BK = 8, GS_PAD = 4, GS_THREADS = 256;
 
+// Tile loads are split into a register fetch (issued before the FFMA block of the current tile, so the global/L2
+// latency overlaps with compute) and a shared-memory store (after the FFMA block).
 template <bool KC>
-__device__ __forceinline__ void gs_load_tile(const float* __restrict__ src, int64_t ld, int64_t mn0, int64_t mn_total,
-                                             int k0, int k_end, float (*dst)[GS_BM + GS_PAD], int tid, bool vec_ok) {
+__device__ __forceinline__ float4 gs_fetch(const float* __restrict__ src, int64_t ld, int64_t mn0, int64_t mn_total, int k0,
+                                           int k_end, int tid, bool vec_ok) {
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
   if (KC) {
-    // K contiguous in memory: each thread fetches 4 consecutive k of one row, stores transposed.
+    // K contiguous in memory: each thread fetches 4 consecutive k of one row.
     int r = tid >> 1;
     int kq = (tid & 1) * 4;
     int64_t row = mn0 + r;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (row < mn_total) {
       const float* p = src + row * ld + (k0 + kq);
       if (vec_ok && (k0 + kq + 3) < k_end) {
-        float4 t = *reinterpret_cast<const float4*>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        t = *reinterpret_cast<const float4*>(p);
       } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (k0 + kq + j < k_end) v[j] = p[j];
+        if (k0 + kq + 0 < k_end) t.x = p[0];
+        if (k0 + kq + 1 < k_end) t.y = p[1];
+        if (k0 + kq + 2 < k_end) t.z = p[2];
+        if (k0 + kq + 3 < k_end) t.w = p[3];
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dst[kq + j][r] = v[j];
   } else {
     // M/N contiguous in memory: each thread fetches 4 consecutive m (or n) of one k.
     int k = tid >> 5;
     int q = (tid & 31) * 4;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k0 + k < k_end) {
       const float* p = src + (int64_t)(k0 + k) * ld + (mn0 + q);
       if (vec_ok && (mn0 + q + 3) < mn_total) {
@@ -53,6 +52,18 @@ __device__ __forceinline__ void gs_load_tile(const float* __restrict__ src, int6
         if (mn0 + q + 3 < mn_total) t.w = p[3];
       }
     }
+  }
+  return t;
+}
+template <bool KC>
+__device__ __forceinline__ void gs_store(float4 t, float (*dst)[GS_BM + GS_PAD], int tid) {
+  if (KC) {
+    int r = tid >> 1;
+    int kq = (tid & 1) * 4;
+    dst[kq + 0][r] = t.x; dst[kq + 1][r] = t.y; dst[kq + 2][r] = t.z; dst[kq + 3][r] = t.w;   // transposed
+  } else {
+    int k = tid >> 5;
+    int q = (tid & 31) * 4;
     *reinterpret_cast<float4*>(&dst[k][q]) = t;
   }
 }
@@ -84,15 +95,17 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 
   const int n_tiles = (k_end + GS_BK - 1) / GS_BK;
   if (n_tiles > 0) {
-    gs_load_tile<A_KC>(Ab, lda, m0, M, 0, k_end, As[0], tid, a_vec);
-    gs_load_tile<B_KC>(Bb, ldb, n0, N, 0, k_end, Bs[0], tid, b_vec);
+    gs_store<A_KC>(gs_fetch<A_KC>(Ab, lda, m0, M, 0, k_end, tid, a_vec), As[0], tid);
+    gs_store<B_KC>(gs_fetch<B_KC>(Bb, ldb, n0, N, 0, k_end, tid, b_vec), Bs[0], tid);
   }
   __syncthreads();
   for (int t = 0; t < n_tiles; ++t) {
     const int cur = t & 1;
-    if (t + 1 < n_tiles) {
-      gs_load_tile<A_KC>(Ab, lda, m0, M, (t + 1) * GS_BK, k_end, As[cur ^ 1], tid, a_vec);
-      gs_load_tile<B_KC>(Bb, ldb, n0, N, (t + 1) * GS_BK, k_end, Bs[cur ^ 1], tid, b_vec);
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+    const bool more = (t + 1 < n_tiles);
+    if (more) {
+      pa = gs_fetch<A_KC>(Ab, lda, m0, M, (t + 1) * GS_BK, k_end, tid, a_vec);
+      pb = gs_fetch<B_KC>(Bb, ldb, n0, N, (t + 1) * GS_BK, k_end, tid, b_vec);
     }
 #pragma unroll
     for (int k = 0; k < GS_BK; ++k) {
@@ -106,6 +119,10 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      gs_store<A_KC>(pa, As[cur ^ 1], tid);
+      gs_store<B_KC>(pb, Bs[cur ^ 1], tid);
     }
     __syncthreads();
   }

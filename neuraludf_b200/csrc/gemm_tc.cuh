@@ -1,6 +1,7 @@
 // tcgen05 tensor-core GEMM engine for sm_100a with an fp32-grade 3xBF16 operand split.
 //
 //   D[128 x N] (fp32, TMEM)  =  sum over K slices of   A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (kind::f16, bf16 inputs)
+//   (2 planes, 3 products, ~4e-6 vs fp64)   or, with 3 planes hi/mid/lo, the 6 products of weight >= 2^-16 (fp32-grade).
 //
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the three products keep ~16 mantissa bits of each operand, which is
 // what the parity tolerance needs (plain BF16/TF32 operands do not: SURVEY.md section 0, fact 3).
@@ -38,41 +39,45 @@ __host__ __device__ inline uint32_t sw128(uint32_t row, uint32_t k) {
 }
 
 // ---- weight image --------------------------------------------------------------------------------------------------
-// For operand B(n, k), n < N, k < K:  n-tiles of 256 rows (last one padded to a multiple of 16), k-slices of 64.
-// Image order: [n_tile][k_slice][hi | lo][tile rows x 128 B, SWIZZLE_128B K-major].  Units below: uint16 elements.
-__host__ __device__ inline int n_tiles(int N) { return (N + 255) / 256; }
-__host__ __device__ inline int tile_rows(int N, int t) { int r = N - 256 * t; return pad16(r < 256 ? r : 256); }
-__host__ __device__ inline int64_t tile_elems(int N, int K, int t) { return (int64_t)(pad64(K) / 64) * 2 * tile_rows(N, t) * 64; }
-__host__ __device__ inline int64_t tile_offset(int N, int K, int t) {
+// For operand B(n, k), n < N, k < K: n-tiles of NT rows (NT = 256 with 2 planes, 128 with 3 planes; the last tile is
+// padded to a multiple of 16), k-slices of 64.  NP planes per element: p0 = bf16(x), p1 = bf16(x - p0),
+// p2 = bf16(x - p0 - p1).  Image order: [n_tile][k_slice][plane][tile rows x 128 B, SWIZZLE_128B K-major].  Units: uint16.
+__host__ __device__ inline int nt_of(int np) { return np == 2 ? 256 : 128; }
+__host__ __device__ inline int n_tiles(int N, int np) { return (N + nt_of(np) - 1) / nt_of(np); }
+__host__ __device__ inline int tile_rows(int N, int t, int np) { int r = N - nt_of(np) * t; return pad16(r < nt_of(np) ? r : nt_of(np)); }
+__host__ __device__ inline int64_t tile_elems(int N, int K, int t, int np) { return (int64_t)(pad64(K) / 64) * np * tile_rows(N, t, np) * 64; }
+__host__ __device__ inline int64_t tile_offset(int N, int K, int t, int np) {
   int64_t o = 0;
-  for (int i = 0; i < t; ++i) o += tile_elems(N, K, i);
+  for (int i = 0; i < t; ++i) o += tile_elems(N, K, i, np);
   return o;
 }
-__host__ __device__ inline int64_t image_elems(int N, int K) { return tile_offset(N, K, n_tiles(N)); }
+__host__ __device__ inline int64_t image_elems(int N, int K, int np) { return tile_offset(N, K, n_tiles(N, np), np); }
 
 // transposed == 0: B(n,k) = W[n*ldw + k]   (X W^T)      transposed == 1: B(n,k) = W[k*ldw + n]   (dY W)
-static __global__ void tc_prep_weights_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int transposed,
-                                       uint16_t* __restrict__ img) {
+static __global__ void tc_prep_weights_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int transposed, int np,
+                                              uint16_t* __restrict__ img) {
   const int Kp = pad64(K);
-  const int nt = n_tiles(N);
+  const int nt = n_tiles(N, np);
   int64_t total = 0;
-  for (int t = 0; t < nt; ++t) total += (int64_t)tile_rows(N, t) * Kp;
+  for (int t = 0; t < nt; ++t) total += (int64_t)tile_rows(N, t, np) * Kp;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t rem = idx;
     int t = 0;
-    while (rem >= (int64_t)tile_rows(N, t) * Kp) { rem -= (int64_t)tile_rows(N, t) * Kp; ++t; }
-    const int rows = tile_rows(N, t);
+    while (rem >= (int64_t)tile_rows(N, t, np) * Kp) { rem -= (int64_t)tile_rows(N, t, np) * Kp; ++t; }
+    const int rows = tile_rows(N, t, np);
     const int nl = (int)(rem / Kp), k = (int)(rem - (int64_t)nl * Kp);
-    const int n = t * 256 + nl;
+    const int n = t * nt_of(np) + nl;
     float x = 0.f;
     if (n < N && k < K) x = transposed ? W[(int64_t)k * ldw + n] : W[(int64_t)n * ldw + k];
-    __nv_bfloat16 hi = __float2bfloat16_rn(x);
-    __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
     const int s = k >> 6, kl = k & 63;
-    uint16_t* base = img + tile_offset(N, K, t) + (int64_t)s * 2 * rows * 64;
+    uint16_t* base = img + tile_offset(N, K, t, np) + (int64_t)s * np * rows * 64;
     const uint32_t off = sw128((uint32_t)nl, (uint32_t)kl) >> 1;
-    base[off] = __bfloat16_as_ushort(hi);
-    base[(int64_t)rows * 64 + off] = __bfloat16_as_ushort(lo);
+    float r = x;
+    for (int p = 0; p < np; ++p) {
+      __nv_bfloat16 h = __float2bfloat16_rn(r);
+      base[(int64_t)p * rows * 64 + off] = __bfloat16_as_ushort(h);
+      r -= __bfloat162float(h);
+    }
   }
 }
 
@@ -164,67 +169,88 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void split4(const float x[4], uint2& hi, uint2& lo) {
-  float h[4], l[4];
+// split 4 consecutive values into NP bf16 planes (packed pairs)
+template <int NP>
+__device__ __forceinline__ void split4(const float x[4], uint2 planes[NP]) {
+  float r[4] = {x[0], x[1], x[2], x[3]};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
-    l[j] = x[j] - h[j];
+  for (int p = 0; p < NP; ++p) {
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16_rn(r[j]));
+      r[j] -= h[j];
+    }
+    planes[p] = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
   }
-  hi = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
-  lo = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
 }
 
-// Stage a [128 x 64] slice of row-major fp32 A (K contiguous) as bf16 hi/lo K-major SW128 tiles.
+// Stage a [128 x 64] slice of row-major fp32 A (K contiguous) as NP bf16 planes in K-major SW128 tiles (16 KB each).
+// All 16 global loads of a thread are issued before the first conversion so that ~32 KB per SM are in flight.
+template <int NP>
 __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int k0, int K,
-                                               uint8_t* sa_hi, uint8_t* sa_lo, int tid, bool vec_ok) {
+                                               uint8_t* sa, int tid, bool vec_ok) {
   const int c = tid & 15;            // float4 chunk along k
   const int rsub = tid >> 4;         // 0..7
-#pragma unroll 4
+  const int k = k0 + c * 4;
+  float4 v[16];
+#pragma unroll
   for (int pass = 0; pass < 16; ++pass) {
-    const int r = pass * 8 + rsub;
-    const int64_t row = m0 + r;
-    const int k = k0 + c * 4;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t row = m0 + pass * 8 + rsub;
+    v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < M) {
       const float* p = A + row * lda + k;
       if (vec_ok && k + 3 < K) {
-        float4 t = *reinterpret_cast<const float4*>(p);
-        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        v[pass] = *reinterpret_cast<const float4*>(p);
       } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (k + j < K) x[j] = p[j];
+        if (k + 0 < K) v[pass].x = p[0];
+        if (k + 1 < K) v[pass].y = p[1];
+        if (k + 2 < K) v[pass].z = p[2];
+        if (k + 3 < K) v[pass].w = p[3];
       }
     }
-    uint2 hi, lo;
-    split4(x, hi, lo);
-    const uint32_t off = sw128((uint32_t)r, (uint32_t)(c * 4));
-    *reinterpret_cast<uint2*>(sa_hi + off) = hi;
-    *reinterpret_cast<uint2*>(sa_lo + off) = lo;
+  }
+#pragma unroll
+  for (int pass = 0; pass < 16; ++pass) {
+    const float x[4] = {v[pass].x, v[pass].y, v[pass].z, v[pass].w};
+    uint2 pl[NP];
+    split4<NP>(x, pl);
+    const uint32_t off = sw128((uint32_t)(pass * 8 + rsub), (uint32_t)(c * 4));
+#pragma unroll
+    for (int p = 0; p < NP; ++p) *reinterpret_cast<uint2*>(sa + p * A_HALF_BYTES + off) = pl[p];
   }
 }
 
-// Stage a [rows x 64] K-major tile of  T(m, k) = X[(k0 + k) * ld + m0 + m]  (on-the-fly transpose; contraction index k
-// runs over points).  Lane mapping chosen so that the 32-bit shared stores of a warp hit 32 distinct banks.
+// Stage a [rows x 64] K-major tile of  T(m, k) = X[(k0 + k) * ld + m0 + m]  as 2 bf16 planes (on-the-fly transpose; the
+// contraction index k runs over points).  One warp iteration covers an 8-row group and all 64 k: lane l owns the k pair
+// (2l, 2l+1) and reads 8 consecutive m (two float4) for each of its two k -- full 32-byte sectors -- and its eight 32-bit
+// shared stores per plane hit 32 distinct banks across the warp.
 __device__ __forceinline__ void stage_transposed(const float* __restrict__ X, int64_t ld, int m0, int m_total, int64_t k0,
-                                                 int64_t k_end, int rows, uint8_t* s_hi, uint8_t* s_lo, int tid) {
+                                                 int64_t k_end, int rows, uint8_t* s_hi, uint8_t* s_lo, int tid, bool vec_ok) {
   const int lane = tid & 31, warp = tid >> 5;
-  const int rsub = lane & 7, kq = lane >> 3;
+  const int64_t ka = k0 + 2 * lane;
   for (int rb = warp; rb * 8 < rows; rb += 4) {
-    const int r = rb * 8 + rsub;
-    const int m = m0 + r;
-#pragma unroll 4
-    for (int q = 0; q < 8; ++q) {
-      const int kk = 4 * q + kq;            // pair index: k = 2kk, 2kk+1
-      const int64_t ka = k0 + 2 * kk;
-      float x0 = 0.f, x1 = 0.f;
-      if (m < m_total) {
-        if (ka < k_end) x0 = X[ka * ld + m];
-        if (ka + 1 < k_end) x1 = X[(ka + 1) * ld + m];
+    const int mbase = m0 + rb * 8;
+    float x[2][8];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const bool k_ok = (ka + kk) < k_end;
+      const float* p = X + (ka + kk) * ld + mbase;
+      if (k_ok && vec_ok && mbase + 7 < m_total) {
+        float4 a = *reinterpret_cast<const float4*>(p);
+        float4 b = *reinterpret_cast<const float4*>(p + 4);
+        x[kk][0] = a.x; x[kk][1] = a.y; x[kk][2] = a.z; x[kk][3] = a.w;
+        x[kk][4] = b.x; x[kk][5] = b.y; x[kk][6] = b.z; x[kk][7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[kk][j] = (k_ok && mbase + j < m_total) ? p[j] : 0.f;
       }
-      float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
-      const uint32_t off = sw128((uint32_t)r, (uint32_t)(2 * kk));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x0 = x[0][j], x1 = x[1][j];
+      const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
+      const uint32_t off = sw128((uint32_t)(rb * 8 + j), (uint32_t)(2 * lane));
       *reinterpret_cast<uint32_t*>(s_hi + off) = pack_bf16(h0, h1);
       *reinterpret_cast<uint32_t*>(s_lo + off) = pack_bf16(x0 - h0, x1 - h1);
     }
@@ -240,21 +266,34 @@ struct SmemCtl {
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : 256u)); }
 
-// issue the 3-product MMA group for one 64-wide K slice
-__device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+// Issue the MMA group of one 64-wide K slice: all plane products whose weight is >= 2^-16 (2 planes: 3 products,
+// 3 planes: 6 products), smallest terms first.  a/b: shared addresses of plane 0; plane p is at +p*stride.
+template <int NP>
+__device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a, uint32_t a_stride, uint32_t b, uint32_t b_stride, uint32_t idesc,
                                             bool first_slice) {
 #pragma unroll
   for (int j = 0; j < BK / 16; ++j) {
-    const uint64_t dah = make_desc(a_hi + j * 32), dal = make_desc(a_lo + j * 32);
-    const uint64_t dbh = make_desc(b_hi + j * 32), dbl = make_desc(b_lo + j * 32);
-    mma_bf16(tmem_d, dal, dbh, idesc, (first_slice && j == 0) ? 0u : 1u);
-    mma_bf16(tmem_d, dah, dbl, idesc, 1u);
-    mma_bf16(tmem_d, dah, dbh, idesc, 1u);
+    uint64_t da[NP], db[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { da[p] = make_desc(a + p * a_stride + j * 32); db[p] = make_desc(b + p * b_stride + j * 32); }
+    const uint32_t acc0 = (first_slice && j == 0) ? 0u : 1u;
+    if (NP == 2) {
+      mma_bf16(tmem_d, da[1], db[0], idesc, acc0);
+      mma_bf16(tmem_d, da[0], db[1], idesc, 1u);
+      mma_bf16(tmem_d, da[0], db[0], idesc, 1u);
+    } else {
+      mma_bf16(tmem_d, da[NP - 1], db[0], idesc, acc0);        // lo * hi
+      mma_bf16(tmem_d, da[0], db[NP - 1], idesc, 1u);          // hi * lo
+      mma_bf16(tmem_d, da[1], db[1], idesc, 1u);               // mid * mid
+      mma_bf16(tmem_d, da[1], db[0], idesc, 1u);               // mid * hi
+      mma_bf16(tmem_d, da[0], db[1], idesc, 1u);               // hi * mid
+      mma_bf16(tmem_d, da[0], db[0], idesc, 1u);               // hi * hi
+    }
   }
 }
 
 template <class Epi>
-__device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int lane, int64_t row, int64_t M, int col_base, int n_pad,
+__device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int64_t row, int64_t M, int col_base, int n_pad,
                                              int n_valid_end, const Epi& epi) {
   for (int c0 = 0; c0 < n_pad; c0 += 32) {
     float v[32];
@@ -268,26 +307,25 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int l
       }
     }
   }
-  (void)lane;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// C[M x N] = epi( A[M x K] * B^T ),  B given as a pre-split weight image.  grid = (ceil(M/128), n_tiles(N)).
+// C[M x N] = epi( A[M x K] * B^T ),  B given as a pre-split NP-plane weight image.  grid = (ceil(M/128), n_tiles(N)).
 // ---------------------------------------------------------------------------------------------------------------
-template <class Epi>
+template <int NP, class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = blockIdx.y;
-  const int rows_b = tile_rows(N, t);                       // padded N of this tile (multiple of 16)
+  const int rows_b = tile_rows(N, t, NP);                   // padded N of this tile (multiple of 16)
   const int n_slices = pad64(K) / 64;
   const uint32_t b_half_bytes = (uint32_t)rows_b * 128u;
-  const uint32_t stage_bytes = 2u * A_HALF_BYTES + 2u * b_half_bytes;
+  const uint32_t stage_bytes = NP * (uint32_t)A_HALF_BYTES + NP * b_half_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + STAGES * stage_bytes);
   const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const uint16_t* img_t = img + tile_offset(N, K, t);
+  const uint16_t* img_t = img + tile_offset(N, K, t, NP);
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], NPROD + 1); mbar_init(&ctl->empty[s], 1); }
@@ -305,15 +343,14 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
     for (int ks = 0; ks < n_slices; ++ks) {
       const int s = ks & 1, u = ks >> 1;
       if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
-      uint8_t* st = smem + s * stage_bytes;
-      stage_a_direct(A, lda, m0, M, ks * BK, K, st, st + A_HALF_BYTES, tid, vec_ok);
+      stage_a_direct<NP>(A, lda, m0, M, ks * BK, K, smem + s * stage_bytes, tid, vec_ok);
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
     }
     // epilogue
     mbar_wait(&ctl->tmem_full, 0);
     tcgen05_fence_after();
-    run_epilogue(tmem_base, warp, lane, m0 + tid, M, t * 256, rows_b, N, epi);
+    run_epilogue(tmem_base, warp, m0 + tid, M, t * nt_of(NP), rows_b, N, epi);
     tcgen05_fence_before();
   } else if (warp == 4) {
     if (lane == 0) {
@@ -323,7 +360,7 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
         mbar_wait(&ctl->full[s], (uint32_t)(u & 1));
         tcgen05_fence_after();
         const uint32_t st = smem_u32(smem + s * stage_bytes);
-        issue_slice(tmem_base, st, st + A_HALF_BYTES, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, idesc, ks == 0);
+        issue_slice<NP>(tmem_base, st, A_HALF_BYTES, st + NP * A_HALF_BYTES, b_half_bytes, idesc, ks == 0);
         mma_commit(&ctl->empty[s]);
       }
       mma_commit(&ctl->tmem_full);
@@ -334,9 +371,9 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
       for (int ks = 0; ks < n_slices; ++ks) {
         const int s = ks & 1, u = ks >> 1;
         if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
-        uint8_t* st = smem + s * stage_bytes + 2 * A_HALF_BYTES;
-        mbar_arrive_expect_tx(&ctl->full[s], 2u * b_half_bytes);
-        bulk_g2s(st, img_t + (int64_t)ks * 2 * rows_b * 64, 2u * b_half_bytes, &ctl->full[s]);
+        uint8_t* st = smem + s * stage_bytes + NP * A_HALF_BYTES;
+        mbar_arrive_expect_tx(&ctl->full[s], NP * b_half_bytes);
+        bulk_g2s(st, img_t + (int64_t)ks * NP * rows_b * 64, NP * b_half_bytes, &ctl->full[s]);
       }
     }
     __syncwarp();
@@ -381,20 +418,22 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   const uint32_t tmem_base = ctl->tmem_addr;
 
   if (warp < 4) {
+    const bool a_vec = ((lda & 3) == 0) && aligned16(A) && ((m0 & 3) == 0);
+    const bool b_vec = ((ldb & 3) == 0) && aligned16(B);
     for (int ks = 0; ks < n_slices; ++ks) {
       const int s = ks & 1, u = ks >> 1;
       if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
       uint8_t* st = smem + s * stage_bytes;
       const int64_t k0 = kb + (int64_t)ks * BK;
-      stage_transposed(A, lda, m0, M, k0, ke, BM, st, st + A_HALF_BYTES, tid);
-      stage_transposed(B, ldb, n0, N, k0, ke, rows_b, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, tid);
+      stage_transposed(A, lda, m0, M, k0, ke, BM, st, st + A_HALF_BYTES, tid, a_vec);
+      stage_transposed(B, ldb, n0, N, k0, ke, rows_b, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, tid, b_vec);
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
     }
     if (n_slices > 0) {
       mbar_wait(&ctl->tmem_full, 0);
       tcgen05_fence_after();
-      run_epilogue(tmem_base, warp, lane, (int64_t)m0 + tid, (int64_t)M, n0, rows_b, N, epi);
+      run_epilogue(tmem_base, warp, (int64_t)m0 + tid, (int64_t)M, n0, rows_b, N, epi);
       tcgen05_fence_before();
     }
   } else if (warp == 4) {
@@ -405,7 +444,7 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
         mbar_wait(&ctl->full[s], (uint32_t)(u & 1));
         tcgen05_fence_after();
         const uint32_t st = smem_u32(smem + s * stage_bytes);
-        issue_slice(tmem_base, st, st + A_HALF_BYTES, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, idesc, ks == 0);
+        issue_slice<2>(tmem_base, st, A_HALF_BYTES, st + 2 * A_HALF_BYTES, b_half_bytes, idesc, ks == 0);
         mma_commit(&ctl->empty[s]);
       }
       mma_commit(&ctl->tmem_full);
@@ -419,22 +458,21 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   }
 }
 
-inline size_t smem_bytes_for(int rows_b) {
-  return (size_t)STAGES * (2 * A_HALF_BYTES + 2 * (size_t)rows_b * 128) + sizeof(SmemCtl) + 1024 + 64;
+inline size_t smem_bytes_for(int rows_b, int np) {
+  return (size_t)STAGES * ((size_t)np * A_HALF_BYTES + (size_t)np * rows_b * 128) + sizeof(SmemCtl) + 1024 + 64;
 }
 
-template <class Epi>
+template <int NP, class Epi>
 static inline int gemm_w(const float* A, int64_t lda, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
-  const int rows_max = tile_rows(N, 0);
-  const size_t smem = smem_bytes_for(rows_max);
+  const size_t smem = smem_bytes_for(tile_rows(N, 0, NP), NP);
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_w_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_w_kernel<NP, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)cdiv(M, BM), (unsigned)n_tiles(N));
-  gemm_w_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi);
+  dim3 grid((unsigned)cdiv(M, BM), (unsigned)n_tiles(N, NP));
+  gemm_w_kernel<NP, Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi);
   NUDF_LAUNCH_OK();
   return 0;
 }
@@ -445,7 +483,7 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   int64_t k_chunk = round_up(cdiv(K, split_k < 1 ? 1 : split_k), BK);
   int splits = (int)cdiv(K, k_chunk);
-  const size_t smem = smem_bytes_for(pad16(N < 256 ? N : 256));
+  const size_t smem = smem_bytes_for(pad16(N < 256 ? N : 256), 2);
   static bool attr_set = false;
   if (!attr_set) {
     NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -457,12 +495,12 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
   return 0;
 }
 
-static inline int prep_weights(const float* W, int64_t ldw, int N, int K, int transposed, uint16_t* img, cudaStream_t st) {
+static inline int prep_weights(const float* W, int64_t ldw, int N, int K, int transposed, int np, uint16_t* img, cudaStream_t st) {
   int64_t total = 0;
-  for (int t = 0; t < n_tiles(N); ++t) total += (int64_t)tile_rows(N, t) * pad64(K);
+  for (int t = 0; t < n_tiles(N, np); ++t) total += (int64_t)tile_rows(N, t, np) * pad64(K);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
-  tc_prep_weights_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K, transposed, img);
+  tc_prep_weights_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K, transposed, np, img);
   NUDF_LAUNCH_OK();
   return 0;
 }

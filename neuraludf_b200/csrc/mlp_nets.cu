@@ -130,10 +130,10 @@ static int color_plan(const nudf_color_desc* d, ColorPlan* p) {
   p->w_total = off; p->b_total = boff;
   int64_t ioff = 0;
   for (int l = 0; l < p->n_lin; ++l) {
-    p->ib_nt[l] = ioff; ioff += tc::image_elems(p->dims_b[l + 1], p->dims_b[l]);
-    p->ib_nn[l] = ioff; ioff += tc::image_elems(p->dims_b[l], p->dims_b[l + 1]);
-    p->im_nt[l] = ioff; ioff += tc::image_elems(p->dims_m[l + 1], p->dims_m[l]);
-    p->im_nn[l] = ioff; ioff += tc::image_elems(p->dims_m[l], p->dims_m[l + 1]);
+    p->ib_nt[l] = ioff; ioff += tc::image_elems(p->dims_b[l + 1], p->dims_b[l], 2);
+    p->ib_nn[l] = ioff; ioff += tc::image_elems(p->dims_b[l], p->dims_b[l + 1], 2);
+    p->im_nt[l] = ioff; ioff += tc::image_elems(p->dims_m[l + 1], p->dims_m[l], 2);
+    p->im_nn[l] = ioff; ioff += tc::image_elems(p->dims_m[l], p->dims_m[l + 1], 2);
   }
   p->img_total = round_up(ioff, 8);
   p->ld_xb = (int)round_up(3 + p->F, 4);
@@ -248,10 +248,10 @@ int nudf_color_fold_weights(const nudf_color_desc* d, float* wfold, void* stream
   if (get_engine() == 1) {
     uint16_t* img = reinterpret_cast<uint16_t*>(wfold + p.w_total);
     for (int l = 0; l < p.n_lin; ++l) {
-      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l + 1], p.dims_b[l], 0, img + p.ib_nt[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l], p.dims_b[l + 1], 1, img + p.ib_nn[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l + 1], p.dims_m[l], 0, img + p.im_nt[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l], p.dims_m[l + 1], 1, img + p.im_nn[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l + 1], p.dims_b[l], 0, 2, img + p.ib_nt[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l], p.dims_b[l + 1], 1, 2, img + p.ib_nn[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l + 1], p.dims_m[l], 0, 2, img + p.im_nt[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l], p.dims_m[l + 1], 1, 2, img + p.im_nn[l], st)) return rc;
     }
   }
   return 0;

@@ -14,7 +14,7 @@ struct UdfPlan {
   int in_dim[NUDF_MAX_LAYERS], out_dim[NUDF_MAX_LAYERS];
   int64_t w_off[NUDF_MAX_LAYERS], w_ld[NUDF_MAX_LAYERS], w_total;
   int64_t b_off[NUDF_MAX_LAYERS], b_total;
-  int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_total;   // uint16 offsets of the bf16 hi/lo weight images
+  int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_nt3[NUDF_MAX_LAYERS], img_total;   // uint16 offsets of the bf16 hi/lo weight images
   int pe_ld, y_ld;
   int a_ld[NUDF_MAX_LAYERS];    // ld of A[l] (input of layer l), l >= 1
   int o_ld[NUDF_MAX_LAYERS];    // ld of D[l] / Q[l] (out_dim rounded)
@@ -47,8 +47,9 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
   p->w_total = off; p->b_total = boff;
   int64_t ioff = 0;
   for (int l = 0; l < p->n_lin; ++l) {
-    p->img_nt[l] = ioff; ioff += tc::image_elems(p->out_dim[l], p->in_dim[l]);   // operand of X W^T  (N = out, K = in)
-    p->img_nn[l] = ioff; ioff += tc::image_elems(p->in_dim[l], p->out_dim[l]);   // operand of dY W   (N = in,  K = out)
+    p->img_nt[l] = ioff; ioff += tc::image_elems(p->out_dim[l], p->in_dim[l], 2);   // operand of X W^T  (N = out, K = in)
+    p->img_nn[l] = ioff; ioff += tc::image_elems(p->in_dim[l], p->out_dim[l], 2);   // operand of dY W   (N = in,  K = out)
+    p->img_nt3[l] = ioff; ioff += tc::image_elems(p->out_dim[l], p->in_dim[l], 3);  // 3-plane image for the value chain
   }
   p->img_total = round_up(ioff, 8);
   NUDF_REQUIRE(p->in_dim[0] == p->d_pe, "in_dim[0] must equal the positional-encoding width");
@@ -320,8 +321,9 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
   if (get_engine() == 1) {
     uint16_t* img = reinterpret_cast<uint16_t*>(wfold + p.w_total);
     for (int l = 0; l < p.n_lin; ++l) {
-      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, img + p.img_nt[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.in_dim[l], p.out_dim[l], 1, img + p.img_nn[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, 2, img + p.img_nt[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.in_dim[l], p.out_dim[l], 1, 2, img + p.img_nn[l], st)) return rc;
+      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, 3, img + p.img_nt3[l], st)) return rc;
     }
   }
   return 0;
@@ -344,7 +346,7 @@ static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wf
     int rc;
     if (l < p.n_lin - 1) {
       EpiAct epi{ctx + c.a[l + 1], p.a_ld[l + 1], d->bias[l], ACT_SOFTPLUS100, (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f};
-      rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st, img_base(p, wfold) + p.img_nt[l], TC_FWD);
+      rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st, img_base(p, wfold) + p.img_nt3[l], TC_FWD, 3);
     } else {
       // the last layer always runs on the exact-fp32 engine: its row 0 is the udf head
       EpiAct epi{ctx + c.y, p.y_ld, d->bias[l], ACT_NONE, 1.0f};
