@@ -16,15 +16,28 @@
 
 namespace nudf {
 
-// nn.Softplus(beta=100, threshold=20)  (reference models/fields.py:180)
+// nn.Softplus(beta=100, threshold=20)  (reference models/fields.py:180):  z if 100 z > 20 else log1p(exp(100 z))/100.
+// Device code uses the overflow-free form max(z,0) + log(1 + e^{-|100 z|})/100 with the MUFU-based __expf/__logf: the
+// argument of the log is in [1,2], where __logf's absolute error is <= 2^-21.4, i.e. <= 4e-9 after the /100 -- an order
+// of magnitude below fp32 resolution of the O(0.1..1) activations -- at ~1/5 of the instruction count of log1pf(expf()).
 NUDF_HD float softplus100(float z) {
   float bz = 100.0f * z;
+#if defined(__CUDA_ARCH__)
+  float t = __expf(-fabsf(bz));
+  float sp = fmaxf(z, 0.0f) + 0.01f * __logf(1.0f + t);
+  return bz > 20.0f ? z : sp;
+#else
   return bz > 20.0f ? z : log1pf(expf(bz)) * 0.01f;
+#endif
 }
 // sigma(100 z) recovered from a = softplus100(z); exactly 1 in the linear regime (torch's softplus backward).
 NUDF_HD float sig_from_softplus(float a) {
   float ba = 100.0f * a;
+#if defined(__CUDA_ARCH__)
+  return ba > 20.0f ? 1.0f : 1.0f - __expf(-ba);
+#else
   return ba > 20.0f ? 1.0f : -expm1f(-ba);
+#endif
 }
 NUDF_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 NUDF_HD float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }

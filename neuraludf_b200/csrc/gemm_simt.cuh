@@ -15,6 +15,19 @@ namespace nudf {
 
 constexpr int GS_BM = 128, GS_BN = 128, GS_BK = 8, GS_PAD = 4, GS_THREADS = 256;
 
+// Blackwell packed fp32 FMA (FFMA2): two IEEE fp32 FMAs per lane per issue slot -- the way sm_100 reaches its fp32 peak.
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
 // Tile loads are split into a register fetch (issued before the FFMA block of the current tile, so the global/L2
 // latency overlaps with compute) and a shared-memory store (after the FFMA block).
 template <bool KC>
@@ -87,11 +100,11 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   const bool a_vec = ((lda & 3) == 0) && aligned16(Ab) && (A_KC || true);
   const bool b_vec = ((ldb & 3) == 0) && aligned16(Bb);
 
-  float acc[8][8];
+  unsigned long long acc2[8][4];   // acc2[i][jp] = (acc[i][2jp], acc[i][2jp+1])
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
 
   const int n_tiles = (k_end + GS_BK - 1) / GS_BK;
   if (n_tiles > 0) {
@@ -113,12 +126,14 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
       float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
       float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
-      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const unsigned long long bp[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const unsigned long long ap = pack2(a[i], a[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) ffma2(acc2[i][j], ap, bp[j]);
+      }
     }
     if (more) {
       gs_store<A_KC>(pa, As[cur ^ 1], tid);
@@ -136,7 +151,9 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       int col = n0 + jg * 64 + tx * 4;
       int nv = N - col;
       if (nv <= 0) continue;
-      float v[4] = {acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]};
+      float v[4];
+      unpack2(acc2[i][jg * 2 + 0], v[0], v[1]);
+      unpack2(acc2[i][jg * 2 + 1], v[2], v[3]);
       epi(row, col, v, nv < 4 ? nv : 4);
     }
   }

@@ -6,13 +6,14 @@
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the three products keep ~16 mantissa bits of each operand, which is
 // what the parity tolerance needs (plain BF16/TF32 operands do not: SURVEY.md section 0, fact 3).
 //
-// Structure of one CTA (192 threads, one 128-row output tile, 2-stage smem ring, K sliced by 64):
-//   warps 0-3  producers: stage the fp32 A tile from global memory, split it to bf16 hi/lo and write it into the UMMA
+// Structure of one CTA (320 threads, one 128-row output tile, 2-stage smem ring, K sliced by 64):
+//   warps 0-7  producers: stage the fp32 A tile from global memory, split it to bf16 planes and write it into the UMMA
 //              K-major SWIZZLE_128B shared-memory layout; after the last slice the same warps run the epilogue
-//              (tcgen05.ld of the accumulator -> fused epilogue functor -> global);
-//   warp 4     MMA issuer: one elected lane issues tcgen05.mma (M=128, N<=256, K=16) and tcgen05.commit;
+//              (tcgen05.ld of the accumulator -> fused epilogue functor -> global): warp w reads TMEM lane quadrant
+//              w%4 and every second 32-column chunk (w/4);
+//   warp 8     MMA issuer: one elected lane issues tcgen05.mma (M=128, N<=256, K=16) and tcgen05.commit;
 //              the warp also owns the TMEM allocation;
-//   warp 5     weight loader: one lane issues cp.async.bulk (TMA engine, UBLKCP) of the pre-split, pre-swizzled weight
+//   warp 9     weight loader: one lane issues cp.async.bulk (TMA engine, UBLKCP) of the pre-split, pre-swizzled weight
 //              slice image (built once per optimiser step by tc_prep_weights_kernel) with mbarrier complete_tx.
 // The weight-gradient variant (gemm_tn) stages BOTH operands from fp32 activations with an on-the-fly transpose
 // (contraction over points) and accumulates split-K partial tiles with red.global.add.
@@ -27,8 +28,8 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int STAGES = 2;
-constexpr int NPROD = 128;
-constexpr int THREADS = 192;
+constexpr int NPROD = 256;     // producer / epilogue threads (warps 0-7)
+constexpr int THREADS = 320;   // + warp 8 (MMA issuer, TMEM owner) + warp 9 (weight loader)
 constexpr int A_HALF_BYTES = BM * BK * 2;   // 16 KB: one of (hi, lo)
 
 __host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
@@ -186,17 +187,18 @@ __device__ __forceinline__ void split4(const float x[4], uint2 planes[NP]) {
 }
 
 // Stage a [128 x 64] slice of row-major fp32 A (K contiguous) as NP bf16 planes in K-major SW128 tiles (16 KB each).
-// All 16 global loads of a thread are issued before the first conversion so that ~32 KB per SM are in flight.
+// All global loads of a thread are issued before the first conversion so that the whole 32 KB slice is in flight.
 template <int NP>
 __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int k0, int K,
                                                uint8_t* sa, int tid, bool vec_ok) {
   const int c = tid & 15;            // float4 chunk along k
-  const int rsub = tid >> 4;         // 0..7
+  const int rsub = tid >> 4;         // 0..15
   const int k = k0 + c * 4;
-  float4 v[16];
+  constexpr int PASSES = BM * 16 / NPROD;   // 8
+  float4 v[PASSES];
 #pragma unroll
-  for (int pass = 0; pass < 16; ++pass) {
-    const int64_t row = m0 + pass * 8 + rsub;
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const int64_t row = m0 + pass * (NPROD / 16) + rsub;
     v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < M) {
       const float* p = A + row * lda + k;
@@ -211,11 +213,11 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
     }
   }
 #pragma unroll
-  for (int pass = 0; pass < 16; ++pass) {
+  for (int pass = 0; pass < PASSES; ++pass) {
     const float x[4] = {v[pass].x, v[pass].y, v[pass].z, v[pass].w};
     uint2 pl[NP];
     split4<NP>(x, pl);
-    const uint32_t off = sw128((uint32_t)(pass * 8 + rsub), (uint32_t)(c * 4));
+    const uint32_t off = sw128((uint32_t)(pass * (NPROD / 16) + rsub), (uint32_t)(c * 4));
 #pragma unroll
     for (int p = 0; p < NP; ++p) *reinterpret_cast<uint2*>(sa + p * A_HALF_BYTES + off) = pl[p];
   }
@@ -229,7 +231,7 @@ __device__ __forceinline__ void stage_transposed(const float* __restrict__ X, in
                                                  int64_t k_end, int rows, uint8_t* s_hi, uint8_t* s_lo, int tid, bool vec_ok) {
   const int lane = tid & 31, warp = tid >> 5;
   const int64_t ka = k0 + 2 * lane;
-  for (int rb = warp; rb * 8 < rows; rb += 4) {
+  for (int rb = warp; rb * 8 < rows; rb += NPROD / 32) {
     const int mbase = m0 + rb * 8;
     float x[2][8];
 #pragma unroll
@@ -292,12 +294,13 @@ __device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a, uint32_
   }
 }
 
+// warp w (0..7): TMEM lane quadrant w & 3 (rows 32 (w&3) + lane of the tile), 32-column chunks (w >> 2), (w >> 2) + 2, ...
 template <class Epi>
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int64_t row, int64_t M, int col_base, int n_pad,
                                              int n_valid_end, const Epi& epi) {
-  for (int c0 = 0; c0 < n_pad; c0 += 32) {
+  for (int c0 = 32 * (warp >> 2); c0 < n_pad; c0 += 64) {
     float v[32];
-    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
     if (row < M) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -332,13 +335,13 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
     mbar_init(&ctl->tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
+  if (warp == 8) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = ctl->tmem_addr;
 
-  if (warp < 4) {
+  if (warp < 8) {
     const bool vec_ok = ((lda & 3) == 0) && aligned16(A);
     for (int ks = 0; ks < n_slices; ++ks) {
       const int s = ks & 1, u = ks >> 1;
@@ -350,9 +353,9 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
     // epilogue
     mbar_wait(&ctl->tmem_full, 0);
     tcgen05_fence_after();
-    run_epilogue(tmem_base, warp, m0 + tid, M, t * nt_of(NP), rows_b, N, epi);
+    run_epilogue(tmem_base, warp, m0 + (warp & 3) * 32 + lane, M, t * nt_of(NP), rows_b, N, epi);
     tcgen05_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc((uint32_t)rows_b);
       for (int ks = 0; ks < n_slices; ++ks) {
@@ -379,7 +382,7 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, tmem_cols_for(rows_b));
   }
@@ -411,13 +414,13 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
     mbar_init(&ctl->tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
+  if (warp == 8) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = ctl->tmem_addr;
 
-  if (warp < 4) {
+  if (warp < 8) {
     const bool a_vec = ((lda & 3) == 0) && aligned16(A) && ((m0 & 3) == 0);
     const bool b_vec = ((ldb & 3) == 0) && aligned16(B);
     for (int ks = 0; ks < n_slices; ++ks) {
@@ -433,10 +436,10 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
     if (n_slices > 0) {
       mbar_wait(&ctl->tmem_full, 0);
       tcgen05_fence_after();
-      run_epilogue(tmem_base, warp, (int64_t)m0 + tid, (int64_t)M, n0, rows_b, N, epi);
+      run_epilogue(tmem_base, warp, (int64_t)m0 + (warp & 3) * 32 + lane, (int64_t)M, n0, rows_b, N, epi);
       tcgen05_fence_before();
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0 && n_slices > 0) {
       const uint32_t idesc = make_idesc((uint32_t)rows_b);
       for (int ks = 0; ks < n_slices; ++ks) {
@@ -452,7 +455,7 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, tmem_cols_for(rows_b));
   }
