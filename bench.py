@@ -168,6 +168,15 @@ def run_ours(args):
     launches = lib.nudf_launch_count() - l0
     clk = clocks.stop() if clocks else None
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                              "value": world * N_RAYS * N_SAMPLES * args.steps / (ms * 1e-3)}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return None
+
     # ---- end-to-end: host (pinned) inputs, H2D + D2H inside the timed region, through the public module API ----
     ho, hd, hz, _ = rays(seed=rank)
     ho, hd, hz = ho.pin_memory(), hd.pin_memory(), hz.contiguous().pin_memory()
@@ -334,6 +343,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="main timed loop only (for profiler runs): no e2e leg, no "
+                    "single-kernel probes, no CPU baseline; prints a reduced JSON line")
     args = ap.parse_args()
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:

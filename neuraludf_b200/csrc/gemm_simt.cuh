@@ -220,6 +220,14 @@ struct EpiRev {
   float* Dprev; int64_t ldd;
   float* Gpe; int64_t ldg;                             // [P, d_pe] or null
   __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+    if (col + nv <= n_main) {                          // whole group inside the activation block: vector path
+      float a[4], d[4];
+      ld4(Anext, lda, row, col, nv, a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = acc[j] * post_scale * sig_from_softplus(a[j] * a_unscale);
+      st4(Dprev, ldd, row, col, nv, d);
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j >= nv) break;
@@ -276,15 +284,14 @@ struct EpiBwd {
   const float* Anext; int64_t lda; float a_unscale;
   float* QZ; int64_t ldq;
   __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+    if (col >= n_main) return;
+    if (col + nv > n_main) nv = n_main - col;
+    float a[4], q[4];
+    ld4(Anext, lda, row, col, nv, a);
+    ld4(QZ, ldq, row, col, nv, q);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j >= nv) break;
-      int c = col + j;
-      if (c >= n_main) break;
-      float s = sig_from_softplus(Anext[row * lda + c] * a_unscale);
-      float* q = QZ + row * ldq + c;
-      *q = acc[j] * post_scale * s + *q;
-    }
+    for (int j = 0; j < 4; ++j) q[j] = acc[j] * post_scale * sig_from_softplus(a[j] * a_unscale) + q[j];
+    st4(QZ, ldq, row, col, nv, q);
   }
 };
 

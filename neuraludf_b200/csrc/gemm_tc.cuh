@@ -227,34 +227,46 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
 // contraction index k runs over points).  One warp iteration covers an 8-row group and all 64 k: lane l owns the k pair
 // (2l, 2l+1) and reads 8 consecutive m (two float4) for each of its two k -- full 32-byte sectors -- and its eight 32-bit
 // shared stores per plane hit 32 distinct banks across the warp.
+template <int R>   // R row-blocks (8 rows each) per warp are fetched before the first conversion: R * 64 B in flight per lane
 __device__ __forceinline__ void stage_transposed(const float* __restrict__ X, int64_t ld, int m0, int m_total, int64_t k0,
                                                  int64_t k_end, int rows, uint8_t* s_hi, uint8_t* s_lo, int tid, bool vec_ok) {
   const int lane = tid & 31, warp = tid >> 5;
   const int64_t ka = k0 + 2 * lane;
-  for (int rb = warp; rb * 8 < rows; rb += NPROD / 32) {
-    const int mbase = m0 + rb * 8;
-    float x[2][8];
+  constexpr int NW = NPROD / 32;
+  for (int rb0 = warp; rb0 * 8 < rows; rb0 += NW * R) {
+    float x[R][2][8];
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      const bool k_ok = (ka + kk) < k_end;
-      const float* p = X + (ka + kk) * ld + mbase;
-      if (k_ok && vec_ok && mbase + 7 < m_total) {
-        float4 a = *reinterpret_cast<const float4*>(p);
-        float4 b = *reinterpret_cast<const float4*>(p + 4);
-        x[kk][0] = a.x; x[kk][1] = a.y; x[kk][2] = a.z; x[kk][3] = a.w;
-        x[kk][4] = b.x; x[kk][5] = b.y; x[kk][6] = b.z; x[kk][7] = b.w;
-      } else {
+    for (int u = 0; u < R; ++u) {
+      const int rb = rb0 + u * NW;
+      const int mbase = m0 + rb * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[kk][j] = (k_ok && mbase + j < m_total) ? p[j] : 0.f;
+      for (int kk = 0; kk < 2; ++kk) {
+        const bool ok = ((ka + kk) < k_end) && (rb * 8 < rows);
+        const float* p = X + (ka + kk) * ld + mbase;
+        if (ok && vec_ok && mbase + 7 < m_total) {
+          float4 a = *reinterpret_cast<const float4*>(p);
+          float4 b = *reinterpret_cast<const float4*>(p + 4);
+          x[u][kk][0] = a.x; x[u][kk][1] = a.y; x[u][kk][2] = a.z; x[u][kk][3] = a.w;
+          x[u][kk][4] = b.x; x[u][kk][5] = b.y; x[u][kk][6] = b.z; x[u][kk][7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[u][kk][j] = (ok && mbase + j < m_total) ? p[j] : 0.f;
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x0 = x[0][j], x1 = x[1][j];
-      const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
-      const uint32_t off = sw128((uint32_t)(rb * 8 + j), (uint32_t)(2 * lane));
-      *reinterpret_cast<uint32_t*>(s_hi + off) = pack_bf16(h0, h1);
-      *reinterpret_cast<uint32_t*>(s_lo + off) = pack_bf16(x0 - h0, x1 - h1);
+    for (int u = 0; u < R; ++u) {
+      const int rb = rb0 + u * NW;
+      if (rb * 8 < rows) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x0 = x[u][0][j], x1 = x[u][1][j];
+          const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
+          const uint32_t off = sw128((uint32_t)(rb * 8 + j), (uint32_t)(2 * lane));
+          *reinterpret_cast<uint32_t*>(s_hi + off) = pack_bf16(h0, h1);
+          *reinterpret_cast<uint32_t*>(s_lo + off) = pack_bf16(x0 - h0, x1 - h1);
+        }
+      }
     }
   }
 }
@@ -294,21 +306,37 @@ __device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a, uint32_
   }
 }
 
-// warp w (0..7): TMEM lane quadrant w & 3 (rows 32 (w&3) + lane of the tile), 32-column chunks (w >> 2), (w >> 2) + 2, ...
+// Epilogue of warp w (0..7): TMEM lane quadrant w & 3 (tile rows 32 (w&3) .. +31), 32-column chunks (w >> 2), (w >> 2)+2, ...
+// tcgen05.ld hands every lane one ROW (32 consecutive columns); the 32x32 block is transposed through a warp-private,
+// padded shared-memory tile so that each epilogue call covers 4 rows x 32 consecutive columns per warp instruction:
+// the fused epilogues' global loads / stores (activations, saved tensors, outputs) are then fully coalesced float4.
+constexpr int EPI_LD = 36;                       // floats per staged row (32 + 4 pad: conflict-free STS.128 / LDS.128)
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
 template <class Epi>
-__device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int64_t row, int64_t M, int col_base, int n_pad,
-                                             int n_valid_end, const Epi& epi) {
+__device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int lane, int64_t row0, int64_t M, int col_base, int n_pad,
+                                             int n_valid_end, float* stg, const Epi& epi) {
+  const int cq = lane & 7, rsub = lane >> 3;
   for (int c0 = 32 * (warp >> 2); c0 < n_pad; c0 += 64) {
     float v[32];
     tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-    if (row < M) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = col_base + c0 + 4 * j;
-        int nv = n_valid_end - col;
-        if (nv > 0) epi(row, col, &v[4 * j], nv < 4 ? nv : 4);
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    const int col = col_base + c0 + 4 * cq;
+    int nv = n_valid_end - col;
+    nv = nv < 4 ? nv : 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rsub + 4 * i;
+      const float4 t = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * cq);
+      const int64_t row = row0 + r;
+      if (row < M && nv > 0) {
+        const float x[4] = {t.x, t.y, t.z, t.w};
+        epi(row, col, x, nv);
       }
     }
+    __syncwarp();
   }
 }
 
@@ -353,7 +381,8 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
     // epilogue
     mbar_wait(&ctl->tmem_full, 0);
     tcgen05_fence_after();
-    run_epilogue(tmem_base, warp, m0 + (warp & 3) * 32 + lane, M, t * nt_of(NP), rows_b, N, epi);
+    run_epilogue(tmem_base, warp, lane, m0 + (warp & 3) * 32, M, t * nt_of(NP), rows_b, N,
+                 reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi);   // operand stages are free by now
     tcgen05_fence_before();
   } else if (warp == 8) {
     if (lane == 0) {
@@ -428,15 +457,16 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
       if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
       uint8_t* st = smem + s * stage_bytes;
       const int64_t k0 = kb + (int64_t)ks * BK;
-      stage_transposed(A, lda, m0, M, k0, ke, BM, st, st + A_HALF_BYTES, tid, a_vec);
-      stage_transposed(B, ldb, n0, N, k0, ke, rows_b, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, tid, b_vec);
+      stage_transposed<2>(A, lda, m0, M, k0, ke, BM, st, st + A_HALF_BYTES, tid, a_vec);
+      stage_transposed<4>(B, ldb, n0, N, k0, ke, rows_b, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, tid, b_vec);
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
     }
     if (n_slices > 0) {
       mbar_wait(&ctl->tmem_full, 0);
       tcgen05_fence_after();
-      run_epilogue(tmem_base, warp, (int64_t)m0 + (warp & 3) * 32 + lane, (int64_t)M, n0, rows_b, N, epi);
+      run_epilogue(tmem_base, warp, lane, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, rows_b, N,
+                   reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi);
       tcgen05_fence_before();
     }
   } else if (warp == 8) {
