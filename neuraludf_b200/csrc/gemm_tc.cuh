@@ -188,17 +188,17 @@ __device__ __forceinline__ void split4(const float x[4], uint2 planes[NP]) {
 
 // Stage a [128 x 64] slice of row-major fp32 A (K contiguous) as NP bf16 planes in K-major SW128 tiles (16 KB each).
 // All global loads of a thread are issued before the first conversion so that the whole 32 KB slice is in flight.
-template <int NP>
+template <int NP, int NT>   // NT = number of producer threads (128 or 256)
 __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int k0, int K,
                                                uint8_t* sa, int tid, bool vec_ok) {
   const int c = tid & 15;            // float4 chunk along k
-  const int rsub = tid >> 4;         // 0..15
+  const int rsub = tid >> 4;         // 0 .. NT/16-1
   const int k = k0 + c * 4;
-  constexpr int PASSES = BM * 16 / NPROD;   // 8
+  constexpr int PASSES = BM * 16 / NT;
   float4 v[PASSES];
 #pragma unroll
   for (int pass = 0; pass < PASSES; ++pass) {
-    const int64_t row = m0 + pass * (NPROD / 16) + rsub;
+    const int64_t row = m0 + pass * (NT / 16) + rsub;
     v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < M) {
       const float* p = A + row * lda + k;
@@ -217,7 +217,7 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
     const float x[4] = {v[pass].x, v[pass].y, v[pass].z, v[pass].w};
     uint2 pl[NP];
     split4<NP>(x, pl);
-    const uint32_t off = sw128((uint32_t)(pass * (NPROD / 16) + rsub), (uint32_t)(c * 4));
+    const uint32_t off = sw128((uint32_t)(pass * (NT / 16) + rsub), (uint32_t)(c * 4));
 #pragma unroll
     for (int p = 0; p < NP; ++p) *reinterpret_cast<uint2*>(sa + p * A_HALF_BYTES + off) = pl[p];
   }
@@ -313,12 +313,19 @@ __device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a, uint32_
 constexpr int EPI_LD = 36;                       // floats per staged row (32 + 4 pad: conflict-free STS.128 / LDS.128)
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
 template <class Epi>
-__device__ __forceinline__ void run_epilogue(uint32_t tmem_base, int warp, int lane, int64_t row0, int64_t M, int col_base, int n_pad,
-                                             int n_valid_end, float* stg, const Epi& epi) {
+__device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int lane, int chunk0, int chunk_step, int n_acc,
+                                             uint32_t acc_stride, int64_t row0, int64_t M, int col_base, int n_pad, int n_valid_end,
+                                             float* stg, const Epi& epi) {
   const int cq = lane & 7, rsub = lane >> 3;
-  for (int c0 = 32 * (warp >> 2); c0 < n_pad; c0 += 64) {
+  for (int c0 = chunk0; c0 < n_pad; c0 += chunk_step) {
     float v[32];
-    tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+    tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+    for (int a = 1; a < n_acc; ++a) {          // per-slice partial accumulators are summed here with round-to-nearest adds
+      float w[32];
+      tmem_ld32(tmem_acc + a * acc_stride + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, w);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] += w[q];
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -363,7 +370,13 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
     mbar_init(&ctl->tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
+  // 3-plane (fp32-grade) variant: every K slice accumulates into its own TMEM accumulator (up to 4 x 128 columns) and the
+  // epilogue adds them in fp32 with round-to-nearest: the tensor core truncates its fp32 accumulator after every MMA
+  // (measured bias ~ -1e-7 per step), so short accumulation chains keep the systematic error at the FFMA level.
+  const int n_acc = (NP == 3) ? (n_slices < 4 ? n_slices : 4) : 1;
+  const uint32_t acc_cols = tmem_cols_for(rows_b);
+  const uint32_t alloc_cols = (n_acc == 1) ? acc_cols : (n_acc == 2 ? 2 * acc_cols : 512u);
+  if (warp == 8) tmem_alloc(&ctl->tmem_addr, alloc_cols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -374,14 +387,14 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
     for (int ks = 0; ks < n_slices; ++ks) {
       const int s = ks & 1, u = ks >> 1;
       if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
-      stage_a_direct<NP>(A, lda, m0, M, ks * BK, K, smem + s * stage_bytes, tid, vec_ok);
+      stage_a_direct<NP, NPROD>(A, lda, m0, M, ks * BK, K, smem + s * stage_bytes, tid, vec_ok);
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
     }
     // epilogue
     mbar_wait(&ctl->tmem_full, 0);
     tcgen05_fence_after();
-    run_epilogue(tmem_base, warp, lane, m0 + (warp & 3) * 32, M, t * nt_of(NP), rows_b, N,
+    run_epilogue(tmem_base, warp & 3, lane, 32 * (warp >> 2), 64, n_acc, acc_cols, m0 + (warp & 3) * 32, M, t * nt_of(NP), rows_b, N,
                  reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi);   // operand stages are free by now
     tcgen05_fence_before();
   } else if (warp == 8) {
@@ -392,7 +405,8 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
         mbar_wait(&ctl->full[s], (uint32_t)(u & 1));
         tcgen05_fence_after();
         const uint32_t st = smem_u32(smem + s * stage_bytes);
-        issue_slice<NP>(tmem_base, st, A_HALF_BYTES, st + NP * A_HALF_BYTES, b_half_bytes, idesc, ks == 0);
+        issue_slice<NP>(tmem_base + (uint32_t)(ks % n_acc) * acc_cols, st, A_HALF_BYTES, st + NP * A_HALF_BYTES, b_half_bytes, idesc,
+                        ks < n_acc);
         mma_commit(&ctl->empty[s]);
       }
       mma_commit(&ctl->tmem_full);
@@ -413,7 +427,117 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
   __syncthreads();
   if (warp == 8) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols_for(rows_b));
+    tmem_dealloc(tmem_base, alloc_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent 2-plane variant of gemm_w: one CTA per SM loops over 128-row tiles; the TMEM accumulator is double
+// buffered so that the epilogue of tile i (warps 4-7) overlaps the operand staging + MMAs of tile i+1 (warps 0-3, 8, 9).
+// ---------------------------------------------------------------------------------------------------------------
+struct SmemCtlP {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_addr;
+};
+constexpr int PPROD = 128;   // producer threads of the persistent kernel (warps 0-3); warps 4-7 run the epilogue
+
+template <class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = blockIdx.y;
+  const int rows_b = tile_rows(N, t, 2);
+  const int n_slices = pad64(K) / 64;
+  const uint32_t b_half_bytes = (uint32_t)rows_b * 128u;
+  const uint32_t stage_bytes = 2u * A_HALF_BYTES + 2u * b_half_bytes;
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
+  SmemCtlP* ctl = reinterpret_cast<SmemCtlP*>(smem + STAGES * stage_bytes + 4 * EPI_WARP_FLOATS * sizeof(float));
+  const uint16_t* img_t = img + tile_offset(N, K, t, 2);
+  const int64_t n_mtiles = (M + BM - 1) / BM;
+  const uint32_t acc_cols = tmem_cols_for(rows_b);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], PPROD + 1); mbar_init(&ctl->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl->tfull[a], 1); mbar_init(&ctl->tempty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&ctl->tmem_addr, 2 * acc_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = ctl->tmem_addr;
+
+  if (warp < 4) {
+    // ---- A producers ----
+    const bool vec_ok = ((lda & 3) == 0) && aligned16(A);
+    uint32_t cnt = 0;
+    for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+      for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
+        const uint32_t s = cnt & 1u, u = cnt >> 1;
+        if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
+        stage_a_direct<2, PPROD>(A, lda, mt * BM, M, ks * BK, K, smem + s * stage_bytes, tid, vec_ok);
+        fence_proxy_async();
+        mbar_arrive(&ctl->full[s]);
+      }
+    }
+  } else if (warp < 8) {
+    // ---- epilogue ----
+    uint32_t it = 0;
+    for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++it) {
+      const uint32_t a = it & 1u, au = it >> 1;
+      mbar_wait(&ctl->tfull[a], au & 1u);
+      tcgen05_fence_after();
+      run_epilogue(tmem_base + a * acc_cols, warp & 3, lane, 0, 32, 1, 0u, mt * BM + (warp & 3) * 32, M, t * 256, rows_b, N,
+                   epi_stage + (warp & 3) * EPI_WARP_FLOATS, epi);
+      tcgen05_fence_before();
+      mbar_arrive(&ctl->tempty[a]);
+    }
+  } else if (warp == 8) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc((uint32_t)rows_b);
+      uint32_t cnt = 0, it = 0;
+      for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++it) {
+        const uint32_t a = it & 1u, au = it >> 1;
+        if (au > 0) mbar_wait(&ctl->tempty[a], (au - 1) & 1u);
+        tcgen05_fence_after();
+        for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
+          const uint32_t s = cnt & 1u, u = cnt >> 1;
+          mbar_wait(&ctl->full[s], u & 1u);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + s * stage_bytes);
+          issue_slice<2>(tmem_base + a * acc_cols, st, A_HALF_BYTES, st + 2 * A_HALF_BYTES, b_half_bytes, idesc, ks == 0);
+          mma_commit(&ctl->empty[s]);
+        }
+        mma_commit(&ctl->tfull[a]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- weight loader ----
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+        for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
+          const uint32_t s = cnt & 1u, u = cnt >> 1;
+          if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
+          uint8_t* st = smem + s * stage_bytes + 2 * A_HALF_BYTES;
+          mbar_arrive_expect_tx(&ctl->full[s], 2u * b_half_bytes);
+          bulk_g2s(st, img_t + (int64_t)ks * 2 * rows_b * 64, 2u * b_half_bytes, &ctl->full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 2 * acc_cols);
   }
 }
 
@@ -465,7 +589,7 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
     if (n_slices > 0) {
       mbar_wait(&ctl->tmem_full, 0);
       tcgen05_fence_after();
-      run_epilogue(tmem_base, warp, lane, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, rows_b, N,
+      run_epilogue(tmem_base, warp & 3, lane, 32 * (warp >> 2), 64, 1, 0u, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, rows_b, N,
                    reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi);
       tcgen05_fence_before();
     }
@@ -495,9 +619,39 @@ inline size_t smem_bytes_for(int rows_b, int np) {
   return (size_t)STAGES * ((size_t)np * A_HALF_BYTES + (size_t)np * rows_b * 128) + sizeof(SmemCtl) + 1024 + 64;
 }
 
+static inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <class Epi>
+static inline int gemm_wp(const float* A, int64_t lda, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
+  const size_t smem = (size_t)STAGES * (2 * A_HALF_BYTES + 2 * (size_t)tile_rows(N, 0, 2) * 128) + 4 * EPI_WARP_FLOATS * sizeof(float) +
+                      sizeof(SmemCtlP) + 1024 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_wp_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int64_t n_mtiles = cdiv(M, BM);
+  const int nt = n_tiles(N, 2);
+  int64_t gx = sm_count() / nt;
+  if (gx < 1) gx = 1;
+  if (gx > n_mtiles) gx = n_mtiles;
+  dim3 grid((unsigned)gx, (unsigned)nt);
+  gemm_wp_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
 template <int NP, class Epi>
 static inline int gemm_w(const float* A, int64_t lda, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
+  if (NP == 2 && M > BM) return gemm_wp(A, lda, M, N, K, img, epi, st);
   const size_t smem = smem_bytes_for(tile_rows(N, 0, NP), NP);
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
