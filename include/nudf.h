@@ -44,6 +44,8 @@ int nudf_dense_forward_tc(const float* X, int64_t ldx, const uint16_t* img, int3
 /* dW[n_out, n_in] += dZ[P, n_out]^T X[P, n_in]  (engine 0: fp32 FFMA, 1: tcgen05) */
 int nudf_wgrad(const float* dZ, int64_t ldz, const float* X, int64_t ldx, int32_t n_out, int32_t n_in, int64_t P,
                float* dW, int64_t ldw, int32_t engine, void* stream);
+/* profiling aid: with NUDF_TC_DEBUG & 16 the persistent tensor kernel records clock64() stamps of CTA 0 (4 roles x 256) */
+int nudf_tc_read_trace(long long* host_buf);
 /* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 int64_t nudf_launch_count(void);
 /* One fused dense layer Y[M,N] = act(X[M,K] W[N,K]^T + bias), act: 0 none, 1 relu, 2 softplus(beta=100), 3 sigmoid.

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "nudf_set_engine": (ctypes.c_int, [ctypes.c_int]),
     "nudf_get_engine": (ctypes.c_int, []),
     "nudf_launch_count": (ctypes.c_int64, []),
+    "nudf_tc_read_trace": (ctypes.c_int, [c_void_p]),
     "nudf_set_tc_mask": (ctypes.c_int, [ctypes.c_int]),
     "nudf_get_tc_mask": (ctypes.c_int, []),
     "nudf_tc_image_elems": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),

@@ -31,6 +31,14 @@ int tc_mask() {
   return g_tc_mask;
 }
 
+namespace tc {
+int tc_debug() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NUDF_TC_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+}  // namespace tc
+
 int get_engine() {
   if (g_engine < 0) {
     const char* e = getenv("NUDF_ENGINE");

@@ -185,31 +185,50 @@ __device__ __forceinline__ void st4(float* __restrict__ base, int64_t ld, int64_
   }
 }
 
+// Every epilogue has two phases so that the tensor-engine epilogue can software-pipeline them: load() fetches the
+// auxiliary global data of one (row, 4-column) group into an Aux record (many groups' loads are put in flight first),
+// apply() consumes the accumulator values + Aux and stores.  operator() = load + apply (used by the FFMA kernel).
+#define NUDF_EPI_CALL                                                                                     \
+  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {    \
+    Aux aux;                                                                                              \
+    load(row, col, nv, aux);                                                                              \
+    apply(row, col, acc, nv, aux);                                                                        \
+  }
+
 // C[row, col] = act(acc + bias[col]) * post_scale
 struct EpiAct {
   float* C; int64_t ldc; const float* bias; int act; float post_scale;
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+  struct Aux { float b[4]; };
+  __device__ __forceinline__ void load(int64_t, int col, int nv, Aux& x) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x.b[j] = (bias != nullptr && j < nv) ? bias[col + j] : 0.f;
+  }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float x = acc[j] + ((bias != nullptr && j < nv) ? bias[col + j] : 0.f);
-      if (act == ACT_RELU) x = fmaxf(x, 0.f);
-      else if (act == ACT_SOFTPLUS100) x = softplus100(x);
-      else if (act == ACT_SIGMOID) x = sigmoidf_(x);
-      v[j] = x * post_scale;
+      float t = acc[j] + x.b[j];
+      if (act == ACT_RELU) t = fmaxf(t, 0.f);
+      else if (act == ACT_SOFTPLUS100) t = softplus100(t);
+      else if (act == ACT_SIGMOID) t = sigmoidf_(t);
+      v[j] = t * post_scale;
     }
     st4(C, ldc, row, col, nv, v);
   }
+  NUDF_EPI_CALL
 };
 
 // C[row, col] += acc   (split-K partial sums of weight gradients)
 struct EpiAtomicAdd {
   float* C; int64_t ldc;
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+  struct Aux {};
+  __device__ __forceinline__ void load(int64_t, int, int, Aux&) const {}
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux&) const {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (j < nv) atomicAdd(C + row * ldc + col + j, acc[j]);
   }
+  NUDF_EPI_CALL
 };
 
 // Reverse sweep (grad_x udf): acc = G = d udf / d A[l].  Converts it into D_{l-1} = G * s * sigma(100 z_{l-1});
@@ -219,12 +238,18 @@ struct EpiRev {
   const float* Anext; int64_t lda; float a_unscale;   // stored activation of layer l-1 (= A[l], first n_main cols)
   float* Dprev; int64_t ldd;
   float* Gpe; int64_t ldg;                             // [P, d_pe] or null
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+  struct Aux { float a[4]; };
+  __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
+    int n = n_main - col;
+    n = n < nv ? n : nv;
+    if (n > 0) ld4(Anext, lda, row, col, n, x.a);
+    else { x.a[0] = x.a[1] = x.a[2] = x.a[3] = 0.f; }
+  }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
     if (col + nv <= n_main) {                          // whole group inside the activation block: vector path
-      float a[4], d[4];
-      ld4(Anext, lda, row, col, nv, a);
+      float d[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) d[j] = acc[j] * post_scale * sig_from_softplus(a[j] * a_unscale);
+      for (int j = 0; j < 4; ++j) d[j] = acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale);
       st4(Dprev, ldd, row, col, nv, d);
       return;
     }
@@ -233,28 +258,28 @@ struct EpiRev {
       if (j >= nv) break;
       int c = col + j;
       float g = acc[j] * post_scale;
-      if (c < n_main) {
-        float a = Anext[row * lda + c] * a_unscale;
-        Dprev[row * ldd + c] = g * sig_from_softplus(a);
-      } else if (Gpe != nullptr) {
-        Gpe[row * ldg + (c - n_main)] = g;
-      }
+      if (c < n_main) Dprev[row * ldd + c] = g * sig_from_softplus(x.a[j] * a_unscale);
+      else if (Gpe != nullptr) Gpe[row * ldg + (c - n_main)] = g;
     }
   }
+  NUDF_EPI_CALL
 };
 
 // Last reverse GEMM (layer 0): Ge = acc + Gpe
 struct EpiRevFinal {
   float* Ge; int64_t ldge; const float* Gpe; int64_t ldg;
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j >= nv) break;
-      float g = acc[j];
-      if (Gpe != nullptr) g += Gpe[row * ldg + col + j];
-      Ge[row * ldge + col + j] = g;
-    }
+  struct Aux { float g[4]; };
+  __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
+    if (Gpe != nullptr) ld4(Gpe, ldg, row, col, nv, x.g);
+    else { x.g[0] = x.g[1] = x.g[2] = x.g[3] = 0.f; }
   }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[j] + x.g[j];
+    st4(Ge, ldge, row, col, nv, v);
+  }
+  NUDF_EPI_CALL
 };
 
 // Tangent chain: acc = Zdot_l.  Q_l = Zdot * D_l * 100 (1 - S_l);  Adot_{l+1} = S_l * Zdot * post_scale.
@@ -263,19 +288,23 @@ struct EpiTan {
   const float* D; int64_t ldd;
   float* Q; int64_t ldq;
   float* AdotNext; int64_t ldn; float post_scale;
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
-    float a[4], d[4], q[4], n[4];
-    ld4(Anext, lda, row, col, nv, a);
-    ld4(D, ldd, row, col, nv, d);
+  struct Aux { float a[4], d[4]; };
+  __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
+    ld4(Anext, lda, row, col, nv, x.a);
+    ld4(D, ldd, row, col, nv, x.d);
+  }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
+    float q[4], n[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float s = sig_from_softplus(a[j] * a_unscale);
-      q[j] = acc[j] * d[j] * (100.0f * (1.0f - s));
+      float s = sig_from_softplus(x.a[j] * a_unscale);
+      q[j] = acc[j] * x.d[j] * (100.0f * (1.0f - s));
       n[j] = s * acc[j] * post_scale;
     }
     st4(Q, ldq, row, col, nv, q);
     st4(AdotNext, ldn, row, col, nv, n);
   }
+  NUDF_EPI_CALL
 };
 
 // Backward chain: acc = Abar wrt A[l].  Zbar_{l-1} = Abar * post_scale * S_{l-1} + Q_{l-1} (in place over Q).
@@ -283,16 +312,21 @@ struct EpiBwd {
   int n_main; float post_scale;
   const float* Anext; int64_t lda; float a_unscale;
   float* QZ; int64_t ldq;
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+  struct Aux { float a[4], q[4]; };
+  __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
+    int n = n_main - col;
+    n = n < nv ? n : nv;
+    if (n > 0) { ld4(Anext, lda, row, col, n, x.a); ld4(QZ, ldq, row, col, n, x.q); }
+  }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
     if (col >= n_main) return;
     if (col + nv > n_main) nv = n_main - col;
-    float a[4], q[4];
-    ld4(Anext, lda, row, col, nv, a);
-    ld4(QZ, ldq, row, col, nv, q);
+    float q[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = acc[j] * post_scale * sig_from_softplus(a[j] * a_unscale) + q[j];
+    for (int j = 0; j < 4; ++j) q[j] = acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale) + x.q[j];
     st4(QZ, ldq, row, col, nv, q);
   }
+  NUDF_EPI_CALL
 };
 
 // ReLU-MLP backward: dZ_prev[row, c - col_lo] = acc * (Yprev > 0) for c in [col_lo, col_hi); optional accumulate.
@@ -300,19 +334,29 @@ struct EpiReluBwd {
   int col_lo, col_hi;
   const float* Yprev; int64_t ldy;   // post-ReLU output of the previous layer (null: no activation)
   float* dZ; int64_t ldz; int accumulate;
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+  struct Aux { float y[4], p[4]; };
+  __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = col + j;
+      bool in = (j < nv) && c >= col_lo && c < col_hi;
+      int cc = c - col_lo;
+      x.y[j] = (in && Yprev != nullptr) ? Yprev[row * ldy + cc] : 1.0f;
+      x.p[j] = (in && accumulate) ? dZ[row * ldz + cc] : 0.0f;
+    }
+  }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j >= nv) break;
       int c = col + j;
       if (c < col_lo || c >= col_hi) continue;
-      int cc = c - col_lo;
-      float* p = dZ + row * ldz + cc;
-      float g = accumulate ? (*p + acc[j]) : acc[j];
-      if (Yprev != nullptr && !(Yprev[row * ldy + cc] > 0.f)) g = 0.f;   // mask applies to the accumulated sum
-      *p = g;
+      float g = x.p[j] + acc[j];
+      if (!(x.y[j] > 0.f)) g = 0.f;                     // mask applies to the accumulated sum
+      dZ[row * ldz + (c - col_lo)] = g;
     }
   }
+  NUDF_EPI_CALL
 };
 
 template <bool A_KC, bool B_KC, class Epi>

@@ -37,4 +37,11 @@ int nudf_wgrad(const float* dZ, int64_t ldz, const float* X, int64_t ldx, int32_
   return gemm_simt<false, false, EpiAtomicAdd>(dZ, ldz, X, ldx, n_out, n_in, P, e, (cudaStream_t)stream, (int)cdiv(P, 2048));
 }
 
+// profiling aid: copies the pipeline trace of CTA 0 (see NUDF_TC_DEBUG bit 16) to a host buffer of 4*256 int64
+int nudf_tc_read_trace(long long* host_buf) {
+  NUDF_CUDA_OK(cudaDeviceSynchronize());
+  NUDF_CUDA_OK(cudaMemcpyFromSymbol(host_buf, tc::g_tc_trace, sizeof(long long) * 4 * 256));
+  return 0;
+}
+
 }  // extern "C"

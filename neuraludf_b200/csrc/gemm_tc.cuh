@@ -186,18 +186,14 @@ __device__ __forceinline__ void split4(const float x[4], uint2 planes[NP]) {
   }
 }
 
-// Stage a [128 x 64] slice of row-major fp32 A (K contiguous) as NP bf16 planes in K-major SW128 tiles (16 KB each).
-// All global loads of a thread are issued before the first conversion so that the whole 32 KB slice is in flight.
-template <int NP, int NT>   // NT = number of producer threads (128 or 256)
-__device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int k0, int K,
-                                               uint8_t* sa, int tid, bool vec_ok) {
+template <int NT>   // NT = number of producer threads (128 or 256); fetches this thread's part of a [128 x 64] fp32 slice
+__device__ __forceinline__ void fetch_a(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int k0, int K, int tid,
+                                        bool vec_ok, float4 (&v)[BM * 16 / NT]) {
   const int c = tid & 15;            // float4 chunk along k
   const int rsub = tid >> 4;         // 0 .. NT/16-1
   const int k = k0 + c * 4;
-  constexpr int PASSES = BM * 16 / NT;
-  float4 v[PASSES];
 #pragma unroll
-  for (int pass = 0; pass < PASSES; ++pass) {
+  for (int pass = 0; pass < BM * 16 / NT; ++pass) {
     const int64_t row = m0 + pass * (NT / 16) + rsub;
     v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < M) {
@@ -212,8 +208,14 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
       }
     }
   }
+}
+// splits the fetched values into NP bf16 planes and writes them into the K-major SW128 stage (16 KB per plane)
+template <int NP, int NT>
+__device__ __forceinline__ void store_a(const float4 (&v)[BM * 16 / NT], uint8_t* sa, int tid) {
+  const int c = tid & 15;
+  const int rsub = tid >> 4;
 #pragma unroll
-  for (int pass = 0; pass < PASSES; ++pass) {
+  for (int pass = 0; pass < BM * 16 / NT; ++pass) {
     const float x[4] = {v[pass].x, v[pass].y, v[pass].z, v[pass].w};
     uint2 pl[NP];
     split4<NP>(x, pl);
@@ -221,6 +223,15 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
 #pragma unroll
     for (int p = 0; p < NP; ++p) *reinterpret_cast<uint2*>(sa + p * A_HALF_BYTES + off) = pl[p];
   }
+}
+// Stage a [128 x 64] slice of row-major fp32 A (K contiguous) as NP bf16 planes.  All global loads of a thread are issued
+// before the first conversion so that the whole 32 KB slice is in flight.
+template <int NP, int NT>
+__device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int k0, int K,
+                                               uint8_t* sa, int tid, bool vec_ok) {
+  float4 v[BM * 16 / NT];
+  fetch_a<NT>(A, lda, m0, M, k0, K, tid, vec_ok, v);
+  store_a<NP, NT>(v, sa, tid);
 }
 
 // Stage a [rows x 64] K-major tile of  T(m, k) = X[(k0 + k) * ld + m0 + m]  as 2 bf16 planes (on-the-fly transpose; the
@@ -333,6 +344,13 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int la
     const int col = col_base + c0 + 4 * cq;
     int nv = n_valid_end - col;
     nv = nv < 4 ? nv : 4;
+    // phase 1: put the auxiliary global loads of all 8 row groups in flight; phase 2: compute + store
+    typename Epi::Aux aux[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t row = row0 + rsub + 4 * i;
+      if (row < M && nv > 0) epi.load(row, col, nv, aux[i]);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = rsub + 4 * i;
@@ -340,7 +358,7 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int la
       const int64_t row = row0 + r;
       if (row < M && nv > 0) {
         const float x[4] = {t.x, t.y, t.z, t.w};
-        epi(row, col, x, nv);
+        epi.apply(row, col, x, nv, aux[i]);
       }
     }
     __syncwarp();
@@ -435,6 +453,10 @@ gemm_w_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K,
 // Persistent 2-plane variant of gemm_w: one CTA per SM loops over 128-row tiles; the TMEM accumulator is double
 // buffered so that the epilogue of tile i (warps 4-7) overlaps the operand staging + MMAs of tile i+1 (warps 0-3, 8, 9).
 // ---------------------------------------------------------------------------------------------------------------
+// profiling aid (NUDF_TC_DEBUG & 16): CTA 0 records clock64() at pipeline events
+__device__ long long g_tc_trace[4][256];
+#define TC_TRACE(role, idx) do { if ((dbg & 16) && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 256) g_tc_trace[role][idx] = clock64(); } while (0)
+
 struct SmemCtlP {
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
@@ -446,7 +468,8 @@ constexpr int PPROD = 128;   // producer threads of the persistent kernel (warps
 
 template <class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi) {
+gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi,
+               int reverse, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -471,31 +494,63 @@ gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = ctl->tmem_addr;
+  if (tid == 0) TC_TRACE(3, 0);
 
   if (warp < 4) {
     // ---- A producers ----
     const bool vec_ok = ((lda & 3) == 0) && aligned16(A);
     uint32_t cnt = 0;
-    for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-      for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
-        const uint32_t s = cnt & 1u, u = cnt >> 1;
-        if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
-        stage_a_direct<2, PPROD>(A, lda, mt * BM, M, ks * BK, K, smem + s * stage_bytes, tid, vec_ok);
-        fence_proxy_async();
-        mbar_arrive(&ctl->full[s]);
+    for (int64_t it = blockIdx.x; it < n_mtiles; it += gridDim.x) {
+      const int64_t mt = reverse ? n_mtiles - 1 - it : it;
+      for (int ks = 0; ks < n_slices; ks += 2) {
+        // two K slices (64 KB of fp32) are fetched before the first conversion: twice the bytes in flight per SM
+        const bool two = ks + 1 < n_slices;
+        float4 v0[BM * 16 / PPROD], v1[BM * 16 / PPROD];
+        if (!(dbg & 1)) {
+          fetch_a<PPROD>(A, lda, mt * BM, M, ks * BK, K, tid, vec_ok, v0);
+          if (two) fetch_a<PPROD>(A, lda, mt * BM, M, (ks + 1) * BK, K, tid, vec_ok, v1);
+        } else {
+#pragma unroll
+          for (int q = 0; q < BM * 16 / PPROD; ++q) { v0[q] = make_float4(1.f, 0.f, 0.f, 0.f); v1[q] = v0[q]; }
+        }
+        {
+          const uint32_t s = cnt & 1u, u = cnt >> 1;
+          if (tid == 0) TC_TRACE(0, 4 * cnt + 0);
+          if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
+          if (tid == 0) TC_TRACE(0, 4 * cnt + 1);
+          store_a<2, PPROD>(v0, smem + s * stage_bytes, tid);
+          if (tid == 0) TC_TRACE(0, 4 * cnt + 2);
+          fence_proxy_async();
+          mbar_arrive(&ctl->full[s]);
+          if (tid == 0) TC_TRACE(0, 4 * cnt + 3);
+          ++cnt;
+        }
+        if (two) {
+          const uint32_t s = cnt & 1u, u = cnt >> 1;
+          if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
+          store_a<2, PPROD>(v1, smem + s * stage_bytes, tid);
+          fence_proxy_async();
+          mbar_arrive(&ctl->full[s]);
+          ++cnt;
+        }
       }
     }
   } else if (warp < 8) {
     // ---- epilogue ----
     uint32_t it = 0;
-    for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++it) {
+    for (int64_t jt = blockIdx.x; jt < n_mtiles; jt += gridDim.x, ++it) {
+      const int64_t mt = reverse ? n_mtiles - 1 - jt : jt;
       const uint32_t a = it & 1u, au = it >> 1;
+      if (tid == 128) TC_TRACE(2, 3 * it + 0);
       mbar_wait(&ctl->tfull[a], au & 1u);
+      if (tid == 128) TC_TRACE(2, 3 * it + 1);
       tcgen05_fence_after();
-      run_epilogue(tmem_base + a * acc_cols, warp & 3, lane, 0, 32, 1, 0u, mt * BM + (warp & 3) * 32, M, t * 256, rows_b, N,
-                   epi_stage + (warp & 3) * EPI_WARP_FLOATS, epi);
+      if (!(dbg & 2))
+        run_epilogue(tmem_base + a * acc_cols, warp & 3, lane, 0, 32, 1, 0u, mt * BM + (warp & 3) * 32, M, t * 256, rows_b, N,
+                     epi_stage + (warp & 3) * EPI_WARP_FLOATS, epi);
       tcgen05_fence_before();
       mbar_arrive(&ctl->tempty[a]);
+      if (tid == 128) TC_TRACE(2, 3 * it + 2);
     }
   } else if (warp == 8) {
     // ---- MMA issuer ----
@@ -508,11 +563,14 @@ gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
         tcgen05_fence_after();
         for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
           const uint32_t s = cnt & 1u, u = cnt >> 1;
+          TC_TRACE(1, 3 * cnt + 0);
           mbar_wait(&ctl->full[s], u & 1u);
+          TC_TRACE(1, 3 * cnt + 1);
           tcgen05_fence_after();
           const uint32_t st = smem_u32(smem + s * stage_bytes);
-          issue_slice<2>(tmem_base + a * acc_cols, st, A_HALF_BYTES, st + 2 * A_HALF_BYTES, b_half_bytes, idesc, ks == 0);
+          if (!(dbg & 8)) issue_slice<2>(tmem_base + a * acc_cols, st, A_HALF_BYTES, st + 2 * A_HALF_BYTES, b_half_bytes, idesc, ks == 0);
           mma_commit(&ctl->empty[s]);
+          TC_TRACE(1, 3 * cnt + 2);
         }
         mma_commit(&ctl->tfull[a]);
       }
@@ -527,10 +585,149 @@ gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
           const uint32_t s = cnt & 1u, u = cnt >> 1;
           if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
           uint8_t* st = smem + s * stage_bytes + 2 * A_HALF_BYTES;
+          if (dbg & 4) { mbar_arrive(&ctl->full[s]); continue; }
           mbar_arrive_expect_tx(&ctl->full[s], 2u * b_half_bytes);
           bulk_g2s(st, img_t + (int64_t)ks * 2 * rows_b * 64, 2u * b_half_bytes, &ctl->full[s]);
         }
       }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid == 0) TC_TRACE(3, 1);
+  if (warp == 8) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 2 * acc_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weights-resident persistent variant (K <= 256): each CTA owns one 128-column half of the output and keeps that half
+// of the pre-split weight image (all K slices, <= 128 KB) in shared memory for its whole lifetime -- it is fetched once
+// with a handful of 16 KB cp.async.bulk copies.  Only the activation slices stream through the 2-stage ring; the TMEM
+// accumulator (128 columns) is double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// (Streaming the weight slices per tile -- gemm_wp_kernel -- turned out to be limited by the bulk-copy engine: one
+// 64 KB copy per K slice per CTA took 6-10 us on B200, see profiles/.)
+// ---------------------------------------------------------------------------------------------------------------
+struct SmemCtlR {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint64_t wfull;
+  uint32_t tmem_addr;
+};
+constexpr int WR_N = 128;        // output columns per CTA
+constexpr int WR_MAX_SLICES = 4; // K <= 256
+
+template <class Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_wr_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi,
+               int reverse) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * WR_N;                          // first output column of this CTA
+  const int t = n0 / 256;                                    // 256-row tile of the 2-plane image this half lives in
+  const int rows_t = tile_rows(N, t, 2);                     // rows of that image tile (multiple of 16)
+  const int row_in_tile = n0 - t * 256;                      // 0 or 128
+  int rows_h = rows_t - row_in_tile; rows_h = rows_h < WR_N ? rows_h : WR_N;   // padded N of this CTA (multiple of 16)
+  const int n_slices = pad64(K) / 64;
+  const uint32_t w_plane_bytes = (uint32_t)rows_h * 128u;    // one plane of one slice of this half
+  uint8_t* w_smem = smem;                                    // [slice][plane][rows_h x 128 B]
+  uint8_t* a_smem = smem + (size_t)n_slices * 2 * w_plane_bytes;             // 2 stages x (2 planes x 16 KB)
+  float* epi_stage = reinterpret_cast<float*>(a_smem + STAGES * 2 * A_HALF_BYTES);
+  SmemCtlR* ctl = reinterpret_cast<SmemCtlR*>(reinterpret_cast<uint8_t*>(epi_stage) + 4 * EPI_WARP_FLOATS * sizeof(float));
+  const uint16_t* img_t = img + tile_offset(N, K, t, 2);
+  const int64_t n_mtiles = (M + BM - 1) / BM;
+  const uint32_t acc_cols = tmem_cols_for(rows_h);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], PPROD); mbar_init(&ctl->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl->tfull[a], 1); mbar_init(&ctl->tempty[a], 128); }
+    mbar_init(&ctl->wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&ctl->tmem_addr, 2 * acc_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = ctl->tmem_addr;
+
+  if (warp < 4) {
+    // ---- A producers ----
+    const bool vec_ok = ((lda & 3) == 0) && aligned16(A);
+    uint32_t cnt = 0;
+    for (int64_t it = blockIdx.x; it < n_mtiles; it += gridDim.x) {
+      const int64_t mt = reverse ? n_mtiles - 1 - it : it;
+      for (int ks = 0; ks < n_slices; ks += 2) {
+        const bool two = ks + 1 < n_slices;
+        float4 v0[BM * 16 / PPROD], v1[BM * 16 / PPROD];
+        fetch_a<PPROD>(A, lda, mt * BM, M, ks * BK, K, tid, vec_ok, v0);
+        if (two) fetch_a<PPROD>(A, lda, mt * BM, M, (ks + 1) * BK, K, tid, vec_ok, v1);
+        {
+          const uint32_t s = cnt & 1u, u = cnt >> 1;
+          if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
+          store_a<2, PPROD>(v0, a_smem + s * 2 * A_HALF_BYTES, tid);
+          fence_proxy_async();
+          mbar_arrive(&ctl->full[s]);
+          ++cnt;
+        }
+        if (two) {
+          const uint32_t s = cnt & 1u, u = cnt >> 1;
+          if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
+          store_a<2, PPROD>(v1, a_smem + s * 2 * A_HALF_BYTES, tid);
+          fence_proxy_async();
+          mbar_arrive(&ctl->full[s]);
+          ++cnt;
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ---- epilogue ----
+    uint32_t it = 0;
+    for (int64_t jt = blockIdx.x; jt < n_mtiles; jt += gridDim.x, ++it) {
+      const int64_t mt = reverse ? n_mtiles - 1 - jt : jt;
+      const uint32_t a = it & 1u, au = it >> 1;
+      mbar_wait(&ctl->tfull[a], au & 1u);
+      tcgen05_fence_after();
+      run_epilogue(tmem_base + a * acc_cols, warp & 3, lane, 0, 32, 1, 0u, mt * BM + (warp & 3) * 32, M, n0, rows_h, N,
+                   epi_stage + (warp & 3) * EPI_WARP_FLOATS, epi);
+      tcgen05_fence_before();
+      mbar_arrive(&ctl->tempty[a]);
+    }
+  } else if (warp == 8) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc((uint32_t)rows_h);
+      const uint32_t w_addr = smem_u32(w_smem);
+      mbar_wait(&ctl->wfull, 0);
+      uint32_t cnt = 0, it = 0;
+      for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++it) {
+        const uint32_t a = it & 1u, au = it >> 1;
+        if (au > 0) mbar_wait(&ctl->tempty[a], (au - 1) & 1u);
+        tcgen05_fence_after();
+        for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
+          const uint32_t s = cnt & 1u, u = cnt >> 1;
+          mbar_wait(&ctl->full[s], u & 1u);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(a_smem + s * 2 * A_HALF_BYTES);
+          issue_slice<2>(tmem_base + a * acc_cols, st, A_HALF_BYTES, w_addr + (uint32_t)ks * 2u * w_plane_bytes, w_plane_bytes, idesc,
+                         ks == 0);
+          mma_commit(&ctl->empty[s]);
+        }
+        mma_commit(&ctl->tfull[a]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- weight loader: once per CTA; lane l < 2*n_slices copies (slice l/2, plane l%2) ----
+    if (lane == 0) mbar_arrive_expect_tx(&ctl->wfull, (uint32_t)n_slices * 2u * w_plane_bytes);
+    __syncwarp();
+    if (lane < 2 * n_slices) {
+      const int ks = lane >> 1, pl = lane & 1;
+      const uint16_t* src = img_t + (int64_t)ks * 2 * rows_t * 64 + (int64_t)pl * rows_t * 64 + (int64_t)row_in_tile * 64;
+      bulk_g2s(w_smem + (size_t)(ks * 2 + pl) * w_plane_bytes, src, w_plane_bytes, &ctl->wfull);
     }
     __syncwarp();
   }
@@ -619,6 +816,8 @@ inline size_t smem_bytes_for(int rows_b, int np) {
   return (size_t)STAGES * ((size_t)np * A_HALF_BYTES + (size_t)np * rows_b * 128) + sizeof(SmemCtl) + 1024 + 64;
 }
 
+int tc_debug();   // NUDF_TC_DEBUG bit mask (profiling aid): 1 skip A fetch, 2 skip epilogue, 4 skip weight copies, 8 skip MMAs
+
 static inline int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -643,7 +842,34 @@ static inline int gemm_wp(const float* A, int64_t lda, int64_t M, int N, int K, 
   if (gx < 1) gx = 1;
   if (gx > n_mtiles) gx = n_mtiles;
   dim3 grid((unsigned)gx, (unsigned)nt);
-  gemm_wp_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi);
+  // consecutive layers walk the row tiles in opposite directions: the rows the previous kernel wrote last are still in
+  // the 126 MB L2 when the next kernel starts with them
+  static int flip = 0;
+  flip ^= 1;
+  gemm_wp_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip, tc_debug());
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+template <class Epi>
+static inline int gemm_wr(const float* A, int64_t lda, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
+  const int n_slices = pad64(K) / 64;
+  const size_t smem = (size_t)n_slices * 2 * WR_N * 128 + (size_t)STAGES * 2 * A_HALF_BYTES + 4 * EPI_WARP_FLOATS * sizeof(float) +
+                      sizeof(SmemCtlR) + 1024 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_wr_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int64_t n_mtiles = cdiv(M, BM);
+  const int nh = (int)cdiv(pad16(N), WR_N);
+  int64_t gx = sm_count() / nh;
+  if (gx < 1) gx = 1;
+  if (gx > n_mtiles) gx = n_mtiles;
+  dim3 grid((unsigned)gx, (unsigned)nh);
+  static int flip = 0;
+  flip ^= 1;
+  gemm_wr_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip);
   NUDF_LAUNCH_OK();
   return 0;
 }
@@ -651,6 +877,7 @@ static inline int gemm_wp(const float* A, int64_t lda, int64_t M, int N, int K, 
 template <int NP, class Epi>
 static inline int gemm_w(const float* A, int64_t lda, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
+  if (NP == 2 && M > BM && pad64(K) <= 64 * WR_MAX_SLICES && tc_debug() != 32) return gemm_wr(A, lda, M, N, K, img, epi, st);
   if (NP == 2 && M > BM) return gemm_wp(A, lda, M, N, K, img, epi, st);
   const size_t smem = smem_bytes_for(tile_rows(N, 0, NP), NP);
   static bool attr_set = false;   // per template instantiation

@@ -18,20 +18,25 @@ struct EpiColorMainIn {
   float* dcb; int64_t ld_dcb;          // [P, d_out]  gradient wrt color_base coming through the main stack
   const float* xhid; int64_t ld_xhid;  // post-ReLU x_hidden (mask)
   float* dzb; int64_t ld_dzb;          // [P, H]      masked gradient wrt the base stack's layer n_lin-2 pre-activation
-  __device__ __forceinline__ void operator()(int64_t row, int col, const float acc[4], int nv) const {
+  struct Aux { float h[4]; };
+  __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = col + j;
+      x.h[j] = (j < nv && c >= c_hid && c < n_total) ? xhid[row * ld_xhid + (c - c_hid)] : 0.f;
+    }
+  }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j >= nv) break;
       int c = col + j;
       if (c < c_cb) continue;
-      if (c < c_hid) {
-        dcb[row * ld_dcb + (c - c_cb)] = acc[j];
-      } else if (c < n_total) {
-        int cc = c - c_hid;
-        dzb[row * ld_dzb + cc] = (xhid[row * ld_xhid + cc] > 0.f) ? acc[j] : 0.f;
-      }
+      if (c < c_hid) dcb[row * ld_dcb + (c - c_cb)] = acc[j];
+      else if (c < n_total) dzb[row * ld_dzb + (c - c_hid)] = (x.h[j] > 0.f) ? acc[j] : 0.f;
     }
   }
+  NUDF_EPI_CALL
 };
 
 // dY = bar * s (1 - s) for the first n_sig columns (sigmoid heads), bar elsewhere; optional extra additive term
