@@ -42,6 +42,28 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the dominant kernel from the committed
+    `ncu --set full` summary under profiles/ (None if not captured)."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_kernels.txt"))):
+        cur, rd, wr = None, None, None
+        for line in open(f):
+            if line.startswith("== "):
+                cur, rd, wr = line, None, None
+            elif cur and kernel_substr in cur:
+                parts = line.split()
+                if parts and parts[0] == "dram__bytes_read.sum":
+                    rd = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e3 if parts[2].startswith("Kbyte") else 1e9 if parts[2].startswith("Gbyte") else 1)
+                if parts and parts[0] == "dram__bytes_write.sum":
+                    wr = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e3 if parts[2].startswith("Kbyte") else 1e9 if parts[2].startswith("Gbyte") else 1)
+                if rd is not None and wr is not None:
+                    best = rd + wr
+                    cur = None
+    return best
+
+
 def scene(device):
     from neuraludf_b200 import synthetic as O
     from neuraludf_b200.models import fields as F
@@ -130,7 +152,8 @@ def run_ours(args):
                               up_sample_steps=1, perturb=0.0)
     o, d, z, sd = rays(seed=rank, device=dev)
     tgt = torch.full((N_RAYS, 3), 0.4, device=dev)
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    from neuraludf_b200.dp import GradBucket
+    bucket = GradBucket(params)
 
     def step(o_, d_, z_):
         for p in params:
@@ -139,12 +162,7 @@ def run_ours(args):
         loss = loss_fn(ret, tgt)
         loss.backward()
         if world > 1:
-            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
-            dist.all_reduce(flat)                      # one flat bucket (0.7 M floats) over NVLink
-            flat.mul_(1.0 / world)
-            off = 0
-            for p in params:
-                n = p.numel(); p.grad.copy_(flat[off:off + n].view_as(p)); off += n
+            bucket.allreduce_mean()                    # ONE NCCL all-reduce of the flat bucket (0.69 M floats) over NVLink
         return loss
 
     def barrier():
@@ -267,7 +285,8 @@ def run_ours(args):
             "kernels": ktimes,
             "roofline": {"bound": "tensor", "kernel": dom + ": dense 65536x256x256 + bias + softplus epilogue (UDF hidden layer)",
                          "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
-                         "traffic": None, "peak_source": pk["source"] + ", bf16 burst",
+                         "traffic": ncu_traffic("gemm_wr_kernel<EpiAct>" if dom.startswith("dense_tc") else "gemm_simt_kernel<1, 1, EpiAct>"),
+                         "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/)", "peak_source": pk["source"] + ", bf16 burst",
                          "note": "algorithmic FLOPs (2MNK); the tensor engine executes 3x that (3xBF16 split)"},
             "cpu_baseline": cpu,
         }
