@@ -82,7 +82,7 @@ __device__ __forceinline__ void gs_store(float4 t, float (*dst)[GS_BM + GS_PAD],
 }
 
 template <bool A_KC, bool B_KC, class Epi>
-__global__ void __launch_bounds__(GS_THREADS)
+__global__ void __launch_bounds__(GS_THREADS, 2)   // <= 128 registers: two CTAs (16 warps) per SM hide the LDS / FFMA2 latencies
 gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t M, int N,
                  int64_t K, int64_t k_chunk, Epi epi) {
   __shared__ __align__(16) float As[2][GS_BK][GS_BM + GS_PAD];

@@ -464,10 +464,14 @@ struct SmemCtlP {
   uint64_t tempty[2];
   uint32_t tmem_addr;
 };
-constexpr int PPROD = 128;   // producer threads of the persistent kernel (warps 0-3); warps 4-7 run the epilogue
+// Persistent kernels: 14 warps.  Measured on B200 with one CTA per SM (tools/ubench/membw.cu): the LSU path sustains
+// 2.3 TB/s with 4 loading warps, 3.9 TB/s with 8, 5.9 TB/s with 16 -- it scales with the number of warps, not with the
+// number of loads per thread -- so the activation operand is fetched by 8 warps.
+constexpr int PPROD = 256;      // producer threads (warps 0-7)
+constexpr int PTHREADS = 448;   // + warps 8-11 epilogue, warp 12 MMA issuer / TMEM owner, warp 13 weight loader
 
 template <class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(PTHREADS, 1)
 gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi,
                int reverse, int dbg) {
   extern __shared__ uint8_t smem_raw[];
@@ -489,14 +493,14 @@ gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
     for (int a = 0; a < 2; ++a) { mbar_init(&ctl->tfull[a], 1); mbar_init(&ctl->tempty[a], 128); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&ctl->tmem_addr, 2 * acc_cols);
+  if (warp == 12) tmem_alloc(&ctl->tmem_addr, 2 * acc_cols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = ctl->tmem_addr;
   if (tid == 0) TC_TRACE(3, 0);
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ---- A producers ----
     const bool vec_ok = ((lda & 3) == 0) && aligned16(A);
     uint32_t cnt = 0;
@@ -535,24 +539,24 @@ gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ---- epilogue ----
     uint32_t it = 0;
     for (int64_t jt = blockIdx.x; jt < n_mtiles; jt += gridDim.x, ++it) {
       const int64_t mt = reverse ? n_mtiles - 1 - jt : jt;
       const uint32_t a = it & 1u, au = it >> 1;
-      if (tid == 128) TC_TRACE(2, 3 * it + 0);
+      if (tid == 256) TC_TRACE(2, 3 * it + 0);
       mbar_wait(&ctl->tfull[a], au & 1u);
-      if (tid == 128) TC_TRACE(2, 3 * it + 1);
+      if (tid == 256) TC_TRACE(2, 3 * it + 1);
       tcgen05_fence_after();
       if (!(dbg & 2))
         run_epilogue(tmem_base + a * acc_cols, warp & 3, lane, 0, 32, 1, 0u, mt * BM + (warp & 3) * 32, M, t * 256, rows_b, N,
                      epi_stage + (warp & 3) * EPI_WARP_FLOATS, epi);
       tcgen05_fence_before();
       mbar_arrive(&ctl->tempty[a]);
-      if (tid == 128) TC_TRACE(2, 3 * it + 2);
+      if (tid == 256) TC_TRACE(2, 3 * it + 2);
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ---- MMA issuer ----
     if (lane == 0) {
       const uint32_t idesc = make_idesc((uint32_t)rows_b);
@@ -595,7 +599,7 @@ gemm_wp_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
   }
   __syncthreads();
   if (tid == 0) TC_TRACE(3, 1);
-  if (warp == 8) {
+  if (warp == 12) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 2 * acc_cols);
   }
@@ -619,9 +623,17 @@ struct SmemCtlR {
 };
 constexpr int WR_N = 128;        // output columns per CTA
 constexpr int WR_MAX_SLICES = 4; // K <= 256
+// Warp-specialised layout of the weights-resident kernel: 20 warps = 5 warpgroups.  LSU streaming rate of a
+// single CTA per SM scales with its number of loading warps (tools/ubench/membw.cu: 4 warps 2.3 TB/s, 8 warps 3.9 TB/s), so both the operand fetch and
+// the epilogue (whose fused functors load 1-2 and store 1-2 tensors) get 8 warps each; registers are re-balanced with
+// setmaxnreg (epilogue 128, MMA / loader warpgroup 32).
+constexpr int RW_THREADS = 640;
+constexpr int RW_PROD = 256;     // warps 0-7   (warpgroups 0-1)
+constexpr int RW_EPI = 256;      // warps 8-15  (warpgroups 2-3): quadrant = warp & 3, column half = (warp >> 2) & 1
+constexpr int RW_MMA_WARP = 16, RW_LOAD_WARP = 17;   // warpgroup 4 (warps 18, 19 idle)
 
 template <class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(RW_THREADS, 1)
 gemm_wr_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi,
                int reverse) {
   extern __shared__ uint8_t smem_raw[];
@@ -637,38 +649,38 @@ gemm_wr_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
   uint8_t* w_smem = smem;                                    // [slice][plane][rows_h x 128 B]
   uint8_t* a_smem = smem + (size_t)n_slices * 2 * w_plane_bytes;             // 2 stages x (2 planes x 16 KB)
   float* epi_stage = reinterpret_cast<float*>(a_smem + STAGES * 2 * A_HALF_BYTES);
-  SmemCtlR* ctl = reinterpret_cast<SmemCtlR*>(reinterpret_cast<uint8_t*>(epi_stage) + 4 * EPI_WARP_FLOATS * sizeof(float));
+  SmemCtlR* ctl = reinterpret_cast<SmemCtlR*>(reinterpret_cast<uint8_t*>(epi_stage) + 8 * EPI_WARP_FLOATS * sizeof(float));
   const uint16_t* img_t = img + tile_offset(N, K, t, 2);
   const int64_t n_mtiles = (M + BM - 1) / BM;
   const uint32_t acc_cols = tmem_cols_for(rows_h);
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], PPROD); mbar_init(&ctl->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&ctl->tfull[a], 1); mbar_init(&ctl->tempty[a], 128); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], RW_PROD); mbar_init(&ctl->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl->tfull[a], 1); mbar_init(&ctl->tempty[a], RW_EPI); }
     mbar_init(&ctl->wfull, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&ctl->tmem_addr, 2 * acc_cols);
+  if (warp == RW_MMA_WARP) tmem_alloc(&ctl->tmem_addr, 2 * acc_cols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = ctl->tmem_addr;
 
-  if (warp < 4) {
-    // ---- A producers ----
+  if (warp < 8) {
+    // ---- A producers (warpgroups 0-1): two K slices (64 KB) are fetched before the first conversion ----
     const bool vec_ok = ((lda & 3) == 0) && aligned16(A);
     uint32_t cnt = 0;
     for (int64_t it = blockIdx.x; it < n_mtiles; it += gridDim.x) {
       const int64_t mt = reverse ? n_mtiles - 1 - it : it;
       for (int ks = 0; ks < n_slices; ks += 2) {
         const bool two = ks + 1 < n_slices;
-        float4 v0[BM * 16 / PPROD], v1[BM * 16 / PPROD];
-        fetch_a<PPROD>(A, lda, mt * BM, M, ks * BK, K, tid, vec_ok, v0);
-        if (two) fetch_a<PPROD>(A, lda, mt * BM, M, (ks + 1) * BK, K, tid, vec_ok, v1);
+        float4 v0[BM * 16 / RW_PROD], v1[BM * 16 / RW_PROD];
+        fetch_a<RW_PROD>(A, lda, mt * BM, M, ks * BK, K, tid, vec_ok, v0);
+        if (two) fetch_a<RW_PROD>(A, lda, mt * BM, M, (ks + 1) * BK, K, tid, vec_ok, v1);
         {
           const uint32_t s = cnt & 1u, u = cnt >> 1;
           if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
-          store_a<2, PPROD>(v0, a_smem + s * 2 * A_HALF_BYTES, tid);
+          store_a<2, RW_PROD>(v0, a_smem + s * 2 * A_HALF_BYTES, tid);
           fence_proxy_async();
           mbar_arrive(&ctl->full[s]);
           ++cnt;
@@ -676,63 +688,68 @@ gemm_wr_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
         if (two) {
           const uint32_t s = cnt & 1u, u = cnt >> 1;
           if (u > 0) mbar_wait(&ctl->empty[s], (u - 1) & 1u);
-          store_a<2, PPROD>(v1, a_smem + s * 2 * A_HALF_BYTES, tid);
+          store_a<2, RW_PROD>(v1, a_smem + s * 2 * A_HALF_BYTES, tid);
           fence_proxy_async();
           mbar_arrive(&ctl->full[s]);
           ++cnt;
         }
       }
     }
-  } else if (warp < 8) {
-    // ---- epilogue ----
+  } else if (warp < 16) {
+    // ---- epilogue (warpgroups 2-3) ----
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    const int ew = warp - 8;
     uint32_t it = 0;
     for (int64_t jt = blockIdx.x; jt < n_mtiles; jt += gridDim.x, ++it) {
       const int64_t mt = reverse ? n_mtiles - 1 - jt : jt;
       const uint32_t a = it & 1u, au = it >> 1;
       mbar_wait(&ctl->tfull[a], au & 1u);
       tcgen05_fence_after();
-      run_epilogue(tmem_base + a * acc_cols, warp & 3, lane, 0, 32, 1, 0u, mt * BM + (warp & 3) * 32, M, n0, rows_h, N,
-                   epi_stage + (warp & 3) * EPI_WARP_FLOATS, epi);
+      run_epilogue(tmem_base + a * acc_cols, ew & 3, lane, 32 * (ew >> 2), 64, 1, 0u, mt * BM + (ew & 3) * 32, M, n0, rows_h, N,
+                   epi_stage + ew * EPI_WARP_FLOATS, epi);
       tcgen05_fence_before();
       mbar_arrive(&ctl->tempty[a]);
     }
-  } else if (warp == 8) {
-    // ---- MMA issuer ----
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc((uint32_t)rows_h);
-      const uint32_t w_addr = smem_u32(w_smem);
-      mbar_wait(&ctl->wfull, 0);
-      uint32_t cnt = 0, it = 0;
-      for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++it) {
-        const uint32_t a = it & 1u, au = it >> 1;
-        if (au > 0) mbar_wait(&ctl->tempty[a], (au - 1) & 1u);
-        tcgen05_fence_after();
-        for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
-          const uint32_t s = cnt & 1u, u = cnt >> 1;
-          mbar_wait(&ctl->full[s], u & 1u);
-          tcgen05_fence_after();
-          const uint32_t st = smem_u32(a_smem + s * 2 * A_HALF_BYTES);
-          issue_slice<2>(tmem_base + a * acc_cols, st, A_HALF_BYTES, w_addr + (uint32_t)ks * 2u * w_plane_bytes, w_plane_bytes, idesc,
-                         ks == 0);
-          mma_commit(&ctl->empty[s]);
-        }
-        mma_commit(&ctl->tfull[a]);
-      }
-    }
-    __syncwarp();
   } else {
-    // ---- weight loader: once per CTA; lane l < 2*n_slices copies (slice l/2, plane l%2) ----
-    if (lane == 0) mbar_arrive_expect_tx(&ctl->wfull, (uint32_t)n_slices * 2u * w_plane_bytes);
-    __syncwarp();
-    if (lane < 2 * n_slices) {
-      const int ks = lane >> 1, pl = lane & 1;
-      const uint16_t* src = img_t + (int64_t)ks * 2 * rows_t * 64 + (int64_t)pl * rows_t * 64 + (int64_t)row_in_tile * 64;
-      bulk_g2s(w_smem + (size_t)(ks * 2 + pl) * w_plane_bytes, src, w_plane_bytes, &ctl->wfull);
+    // ---- warpgroup 4: MMA issuer (warp 16), weight loader (warp 17) ----
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == RW_MMA_WARP) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc((uint32_t)rows_h);
+        const uint32_t w_addr = smem_u32(w_smem);
+        mbar_wait(&ctl->wfull, 0);
+        uint32_t cnt = 0, it = 0;
+        for (int64_t mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++it) {
+          const uint32_t a = it & 1u, au = it >> 1;
+          if (au > 0) mbar_wait(&ctl->tempty[a], (au - 1) & 1u);
+          tcgen05_fence_after();
+          for (int ks = 0; ks < n_slices; ++ks, ++cnt) {
+            const uint32_t s = cnt & 1u, u = cnt >> 1;
+            mbar_wait(&ctl->full[s], u & 1u);
+            tcgen05_fence_after();
+            const uint32_t st = smem_u32(a_smem + s * 2 * A_HALF_BYTES);
+            issue_slice<2>(tmem_base + a * acc_cols, st, A_HALF_BYTES, w_addr + (uint32_t)ks * 2u * w_plane_bytes, w_plane_bytes, idesc,
+                           ks == 0);
+            mma_commit(&ctl->empty[s]);
+          }
+          mma_commit(&ctl->tfull[a]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == RW_LOAD_WARP) {
+      // weight half: fetched once per CTA; lane l < 2*n_slices copies (slice l/2, plane l%2), 16 KB each
+      if (lane == 0) mbar_arrive_expect_tx(&ctl->wfull, (uint32_t)n_slices * 2u * w_plane_bytes);
+      __syncwarp();
+      if (lane < 2 * n_slices) {
+        const int ks = lane >> 1, pl = lane & 1;
+        const uint16_t* src = img_t + (int64_t)ks * 2 * rows_t * 64 + (int64_t)pl * rows_t * 64 + (int64_t)row_in_tile * 64;
+        bulk_g2s(w_smem + (size_t)(ks * 2 + pl) * w_plane_bytes, src, w_plane_bytes, &ctl->wfull);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == RW_MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 2 * acc_cols);
   }
@@ -846,7 +863,7 @@ static inline int gemm_wp(const float* A, int64_t lda, int64_t M, int N, int K, 
   // the 126 MB L2 when the next kernel starts with them
   static int flip = 0;
   flip ^= 1;
-  gemm_wp_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip, tc_debug());
+  gemm_wp_kernel<Epi><<<grid, PTHREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip, tc_debug());
   NUDF_LAUNCH_OK();
   return 0;
 }
@@ -854,7 +871,7 @@ static inline int gemm_wp(const float* A, int64_t lda, int64_t M, int N, int K, 
 template <class Epi>
 static inline int gemm_wr(const float* A, int64_t lda, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
   const int n_slices = pad64(K) / 64;
-  const size_t smem = (size_t)n_slices * 2 * WR_N * 128 + (size_t)STAGES * 2 * A_HALF_BYTES + 4 * EPI_WARP_FLOATS * sizeof(float) +
+  const size_t smem = (size_t)n_slices * 2 * WR_N * 128 + (size_t)STAGES * 2 * A_HALF_BYTES + 8 * EPI_WARP_FLOATS * sizeof(float) +
                       sizeof(SmemCtlR) + 1024 + 64;
   static bool attr_set = false;
   if (!attr_set) {
@@ -869,7 +886,7 @@ static inline int gemm_wr(const float* A, int64_t lda, int64_t M, int N, int K, 
   dim3 grid((unsigned)gx, (unsigned)nh);
   static int flip = 0;
   flip ^= 1;
-  gemm_wr_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip);
+  gemm_wr_kernel<Epi><<<grid, RW_THREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip);
   NUDF_LAUNCH_OK();
   return 0;
 }
