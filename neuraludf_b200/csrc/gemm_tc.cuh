@@ -322,7 +322,7 @@ __device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a, uint32_
 // padded shared-memory tile so that each epilogue call covers 4 rows x 32 consecutive columns per warp instruction:
 // the fused epilogues' global loads / stores (activations, saved tensors, outputs) are then fully coalesced float4.
 constexpr int EPI_LD = 36;                       // floats per staged row (32 + 4 pad: conflict-free STS.128 / LDS.128)
-constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
+constexpr int EPI_WARP_FLOATS = 16 * EPI_LD;     // the 32x32 block goes through the staging tile in two 16-row passes
 template <class Epi>
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int lane, int chunk0, int chunk_step, int n_acc,
                                              uint32_t acc_stride, int64_t row0, int64_t M, int col_base, int n_pad, int n_valid_end,
@@ -337,31 +337,36 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int la
 #pragma unroll
       for (int q = 0; q < 32; ++q) v[q] += w[q];
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    __syncwarp();
     const int col = col_base + c0 + 4 * cq;
     int nv = n_valid_end - col;
     nv = nv < 4 ? nv : 4;
-    // phase 1: put the auxiliary global loads of all 8 row groups in flight; phase 2: compute + store
-    typename Epi::Aux aux[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t row = row0 + rsub + 4 * i;
-      if (row < M && nv > 0) epi.load(row, col, nv, aux[i]);
-    }
+    for (int h = 0; h < 2; ++h) {
+      if ((lane >> 4) == h) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rsub + 4 * i;
-      const float4 t = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * cq);
-      const int64_t row = row0 + r;
-      if (row < M && nv > 0) {
-        const float x[4] = {t.x, t.y, t.z, t.w};
-        epi.apply(row, col, x, nv, aux[i]);
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(stg + (lane & 15) * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
+      __syncwarp();
+      // phase 1: put the auxiliary global loads of the 4 row groups in flight; phase 2: compute + store
+      typename Epi::Aux aux[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = row0 + 16 * h + rsub + 4 * i;
+        if (row < M && nv > 0) epi.load(row, col, nv, aux[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rsub + 4 * i;
+        const float4 t = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * cq);
+        const int64_t row = row0 + 16 * h + r;
+        if (row < M && nv > 0) {
+          const float x[4] = {t.x, t.y, t.z, t.w};
+          epi.apply(row, col, x, nv, aux[i]);
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
