@@ -34,7 +34,12 @@ template <class Epi>
 static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K,
                           const Epi& epi, cudaStream_t st, int split_k, int chain = TC_WGRAD) {
   if (tc_on(chain) && M >= 32 && N >= 32 && K >= 128) {
-    int splits = (int)cdiv(K, 1024);          // 16 slices of 64 points per CTA
+    // split the points so that (M tiles x N tiles x splits) fills the SMs once, with at least 8 slices of 64 points per CTA
+    const int tiles = (int)(cdiv(M, 128) * cdiv(N, 256));
+    int splits = tc::sm_count() / tiles;
+    const int max_splits = (int)cdiv(K, 512);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
     return tc::gemm_tn(A, lda, B, ldb, M, N, K, epi, st, splits);
   }
   return gemm_simt<false, false, Epi>(A, lda, B, ldb, M, N, K, epi, st, split_k);

@@ -234,50 +234,45 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
   store_a<NP, NT>(v, sa, tid);
 }
 
-// Stage a [rows x 64] K-major tile of  T(m, k) = X[(k0 + k) * ld + m0 + m]  as 2 bf16 planes (on-the-fly transpose; the
-// contraction index k runs over points).  One warp iteration covers an 8-row group and all 64 k: lane l owns the k pair
-// (2l, 2l+1) and reads 8 consecutive m (two float4) for each of its two k -- full 32-byte sectors -- and its eight 32-bit
-// shared stores per plane hit 32 distinct banks across the warp.
-template <int R>   // R row-blocks (8 rows each) per warp are fetched before the first conversion: R * 64 B in flight per lane
-__device__ __forceinline__ void stage_transposed(const float* __restrict__ X, int64_t ld, int m0, int m_total, int64_t k0,
-                                                 int64_t k_end, int rows, uint8_t* s_hi, uint8_t* s_lo, int tid, bool vec_ok) {
-  const int lane = tid & 31, warp = tid >> 5;
-  const int64_t ka = k0 + 2 * lane;
-  constexpr int NW = NPROD / 32;
-  for (int rb0 = warp; rb0 * 8 < rows; rb0 += NW * R) {
-    float x[R][2][8];
+// One warp stages a [32 rows x 64 k] block of the K-major tile  T(r, k) = X[(k0 + k) * ld + m0 + r]  as 2 bf16 planes
+// (on-the-fly transpose; the contraction index k runs over points).  Lane l owns the m-quad (l & 7) and, in iteration q,
+// the k pair 4q + (l >> 3): every warp-level load covers 4 rows of X x 128 contiguous bytes (4 L1 wavefronts instead of
+// the 32 of a lane-per-row mapping); all 16 loads of a lane are issued before the first conversion.
+__device__ __forceinline__ void stage_block_t(const float* __restrict__ X, int64_t ld, int m0, int m_total, int r0, int rows,
+                                              int64_t k0, int64_t k_end, uint8_t* s_hi, uint8_t* s_lo, int lane, bool vec_ok) {
+  const int mq = lane & 7, kq = lane >> 3;
+  if (r0 + 4 * mq >= rows) return;      // tile rows are padded to 16, blocks cover 32: skip quads beyond the tile
+  const int m = m0 + r0 + 4 * mq;
+  float4 v[8][2];
 #pragma unroll
-    for (int u = 0; u < R; ++u) {
-      const int rb = rb0 + u * NW;
-      const int mbase = m0 + rb * 8;
+  for (int q = 0; q < 8; ++q) {
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const bool ok = ((ka + kk) < k_end) && (rb * 8 < rows);
-        const float* p = X + (ka + kk) * ld + mbase;
-        if (ok && vec_ok && mbase + 7 < m_total) {
-          float4 a = *reinterpret_cast<const float4*>(p);
-          float4 b = *reinterpret_cast<const float4*>(p + 4);
-          x[u][kk][0] = a.x; x[u][kk][1] = a.y; x[u][kk][2] = a.z; x[u][kk][3] = a.w;
-          x[u][kk][4] = b.x; x[u][kk][5] = b.y; x[u][kk][6] = b.z; x[u][kk][7] = b.w;
+    for (int kk = 0; kk < 2; ++kk) {
+      const int64_t k = k0 + 2 * (4 * q + kq) + kk;
+      v[q][kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < k_end) {
+        const float* p = X + k * ld + m;
+        if (vec_ok && m + 3 < m_total) {
+          v[q][kk] = *reinterpret_cast<const float4*>(p);
         } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[u][kk][j] = (ok && mbase + j < m_total) ? p[j] : 0.f;
+          if (m + 0 < m_total) v[q][kk].x = p[0];
+          if (m + 1 < m_total) v[q][kk].y = p[1];
+          if (m + 2 < m_total) v[q][kk].z = p[2];
+          if (m + 3 < m_total) v[q][kk].w = p[3];
         }
       }
     }
+  }
 #pragma unroll
-    for (int u = 0; u < R; ++u) {
-      const int rb = rb0 + u * NW;
-      if (rb * 8 < rows) {
+  for (int q = 0; q < 8; ++q) {
+    const float x0[4] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w};
+    const float x1[4] = {v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x0 = x[u][0][j], x1 = x[u][1][j];
-          const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
-          const uint32_t off = sw128((uint32_t)(rb * 8 + j), (uint32_t)(2 * lane));
-          *reinterpret_cast<uint32_t*>(s_hi + off) = pack_bf16(h0, h1);
-          *reinterpret_cast<uint32_t*>(s_lo + off) = pack_bf16(x0 - h0, x1 - h1);
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float h0 = __bfloat162float(__float2bfloat16_rn(x0[j])), h1 = __bfloat162float(__float2bfloat16_rn(x1[j]));
+      const uint32_t off = sw128((uint32_t)(r0 + 4 * mq + j), (uint32_t)(2 * (4 * q + kq)));
+      *reinterpret_cast<uint32_t*>(s_hi + off) = pack_bf16(h0, h1);
+      *reinterpret_cast<uint32_t*>(s_lo + off) = pack_bf16(x0[j] - h0, x1[j] - h1);
     }
   }
 }
@@ -764,8 +759,10 @@ gemm_wr_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
 // C[M x N] += A[K x M]^T B[K x N]  (weight gradients; contraction over points, split over gridDim.z).
 // grid = (ceil(M/128), ceil(N/256), splits).  Epi is applied to the partial tile (EpiAtomicAdd).
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int TN_PROD = 384;      // 12 loading / epilogue warps: 4 stage the [128 x 64] A^T tile, 8 the [256 x 64] B^T tile
+constexpr int TN_THREADS = 416;   // + warp 12: MMA issuer and TMEM owner
 template <class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int M, int N, int64_t K,
                int64_t k_chunk, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
@@ -782,17 +779,17 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + STAGES * stage_bytes);
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], NPROD); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], TN_PROD); mbar_init(&ctl->empty[s], 1); }
     mbar_init(&ctl->tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
+  if (warp == 12) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = ctl->tmem_addr;
 
-  if (warp < 8) {
+  if (warp < 12) {
     const bool a_vec = ((lda & 3) == 0) && aligned16(A) && ((m0 & 3) == 0);
     const bool b_vec = ((ldb & 3) == 0) && aligned16(B);
     for (int ks = 0; ks < n_slices; ++ks) {
@@ -800,19 +797,23 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
       if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
       uint8_t* st = smem + s * stage_bytes;
       const int64_t k0 = kb + (int64_t)ks * BK;
-      stage_transposed<2>(A, lda, m0, M, k0, ke, BM, st, st + A_HALF_BYTES, tid, a_vec);
-      stage_transposed<4>(B, ldb, n0, N, k0, ke, rows_b, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, tid, b_vec);
+      if (warp < 4) {
+        stage_block_t(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec);
+      } else if (32 * (warp - 4) < rows_b) {
+        stage_block_t(B, ldb, n0, N, 32 * (warp - 4), rows_b, k0, ke, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, lane, b_vec);
+      }
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
     }
     if (n_slices > 0) {
       mbar_wait(&ctl->tmem_full, 0);
       tcgen05_fence_after();
-      run_epilogue(tmem_base, warp & 3, lane, 32 * (warp >> 2), 64, 1, 0u, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, rows_b, N,
+      // warp w: TMEM quadrant w & 3, 32-column chunks (w >> 2), (w >> 2) + 3, ...
+      run_epilogue(tmem_base, warp & 3, lane, 32 * (warp >> 2), 96, 1, 0u, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, rows_b, N,
                    reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi);
       tcgen05_fence_before();
     }
-  } else if (warp == 8) {
+  } else {
     if (lane == 0 && n_slices > 0) {
       const uint32_t idesc = make_idesc((uint32_t)rows_b);
       for (int ks = 0; ks < n_slices; ++ks) {
@@ -828,7 +829,7 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, tmem_cols_for(rows_b));
   }
@@ -926,7 +927,7 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     attr_set = true;
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, 256), (unsigned)splits);
-  gemm_tn_kernel<Epi><<<grid, THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi);
+  gemm_tn_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi);
   NUDF_LAUNCH_OK();
   return 0;
 }
