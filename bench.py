@@ -64,6 +64,14 @@ def ncu_traffic(kernel_substr):
     return best
 
 
+def nerf_module(device):
+    from neuraludf_b200 import synthetic as O
+    from neuraludf_b200.models import fields as F
+    nerf = F.NeRF(D=8, d_in=4, d_in_view=3, W=256, multires=10, multires_view=4, output_ch=4, skips=[4], use_viewdirs=True)
+    nerf.load_state_dict(O.make_nerf_params(O.nerf_cfg(), seed=2))
+    return nerf.to(device)
+
+
 def scene(device):
     from neuraludf_b200 import synthetic as O
     from neuraludf_b200.models import fields as F
@@ -97,7 +105,7 @@ class Clocks:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -150,6 +158,8 @@ def run_ours(args):
     params = [p for m in (udf, col, var, beta) for p in m.parameters() if p.requires_grad]
     ren = UDFRendererBlending(None, udf, var, col, beta, n_samples=N_SAMPLES, n_importance=0, n_outside=0,
                               up_sample_steps=1, perturb=0.0)
+    if args.workload == "c4":
+        return run_c4(args, dev, lib, udf, col, var, beta, rank, world)
     o, d, z, sd = rays(seed=rank, device=dev)
     tgt = torch.full((N_RAYS, 3), 0.4, device=dev)
     from neuraludf_b200.dp import GradBucket
@@ -296,6 +306,53 @@ def run_ours(args):
     return out
 
 
+def run_c4(args, dev, lib, udf, col, var, beta, rank, world):
+    """Whole render() of the DTU conf (one rank's 512 rays): sampling + NeRF++ background + fine pass,
+    forward + backward.  Secondary number (not the BASELINE.json headline); printed as a reduced JSON line."""
+    import torch.distributed as dist
+    from neuraludf_b200 import synthetic as O
+    from neuraludf_b200.dp import GradBucket
+    from neuraludf_b200.models.udf_renderer_blending import UDFRendererBlending
+    nerf = nerf_module(dev)
+    ren = UDFRendererBlending(nerf, udf, var, col, beta, n_samples=64, n_importance=50, n_outside=32, up_sample_steps=5,
+                              perturb=1.0)
+    params = [p for m in (udf, col, var, beta, nerf) for p in m.parameters() if p.requires_grad]
+    bucket = GradBucket(params)
+    o, d, near, far = [t.to(dev) for t in O.make_rays(N_RAYS, seed=rank)]
+    tgt = torch.full((N_RAYS, 3), 0.4, device=dev)
+
+    def step():
+        for p in params:
+            p.grad = None
+        ret = ren.render(o, d, near, far, cos_anneal_ratio=0.5, flip_saturation=0.1)
+        loss = loss_fn(ret, tgt)
+        loss.backward()
+        if world > 1:
+            bucket.allreduce_mean()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = lib.nudf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if rank == 0:
+        print(json.dumps({"workload": "c4: render() fwd+bwd, confs/udf_dtu_blending.conf shapes, 512 rays per GPU",
+                          "ms_per_step": ms, "rays_per_s": world * N_RAYS / (ms * 1e-3),
+                          "fine_ray_samples_per_s": world * N_RAYS * 114 / (ms * 1e-3), "n_gpus": world,
+                          "gpu_launches_per_step": (lib.nudf_launch_count() - l0) / args.steps}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return None
+
+
 def cpu_baseline(steps, warmup, n_rays):
     """The oracle port (pinned restatement of the reference's PyTorch code) on the host cores: a bounded sample of the
     same workload (n_rays of the 512 rays x 128 samples, forward + backward)."""
@@ -362,6 +419,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 (default, the BASELINE.json headline): render_core fwd+bwd on 512x128 uniform samples; "
+                         "c4: whole render() of confs/udf_dtu_blending.conf (64+50 samples, 32 outside, perturb) fwd+bwd")
     ap.add_argument("--quick", action="store_true", help="main timed loop only (for profiler runs): no e2e leg, no "
                     "single-kernel probes, no CPU baseline; prints a reduced JSON line")
     args = ap.parse_args()

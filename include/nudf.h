@@ -146,15 +146,19 @@ typedef struct nudf_nerf_desc {
   const float* rgb_w; const float* rgb_b;
 } nudf_nerf_desc;
 
+/* tensor-engine weight images of the NeRF layers (floats); build with nudf_nerf_prepare once per optimiser step and pass
+ * to forward/backward (NULL = exact-fp32 engine) */
+int64_t nudf_nerf_image_floats(const nudf_nerf_desc* d);
+int nudf_nerf_prepare(const nudf_nerf_desc* d, float* wimg, void* stream);
 int64_t nudf_nerf_ctx_floats(const nudf_nerf_desc* d, int64_t P);
 int64_t nudf_nerf_scratch_floats(const nudf_nerf_desc* d, int64_t P);
 /* sigma[P], rgb[P,3] <- NeRF.forward(pts4, view_dirs) (fields.py:599-628; no sigmoid on rgb) */
-int nudf_nerf_forward(const nudf_nerf_desc* d, const float* pts, const float* dirs, int32_t samples_per_ray,
-                      int64_t P, float* sigma, float* rgb, float* ctx, void* stream);
+int nudf_nerf_forward(const nudf_nerf_desc* d, const float* wimg, const float* pts, const float* dirs,
+                      int32_t samples_per_ray, int64_t P, float* sigma, float* rgb, float* ctx, void* stream);
 /* parameter gradients; dparams[] order: pts_w[0], pts_b[0], ..., views_w, views_b, feature_w, feature_b, alpha_w,
  * alpha_b, rgb_w, rgb_b  (each overwritten, same shape as the parameter). */
-int nudf_nerf_backward(const nudf_nerf_desc* d, int64_t P, const float* sigma_bar, const float* rgb_bar,
-                       const float* ctx, float* scratch, float* const* dparams, void* stream);
+int nudf_nerf_backward(const nudf_nerf_desc* d, const float* wimg, int64_t P, const float* sigma_bar,
+                       const float* rgb_bar, const float* ctx, float* scratch, float* const* dparams, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * render_core ray kernels  (reference: models/udf_renderer_blending.py:327-584)

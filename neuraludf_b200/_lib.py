@@ -101,12 +101,14 @@ _SIGNATURES = {
     "nudf_color_backward": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p]),
     "nudf_color_unfold_grads": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nudf_nerf_image_floats": (ctypes.c_int64, [c_void_p]),
+    "nudf_nerf_prepare": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "nudf_nerf_ctx_floats": (ctypes.c_int64, [c_void_p, ctypes.c_int64]),
     "nudf_nerf_scratch_floats": (ctypes.c_int64, [c_void_p, ctypes.c_int64]),
-    "nudf_nerf_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int64, c_void_p,
+    "nudf_nerf_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int64, c_void_p,
                                          c_void_p, c_void_p, c_void_p]),
-    "nudf_nerf_backward": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                          c_void_p]),
+    "nudf_nerf_backward": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p]),
     "nudf_ray_points": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "nudf_render_composite_forward": (ctypes.c_int, [c_void_p] * 2 + [c_void_p] * 5 + [ctypes.c_int64] + [c_void_p] * 7),

@@ -21,12 +21,12 @@ void set_error(const char* fmt, ...) {
 }
 
 // NUDF_TC_MASK: which chains may run on the tensor engine (bits: 1 fwd value, 2 reverse sweep, 4 tangent, 8 backward,
-// 16 weight gradients, 32 colour net, 64 NeRF).  Default: everything except the forward value chain.
+// 16 weight gradients, 32 colour net, 64 NeRF).  Default (126): everything except the forward value chain.
 static int g_tc_mask = -1;
 int tc_mask() {
   if (g_tc_mask < 0) {
     const char* e = getenv("NUDF_TC_MASK");
-    g_tc_mask = e ? atoi(e) : (2 | 4 | 8 | 16 | 32);
+    g_tc_mask = e ? atoi(e) : (2 | 4 | 8 | 16 | 32 | 64);
   }
   return g_tc_mask;
 }

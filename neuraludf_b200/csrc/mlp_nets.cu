@@ -432,6 +432,8 @@ namespace nudf {
 struct NerfPlan {
   int D, W, d_in, L, Lv, skip, ch, chv, ld_f, ld_x5;
   int in_dim[NUDF_MAX_LAYERS];
+  // tensor-engine weight images (uint16 offsets): per pts layer X W^T and dY W operands, feature layer, views layer
+  int64_t ipts_nt[NUDF_MAX_LAYERS], ipts_nn[NUDF_MAX_LAYERS], ifeat_nt, ifeat_nn, iviews_nt, iviews_nn, img_total;
 };
 static int nerf_plan(const nudf_nerf_desc* d, NerfPlan* p) {
   NUDF_REQUIRE(d != nullptr, "null desc");
@@ -444,6 +446,16 @@ static int nerf_plan(const nudf_nerf_desc* d, NerfPlan* p) {
   for (int i = 0; i < p->D; ++i) p->in_dim[i] = i == 0 ? p->ch : (i - 1 == p->skip ? p->W + p->ch : p->W);
   p->ld_f = (int)round_up(p->W + p->chv, 4);
   p->ld_x5 = (int)round_up(p->W + p->ch, 4);
+  int64_t io = 0;
+  for (int i = 0; i < p->D; ++i) {
+    p->ipts_nt[i] = io; io += tc::image_elems(p->W, p->in_dim[i], 2);
+    p->ipts_nn[i] = io; io += tc::image_elems(p->in_dim[i], p->W, 2);
+  }
+  p->ifeat_nt = io; io += tc::image_elems(p->W, p->W, 2);
+  p->ifeat_nn = io; io += tc::image_elems(p->W, p->W, 2);
+  p->iviews_nt = io; io += tc::image_elems(p->W / 2, p->W + p->chv, 2);
+  p->iviews_nn = io; io += tc::image_elems(p->W + p->chv, p->W / 2, 2);
+  p->img_total = round_up(io, 8);
   return 0;
 }
 struct NerfCtx { int64_t e, h[NUDF_MAX_LAYERS], f, hv, total; };
@@ -480,6 +492,29 @@ static inline const float* nerf_x(const NerfPlan& p, float* ctx, const NerfCtx& 
 
 extern "C" {
 
+int64_t nudf_nerf_image_floats(const nudf_nerf_desc* d) {
+  NerfPlan p;
+  if (nerf_plan(d, &p)) return -1;
+  return p.img_total / 2;
+}
+
+int nudf_nerf_prepare(const nudf_nerf_desc* d, float* wimg, void* stream) {
+  NerfPlan p;
+  if (int rc = nerf_plan(d, &p)) return rc;
+  NUDF_REQUIRE(wimg != nullptr, "null wimg");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint16_t* img = reinterpret_cast<uint16_t*>(wimg);
+  for (int i = 0; i < p.D; ++i) {
+    if (int rc = tc::prep_weights(d->pts_w[i], p.in_dim[i], p.W, p.in_dim[i], 0, 2, img + p.ipts_nt[i], st)) return rc;
+    if (int rc = tc::prep_weights(d->pts_w[i], p.in_dim[i], p.in_dim[i], p.W, 1, 2, img + p.ipts_nn[i], st)) return rc;
+  }
+  if (int rc = tc::prep_weights(d->feature_w, p.W, p.W, p.W, 0, 2, img + p.ifeat_nt, st)) return rc;
+  if (int rc = tc::prep_weights(d->feature_w, p.W, p.W, p.W, 1, 2, img + p.ifeat_nn, st)) return rc;
+  if (int rc = tc::prep_weights(d->views_w, p.W + p.chv, p.W / 2, p.W + p.chv, 0, 2, img + p.iviews_nt, st)) return rc;
+  if (int rc = tc::prep_weights(d->views_w, p.W + p.chv, p.W + p.chv, p.W / 2, 1, 2, img + p.iviews_nn, st)) return rc;
+  return 0;
+}
+
 int64_t nudf_nerf_ctx_floats(const nudf_nerf_desc* d, int64_t P) {
   NerfPlan p;
   if (nerf_plan(d, &p)) return -1;
@@ -495,8 +530,8 @@ int64_t nudf_nerf_scratch_floats(const nudf_nerf_desc* d, int64_t P) {
   return s.total;
 }
 
-int nudf_nerf_forward(const nudf_nerf_desc* d, const float* pts, const float* dirs, int32_t samples_per_ray, int64_t P,
-                      float* sigma, float* rgb, float* ctx, void* stream) {
+int nudf_nerf_forward(const nudf_nerf_desc* d, const float* wimg, const float* pts, const float* dirs, int32_t samples_per_ray,
+                      int64_t P, float* sigma, float* rgb, float* ctx, void* stream) {
   NerfPlan p;
   if (int rc = nerf_plan(d, &p)) return rc;
   NUDF_REQUIRE(pts && dirs && sigma && rgb && ctx, "null pointer");
@@ -506,6 +541,7 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* pts, const float* di
   NerfCtx c;
   nerf_ctx_layout(p, P, &c);
   const int ld_e = (int)round_up(p.ch, 4);
+  const uint16_t* img = reinterpret_cast<const uint16_t*>(wimg);   // null: exact-fp32 engine
   float* x5 = (p.skip >= 0) ? ctx + c.h[p.skip] : nullptr;
   ew_pe_kernel<<<ew_blocks(P, 128), 128, 0, st>>>(pts, p.d_in, p.L, 1, P, ctx + c.e, ld_e, 0, x5, p.ld_x5, 0);
   NUDF_LAUNCH_OK();
@@ -516,7 +552,7 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* pts, const float* di
     const float* X = nerf_x(p, ctx, c, i, &ldx);
     float* Hh = nerf_h(p, ctx, c, i, &ldh);
     EpiAct e{Hh, ldh, d->pts_b[i], ACT_RELU, 1.0f};
-    if (int rc = gemm_nt(X, ldx, d->pts_w[i], p.in_dim[i], P, p.W, p.in_dim[i], e, st)) return rc;
+    if (int rc = gemm_nt(X, ldx, d->pts_w[i], p.in_dim[i], P, p.W, p.in_dim[i], e, st, img ? img + p.ipts_nt[i] : nullptr, TC_NERF)) return rc;
   }
   int64_t ldl;
   const float* Hl = nerf_h(p, ctx, c, p.D - 1, &ldl);
@@ -526,11 +562,11 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* pts, const float* di
   }
   {
     EpiAct e{ctx + c.f, p.ld_f, d->feature_b, ACT_NONE, 1.0f};
-    if (int rc = gemm_nt(Hl, ldl, d->feature_w, p.W, P, p.W, p.W, e, st)) return rc;
+    if (int rc = gemm_nt(Hl, ldl, d->feature_w, p.W, P, p.W, p.W, e, st, img ? img + p.ifeat_nt : nullptr, TC_NERF)) return rc;
   }
   {
     EpiAct e{ctx + c.hv, p.W / 2, d->views_b, ACT_RELU, 1.0f};
-    if (int rc = gemm_nt(ctx + c.f, p.ld_f, d->views_w, p.W + p.chv, P, p.W / 2, p.W + p.chv, e, st)) return rc;
+    if (int rc = gemm_nt(ctx + c.f, p.ld_f, d->views_w, p.W + p.chv, P, p.W / 2, p.W + p.chv, e, st, img ? img + p.iviews_nt : nullptr, TC_NERF)) return rc;
   }
   {
     EpiAct e{rgb, 3, d->rgb_b, ACT_NONE, 1.0f};
@@ -539,12 +575,13 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* pts, const float* di
   return 0;
 }
 
-int nudf_nerf_backward(const nudf_nerf_desc* d, int64_t P, const float* sigma_bar, const float* rgb_bar, const float* ctx_c,
-                       float* scratch, float* const* dparams, void* stream) {
+int nudf_nerf_backward(const nudf_nerf_desc* d, const float* wimg, int64_t P, const float* sigma_bar, const float* rgb_bar,
+                       const float* ctx_c, float* scratch, float* const* dparams, void* stream) {
   NerfPlan p;
   if (int rc = nerf_plan(d, &p)) return rc;
   NUDF_REQUIRE(sigma_bar && rgb_bar && ctx_c && scratch && dparams, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  const uint16_t* img = reinterpret_cast<const uint16_t*>(wimg);
   const int D = p.D, W = p.W, W2 = p.W / 2;
   float* const* dpts = dparams;                 // [2*i], [2*i+1]
   float* dviews_w = dparams[2 * D + 0]; float* dviews_b = dparams[2 * D + 1];
@@ -581,7 +618,7 @@ int nudf_nerf_backward(const nudf_nerf_desc* d, int64_t P, const float* sigma_ba
   float* dfeat = scratch + s.buf[0];
   {
     EpiReluBwd e{0, W, nullptr, 0, dfeat, W, 0};
-    if (int rc = gemm_nn(dzv, W2, d->views_w, W + p.chv, P, W + p.chv, W2, e, st)) return rc;
+    if (int rc = gemm_nn(dzv, W2, d->views_w, W + p.chv, P, W + p.chv, W2, e, st, img ? img + p.iviews_nn : nullptr, TC_NERF)) return rc;
   }
   // feature + alpha heads -> dZ of the last pts layer
   int64_t ldl;
@@ -593,7 +630,7 @@ int nudf_nerf_backward(const nudf_nerf_desc* d, int64_t P, const float* sigma_ba
     EpiReluBwd e0{0, W, nullptr, 0, dz, W, 0};
     if (int rc = gemm_nn(sigma_bar, 1, d->alpha_w, W, P, W, 1, e0, st)) return rc;
     EpiReluBwd e1{0, W, Hl, ldl, dz, W, 1};
-    if (int rc = gemm_nn(dfeat, W, d->feature_w, W, P, W, W, e1, st)) return rc;
+    if (int rc = gemm_nn(dfeat, W, d->feature_w, W, P, W, W, e1, st, img ? img + p.ifeat_nn : nullptr, TC_NERF)) return rc;
   }
   int flip = 0;  // dz lives in buf[1]; next output goes to buf[0]
   for (int i = D - 1; i >= 0; --i) {
@@ -606,7 +643,7 @@ int nudf_nerf_backward(const nudf_nerf_desc* d, int64_t P, const float* sigma_ba
     const float* Hprev = nerf_h(p, ctx, c, i - 1, &ldh);
     int col_lo = (i - 1 == p.skip) ? p.ch : 0;
     EpiReluBwd e{col_lo, col_lo + W, Hprev, ldh, out, W, 0};
-    if (int rc = gemm_nn(dz, W, d->pts_w[i], p.in_dim[i], P, p.in_dim[i], W, e, st)) return rc;
+    if (int rc = gemm_nn(dz, W, d->pts_w[i], p.in_dim[i], P, p.in_dim[i], W, e, st, img ? img + p.ipts_nn[i] : nullptr, TC_NERF)) return rc;
     dz = out; flip ^= 1;
   }
   return 0;

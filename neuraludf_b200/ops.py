@@ -56,7 +56,7 @@ class UdfHandle:
     def refresh(self):
         ps = self.params()
         _require_cuda(*ps)
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (L.lib().nudf_get_engine(),)
         if key == self._key:
             return
         d = L.UdfDesc()
@@ -179,7 +179,7 @@ class ColorHandle:
     def refresh(self):
         ps = self.params()
         _require_cuda(*ps)
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (L.lib().nudf_get_engine(),)
         if key == self._key:
             return
         d = L.ColorDesc()
@@ -277,6 +277,24 @@ class NerfHandle:
     def __init__(self, module, D, W, d_in, multires, multires_view, skip):
         self.m = module
         self.meta = (D, W, d_in, multires, multires_view, skip)
+        self._key = None
+        self.wimg = None
+
+    def images(self):
+        """bf16 hi/lo weight images for the tensor engine, rebuilt when a parameter changed (None on the fp32 engine)."""
+        lib = L.lib()
+        if lib.nudf_get_engine() != 1 or not (lib.nudf_get_tc_mask() & 64):
+            return None
+        ps = self.params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._key:
+            d = self.desc()
+            n = lib.nudf_nerf_image_floats(ctypes.byref(d))
+            if self.wimg is None or self.wimg.numel() != n or self.wimg.device != ps[0].device:
+                self.wimg = torch.empty(n, dtype=torch.float32, device=ps[0].device)
+            L.check(lib.nudf_nerf_prepare(ctypes.byref(d), L.ptr(self.wimg), L.stream_ptr()), "nudf_nerf_prepare")
+            self._key = key
+        return self.wimg
 
     def params(self):
         m = self.m
@@ -316,9 +334,10 @@ class _NerfFunction(torch.autograd.Function):
         rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
         n = lib.nudf_nerf_ctx_floats(ctypes.byref(d), P)
         buf = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
-        L.check(lib.nudf_nerf_forward(ctypes.byref(d), L.ptr(pts), L.ptr(dirs), int(samples_per_ray), P, L.ptr(sigma),
-                                      L.ptr(rgb), L.ptr(buf), L.stream_ptr()), "nudf_nerf_forward")
-        ctx.handle, ctx.P = handle, P
+        wimg = handle.images()
+        L.check(lib.nudf_nerf_forward(ctypes.byref(d), L.ptr(wimg), L.ptr(pts), L.ptr(dirs), int(samples_per_ray), P,
+                                      L.ptr(sigma), L.ptr(rgb), L.ptr(buf), L.stream_ptr()), "nudf_nerf_forward")
+        ctx.handle, ctx.P, ctx.wimg = handle, P, wimg
         ctx.versions = tuple(p._version for p in params)
         ctx.save_for_backward(buf, *params)
         return sigma, rgb
@@ -335,8 +354,8 @@ class _NerfFunction(torch.autograd.Function):
         n = lib.nudf_nerf_scratch_floats(ctypes.byref(d), P)
         scratch = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
         grads = [torch.empty_like(p) for p in params]
-        L.check(lib.nudf_nerf_backward(ctypes.byref(d), P, L.ptr(sigma_bar), L.ptr(rgb_bar), L.ptr(buf), L.ptr(scratch),
-                                       _ptr_array(grads), L.stream_ptr()), "nudf_nerf_backward")
+        L.check(lib.nudf_nerf_backward(ctypes.byref(d), L.ptr(ctx.wimg), P, L.ptr(sigma_bar), L.ptr(rgb_bar), L.ptr(buf),
+                                       L.ptr(scratch), _ptr_array(grads), L.stream_ptr()), "nudf_nerf_backward")
         return (None, None, None, None) + tuple(grads)
 
 
