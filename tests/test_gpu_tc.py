@@ -135,3 +135,70 @@ def test_render_core_accuracy_by_tc_mask(golden, mask):
     finally:
         lib.nudf_set_engine(old_engine)
         lib.nudf_set_tc_mask(old_mask)
+
+
+def test_nerf_and_color_on_tensor_engine_vs_oracle(golden):
+    """NeRF++ and colour networks with the tensor engine enabled (default chain mask) against fp64 oracle autograd."""
+    from oracle import oracle_torch as O
+    from tests.gpu_util import oracle_params
+    L, lib = _lib()
+    old_engine, old_mask = lib.nudf_get_engine(), lib.nudf_get_tc_mask()
+    lib.nudf_set_engine(1)
+    lib.nudf_set_tc_mask(126)
+    try:
+        g = golden
+        _, col, nerf, _, _ = build_modules(g, DEV)
+        gen = torch.Generator().manual_seed(21)
+        P = 700
+        pts4 = torch.randn(P, 4, generator=gen, dtype=torch.float64)
+        pts4 = pts4 / pts4[:, :3].norm(dim=1, keepdim=True)
+        dirs = torch.randn(P, 3, generator=gen, dtype=torch.float64)
+        dirs = dirs / dirs.norm(dim=1, keepdim=True)
+        ab = torch.randn(P, 1, generator=gen, dtype=torch.float64)
+        rb = torch.randn(P, 3, generator=gen, dtype=torch.float64)
+        p64 = oracle_params(g, "nerf", torch.float64, True)
+        oa, orgb = O.nerf_mlp(p64, g.nerf_c, pts4, dirs)
+        gr = dict(zip(p64.keys(), torch.autograd.grad((oa * ab).sum() + (orgb * rb).sum(), list(p64.values()))))
+        a, rgb = nerf(pts4.float().to(DEV), dirs.float().to(DEV))
+        parity("tc.nerf.alpha", a, oa, None, tol=1e-4)
+        parity("tc.nerf.rgb", rgb, orgb, None, tol=1e-4)
+        ((a * ab.float().to(DEV)).sum() + (rgb * rb.float().to(DEV)).sum()).backward()
+        for k, v in nerf.named_parameters():
+            parity("tc.nerf.dparam." + k, v.grad, gr[k], None, tol=5e-4)
+        # colour network
+        pts = g.t("col_pts").to(DEV); d3 = g.t("col_dirs").to(DEV); feat = g.t("col_feat").to(DEV).requires_grad_(True)
+        cb, c, bl = col(pts, None, d3, feat)
+        parity("tc.color.base", cb, g.t("col_base_f64"), None, tol=1e-4)
+        parity("tc.color.color", c, g.t("col_color_f64"), None, tol=1e-4)
+        parity("tc.color.blend", bl, g.t("col_blend_f64"), None, tol=1e-4)
+        bars = [torch.randn(t.shape, generator=gen, dtype=torch.float64) for t in (cb, c, bl)]
+        pc = oracle_params(g, "color", torch.float64, True)
+        f64 = g.t("col_feat", torch.float64).clone().requires_grad_(True)
+        o = O.color_mlp(pc, g.col_c, g.t("col_pts", torch.float64), g.t("col_dirs", torch.float64), f64)
+        grc = torch.autograd.grad(sum((x * b).sum() for x, b in zip(o, bars)), list(pc.values()) + [f64])
+        grc = dict(zip(list(pc.keys()) + ["feat"], grc))
+        sum((x * b.float().to(DEV)).sum() for x, b in zip((cb, c, bl), bars)).backward()
+        parity("tc.color.dfeat", feat.grad, grc["feat"], None, tol=5e-4)
+        for k, v in col.named_parameters():
+            parity("tc.color.dparam." + k, v.grad, grc[k], None, tol=5e-4)
+    finally:
+        lib.nudf_set_engine(old_engine)
+        lib.nudf_set_tc_mask(old_mask)
+
+
+def test_degenerate_sizes():
+    """empty / single-point / ragged inputs go through both engines without touching memory they should not"""
+    L, lib = _lib()
+    from neuraludf_b200.models import fields as F
+    for engine in (0, 1):
+        lib.nudf_set_engine(engine)
+        udf = F.UDFNetwork(d_in=3, d_out=257, d_hidden=64, n_layers=4, skip_in=(2,), multires=6).to(DEV)
+        for P in (0, 1, 127, 129, 130):
+            x = torch.rand(P, 3, device=DEV) - 0.5
+            out, grad = udf.value_and_gradient(x)
+            assert out.shape == (P, 257) and grad.shape == (P, 3)
+            assert torch.isfinite(out).all() and torch.isfinite(grad).all()
+            if P > 0:
+                (out.sum() + grad.sum()).backward()
+                assert all(torch.isfinite(p.grad).all() for p in udf.parameters())
+    lib.nudf_set_engine(1)
