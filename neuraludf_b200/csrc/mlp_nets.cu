@@ -323,9 +323,9 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
                        float* color, float* blend, float* ctx, void* stream) {
   ColorPlan p;
   if (int rc = color_plan(d, &p)) return rc;
+  if (P <= 0) return 0;
   NUDF_REQUIRE(wfold && pts && dirs && feat && ctx, "null pointer");
   NUDF_REQUIRE(ld_feat >= p.F, "ld_feat too small");
-  if (P <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int spr = samples_per_ray > 0 ? samples_per_ray : 1;
   ColorCtx c;
@@ -575,8 +575,8 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* wimg, const float* p
                       int64_t P, float* sigma, float* rgb, float* ctx, void* stream) {
   NerfPlan p;
   if (int rc = nerf_plan(d, &p)) return rc;
-  NUDF_REQUIRE(pts && dirs && sigma && rgb && ctx, "null pointer");
   if (P <= 0) return 0;
+  NUDF_REQUIRE(pts && dirs && sigma && rgb && ctx, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int spr = samples_per_ray > 0 ? samples_per_ray : 1;
   NerfCtx c;

@@ -433,9 +433,9 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
                      float* grad, float* ctx, void* stream) {
   UdfPlan p;
   if (int rc = make_plan(d, &p)) return rc;
+  if (P <= 0) return 0;
   NUDF_REQUIRE(wfold && pts && ctx, "null pointer");
   NUDF_REQUIRE(out == nullptr || ld_out >= p.d_out, "ld_out too small");
-  if (P <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   UdfCtx c;
   ctx_layout(p, P, grad != nullptr, &c);
@@ -451,8 +451,8 @@ int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts,
                    void* stream) {
   UdfPlan p;
   if (int rc = make_plan(d, &p)) return rc;
-  NUDF_REQUIRE(wfold && pts && work && udf, "null pointer");
   if (P <= 0) return 0;
+  NUDF_REQUIRE(wfold && pts && work && udf, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   UdfCtx c;
   ctx_layout(p, P, 0, &c);
@@ -471,11 +471,12 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
                       float* dbias, void* stream) {
   UdfPlan p;
   if (int rc = make_plan(d, &p)) return rc;
-  NUDF_REQUIRE(wfold && pts && ctx_c && scratch && dwfold && dbias, "null pointer");
+  NUDF_REQUIRE(wfold && dwfold && dbias, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   NUDF_CUDA_OK(cudaMemsetAsync(dwfold, 0, sizeof(float) * p.w_total, st));
   NUDF_CUDA_OK(cudaMemsetAsync(dbias, 0, sizeof(float) * p.b_total, st));
   if (P <= 0) return 0;
+  NUDF_REQUIRE(pts && ctx_c && scratch, "null pointer");
   float* ctx = const_cast<float*>(ctx_c);  // read-only use
   UdfCtx c;
   ctx_layout(p, P, 1, &c);
