@@ -205,6 +205,7 @@ int nudf_render_composite_forward(const nudf_render_cfg* cfg, const float* heads
 typedef struct nudf_render_bar {   /* upstream gradients, any may be NULL */
   const float* color_base; const float* color; const float* depth;       /* [N,3] [N,3] [N,1] */
   const float* weight_sum; const float* weight_sum_fg_bg;                 /* [N,1] */
+  const float* weights;  /* [N,S+O] d loss / d weights (pixel / patch blending composites are formed from `weights`) */
   const float* ray_sums; /* [N,5] d loss / d ray_sums (columns 1 and 3, the detached mask counts, are ignored) */
 } nudf_render_bar;
 

@@ -56,7 +56,8 @@ class RenderOut(ctypes.Structure):
 
 
 class RenderBar(ctypes.Structure):
-    _fields_ = [(n, c_void_p) for n in ("color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "ray_sums")]
+    _fields_ = [(n, c_void_p) for n in ("color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "weights",
+                                        "ray_sums")]
 
 
 _lib = None

@@ -274,6 +274,7 @@ struct RayBwdOut {
 };
 struct RayBar {
   const float* color_base; const float* color; const float* depth; const float* weight_sum; const float* weight_sum_fg_bg;
+  const float* weights;   // [N, S+O] or null
   const float* ray_sums;  // [N,5] upstream gradient of the per-ray regulariser sums
 };
 
@@ -314,6 +315,7 @@ composite_backward_kernel(nudf_render_cfg cfg, RayIn in, RayBar bar, RayBwdOut o
   for (int i = lane; i < SO; i += 32) {
     float w = sm.alpha[i] * sm.T[i];
     float wb = wsall_b;
+    if (bar.weights) wb += bar.weights[(int64_t)r * SO + i];
     if (i < S) {
       const int64_t p = base + i;
       float dcb = 0.f, dcc = 0.f;
@@ -501,6 +503,7 @@ int nudf_render_composite_backward(const nudf_render_cfg* cfg, const float* head
   RayBar rb;
   rb.color_base = bar->color_base; rb.color = bar->color; rb.depth = bar->depth; rb.weight_sum = bar->weight_sum;
   rb.weight_sum_fg_bg = bar->weight_sum_fg_bg;
+  rb.weights = bar->weights;
   rb.ray_sums = bar->ray_sums;
   RayBwdOut ob{udf_bar, grads_bar, scb_bar, sc_bar, bg_alpha_bar, bg_color_bar, scalar_bar};
   size_t smem = (size_t)RK_WARPS * RK_ARRAYS * (cfg->n_samples + cfg->n_outside) * sizeof(float);

@@ -7,15 +7,18 @@ Differences that are deliberate (DESIGN.md "boundary"):
   * importance sampling, compositing and the regulariser sums never synchronise with the host (the reference has 13
     blocking syncs per step); NaNs raise a RuntimeError at the end of render() instead of dropping into pdb;
   * `render()` evaluates the NeRF++ background only on the n_outside samples render_core consumes (:493-501);
-  * per-sample outputs (`weights`, `gradients`, `alpha*`, ...) are returned detached -- the trainer only uses them
-    after .detach() or for logging (exp_runner_blending.py:309-371, 641-668).
-Pixel / patch blending inputs (fine-tuning stage, :431-480) are not implemented yet and raise NotImplementedError.
+  * per-sample outputs (`gradients`, `alpha*`, ...) are returned detached -- the trainer only uses them after
+    .detach() or for logging (exp_runner_blending.py:309-371, 641-668); `weights` is differentiable.
+Pixel / patch blending (fine-tuning stage, :431-480) warps and blends with torch ops on the GPU (patch_projector.py,
+fields.color_blend) and composites with the differentiable ray weights of the CUDA compositing kernel.
 """
 import numpy as np
 import torch
 import torch.nn.functional as F
 
 from .. import ops
+from .fields import color_blend
+from .patch_projector import PatchProjector
 
 
 def extract_fields(bound_min, bound_max, resolution, query_func, device):
@@ -95,6 +98,7 @@ class UDFRendererBlending:
         self.upsampling_type = upsampling_type
         self.sparse_scale_factor = sparse_scale_factor
         self.h_patch_size = h_patch_size
+        self.patch_projector = PatchProjector(self.h_patch_size)
         self.use_norm_grad_for_cosine = use_norm_grad_for_cosine
         self.want_diagnostics = True     # per-sample dict entries (consumed only by validate / visualize_one_ray)
 
@@ -197,9 +201,6 @@ class UDFRendererBlending:
                     beta_network=None, cos_anneal_ratio=None, background_rgb=None, background_alpha=None,
                     background_sampled_color=None, flip_saturation=0.0, color_maps=None, w2cs=None, intrinsics=None,
                     query_c2w=None, img_index=None, rays_uv=None):
-        if color_maps is not None or rays_uv is not None:
-            raise NotImplementedError("pixel / patch blending (fine-tuning stage, reference :431-480) is the next row of "
-                                      "the scope table (SURVEY 8(f) rank 1) and not implemented yet")
         device = z_vals.device
         batch_size, n_samples = z_vals.shape
         rays_o = rays_o.float().contiguous()
@@ -233,9 +234,13 @@ class UDFRendererBlending:
         sparse_error = rs[:, 4].sum() / batch_size
 
         g3 = gradients.detach().reshape(batch_size, n_samples, 3)
+        blending_weights = blending_weights.reshape(batch_size, n_samples, -1)
+        color_pixel, patch_colors, patch_mask = self._blend(
+            comp['weights'], pts, rays_d, g3, blending_weights, background_sampled_color, color_maps, w2cs, intrinsics,
+            query_c2w, img_index, rays_uv)
         ret = {
-            'color_base': comp['color_base'], 'color': comp['color'], 'color_pixel': None, 'patch_colors': None,
-            'patch_mask': None, 'weights': comp['weights'],
+            'color_base': comp['color_base'], 'color': comp['color'], 'color_pixel': color_pixel,
+            'patch_colors': patch_colors, 'patch_mask': patch_mask, 'weights': comp['weights'],
             's_val': (1.0 / inv_s).expand(batch_size * n_samples, 1), 'beta': 1.0 / beta, 'gamma': gamma,
             'depth': comp['depth'], 'gradient_error': gradient_error,
             'gradient_error_near_surface': gradient_error_near_surface, 'normals': comp['normals'], 'gradients': g3,
@@ -243,12 +248,48 @@ class UDFRendererBlending:
             'sparse_error': sparse_error,
             # extra (not in the reference dict): differentiable per-ray weight sums, blending logits
             'weight_sum': comp['weight_sum'], 'weight_sum_fg_bg': comp['weight_sum_fg_bg'],
-            'blending_weights': blending_weights.reshape(batch_size, n_samples, -1),
+            'blending_weights': blending_weights,
         }
         for k in ('gradients_flip', 'inside_sphere', 'gradient_mag', 'true_cos', 'vis_prob', 'alpha', 'alpha_plus',
                   'alpha_minus', 'alpha_occ', 'raw_occ'):
             ret[k] = comp.get(k)
         return ret
+
+    def _blend(self, weights, pts, rays_d, g3, blending_weights, background_sampled_color, color_maps, w2cs, intrinsics,
+               query_c2w, img_index, rays_uv):
+        """Pixel / patch blending of the fine-tuning stage (reference :431-480 and :503-524): colours warped from the
+        source views, blended per sample with the colour network's logits and composited with the ray weights (which
+        carry the gradient to the UDF through nudf_render_composite_backward's `weights` adjoint)."""
+        if color_maps is None and rays_uv is None:
+            return None, None, None
+        if color_maps is None:
+            raise ValueError("patch blending (rays_uv) needs color_maps as well (the reference fails here too, "
+                             "fields.py:505)")
+        batch_size, n_samples = g3.shape[:2]
+        p3 = pts.reshape(batch_size, n_samples, 3)
+        pix_col, pix_mask = self.patch_projector.pixel_warp(p3, color_maps, intrinsics, w2cs, img_wh=None)
+        pat_col, pat_mask = None, None
+        if rays_uv is not None:
+            gn = g3 / (torch.linalg.norm(g3, ord=2, dim=-1, keepdim=True) + 1e-5)
+            cos = (rays_d[:, None, :] * gn).sum(-1, keepdim=True)
+            flip_sign = torch.where(cos == 0, torch.ones_like(cos), -torch.sign(cos))
+            pat_col, pat_mask = self.patch_projector.patch_warp(
+                p3, rays_uv, flip_sign * gn, color_maps, intrinsics[0], intrinsics, query_c2w, torch.inverse(w2cs),
+                img_wh=None, detach_normal=True)
+        c_pix, _, c_pat, m_pat = color_blend(blending_weights, img_index=img_index, pts_pixel_color=pix_col,
+                                             pts_pixel_mask=pix_mask, pts_patch_color=pat_col, pts_patch_mask=pat_mask)
+        c_pix = c_pix.view(batch_size, n_samples, 3)
+        if background_sampled_color is not None:
+            inside = (torch.linalg.norm(p3, ord=2, dim=-1) < 1.0).float()[:, :, None]
+            c_pix = c_pix * inside + background_sampled_color[:, :n_samples] * (1.0 - inside)
+            c_pix = torch.cat([c_pix, background_sampled_color[:, n_samples:]], dim=1)
+        color_pixel = (c_pix * weights[:, :c_pix.shape[1], None]).sum(dim=1)
+        patch_colors, patch_mask = None, None
+        if c_pat is not None:
+            w_in = weights[:, :n_samples]
+            patch_colors = (c_pat.view(batch_size, n_samples, -1, 3) * w_in[:, :, None, None]).sum(dim=1)
+            patch_mask = (m_pat.view(batch_size, n_samples).float() * w_in).sum(dim=1)
+        return color_pixel, patch_colors, patch_mask
 
     # ------------------------------------------------------------------------------------------------------------
     # whole render (reference :586-721)
@@ -298,10 +339,15 @@ class UDFRendererBlending:
         if self.n_outside > 0:
             z_out = z_vals_outside.expand(batch_size, -1) if z_vals_outside.shape[0] != batch_size else z_vals_outside
             z_vals_feed, _ = torch.sort(torch.cat([z_vals, z_out], dim=-1), dim=-1)
-            # only the outside columns are consumed by render_core (:493-501)
-            a_o, c_o = self._outside(rays_o, rays_d, z_vals_feed.contiguous(), sample_dist, self.nerf, n_samples)
-            background_alpha = torch.cat([torch.zeros(batch_size, n_samples, device=device), a_o], dim=1)
-            background_sampled_color = torch.cat([torch.zeros(batch_size, n_samples, 3, device=device), c_o], dim=1)
+            if color_maps is None:
+                # only the outside columns are consumed by render_core (:493-501)
+                a_o, c_o = self._outside(rays_o, rays_d, z_vals_feed.contiguous(), sample_dist, self.nerf, n_samples)
+                background_alpha = torch.cat([torch.zeros(batch_size, n_samples, device=device), a_o], dim=1)
+                background_sampled_color = torch.cat([torch.zeros(batch_size, n_samples, 3, device=device), c_o], dim=1)
+            else:
+                # pixel blending mixes the NeRF colour of the inside columns into color_pixel outside the sphere (:507)
+                background_alpha, background_sampled_color = self._outside(
+                    rays_o, rays_d, z_vals_feed.contiguous(), sample_dist, self.nerf, 0)
 
         ret_fine = self.render_core(rays_o, rays_d, z_vals, sample_dist, self.udf_network, self.deviation_network,
                                     self.color_network, beta_network=self.beta_network,

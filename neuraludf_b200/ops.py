@@ -436,7 +436,7 @@ class _CompositeFunction(torch.autograd.Function):
         ctx.cfg, ctx.geom, ctx.ld_udf = cfg, geom, ld_udf
         ctx.has_bg = bg_alpha is not None
         ctx.save_for_backward(udf, grads, scb, sc, bg_alpha, bg_color, heads)
-        diff = ("color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "ray_sums")
+        diff = ("color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "ray_sums", "weights")
         nondiff = [outs[k] for k in outs if k not in diff]
         ctx.mark_non_differentiable(*nondiff)
         ctx.n_extra = len(nondiff)
@@ -444,7 +444,7 @@ class _CompositeFunction(torch.autograd.Function):
         return tuple(outs[k] for k in diff) + tuple(nondiff)
 
     @staticmethod
-    def backward(ctx, cb_bar, c_bar, depth_bar, ws_bar, wsa_bar, rs_bar, *unused):
+    def backward(ctx, cb_bar, c_bar, depth_bar, ws_bar, wsa_bar, rs_bar, w_bar, *unused):
         lib = L.lib()
         udf, grads, scb, sc, bg_alpha, bg_color, heads = ctx.saved_tensors
         cfg = ctx.cfg
@@ -455,7 +455,7 @@ class _CompositeFunction(torch.autograd.Function):
         bar = L.RenderBar()
         keep = []
         for name, t in (("color_base", cb_bar), ("color", c_bar), ("depth", depth_bar), ("weight_sum", ws_bar),
-                        ("weight_sum_fg_bg", wsa_bar), ("ray_sums", rs_bar)):
+                        ("weight_sum_fg_bg", wsa_bar), ("ray_sums", rs_bar), ("weights", w_bar)):
             t = _f32c(t)
             keep.append(t)
             setattr(bar, name, None if t is None else t.data_ptr())
@@ -479,7 +479,7 @@ class _CompositeFunction(torch.autograd.Function):
 
 def composite(udf, grads, scb, sc, bg_alpha, bg_color, heads, geom, cfg, want_diag=True):
     res = _CompositeFunction.apply(udf, grads, scb, sc, bg_alpha, bg_color, heads, geom, cfg, want_diag)
-    names = ["color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "ray_sums", "normals", "weights"]
+    names = ["color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "ray_sums", "weights", "normals"]
     if want_diag:
         names += DIAG_KEYS + ["gradients_flip"]
     return dict(zip(names, res))

@@ -54,6 +54,10 @@ def _randn(gen, *shape):
     return torch.randn(*shape, generator=gen, dtype=torch.float64)
 
 
+def _rand(gen, *shape):
+    return torch.rand(*shape, generator=gen, dtype=torch.float64)
+
+
 def make_udf_params(cfg, seed=0, noise=1e-3):
     """Geometric initialisation, models/fields.py:156-173, then weight-norm split (g = row norms)
     and a small perturbation so that the scene is not exactly a sphere."""
@@ -145,3 +149,58 @@ def make_rays(n_rays, seed=0):
     return o.float(), d.float(), (mid - 1.0).float(), (mid + 1.0).float()
 
 
+def _look_at(cam_pos):
+    """OpenCV-convention camera-to-world matrix (x right, y down, z forward) of a camera at cam_pos looking at 0."""
+    z = -cam_pos / cam_pos.norm()
+    up = torch.tensor([0.0, 0.0, 1.0], dtype=cam_pos.dtype)
+    if abs(float((z * up).sum())) > 0.95:
+        up = torch.tensor([0.0, 1.0, 0.0], dtype=cam_pos.dtype)
+    x = torch.linalg.cross(z, up)
+    x = x / x.norm()
+    y = torch.linalg.cross(z, x)
+    c2w = torch.eye(4, dtype=cam_pos.dtype)
+    c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = x, y, z, cam_pos
+    return c2w
+
+
+def make_blend_views(n_rays, n_views=6, height=48, width=64, seed=0):
+    """A query camera plus n_views source views around it for the pixel / patch blending stage (config C3): the inputs
+    exp_runner_blending.py:270-306 takes from dataset/dataset.py -- rays of random query pixels, their normalised uv,
+    source images (smooth synthetic textures), world-to-camera matrices and a shared 4x4 intrinsic matrix."""
+    gen = torch.Generator().manual_seed(2000 + seed)
+    q = _randn(gen, 3)
+    q = 2.5 * q / q.norm()
+    focal = 1.1 * width
+    K = torch.eye(4, dtype=torch.float64)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = focal, focal, (width - 1) / 2.0, (height - 1) / 2.0
+    query_c2w = _look_at(q.double())
+    c2ws = []
+    for _ in range(n_views):
+        p = q.double() + 0.9 * _randn(gen, 3).double()
+        c2ws.append(_look_at(2.5 * p / p.norm()))
+    c2ws = torch.stack(c2ws)
+    w2cs = torch.inverse(c2ws)
+    # rays through random (non-integer) pixels of the query image, kept 6 px away from the border
+    u = 6 + _rand(gen, n_rays).double() * (width - 13)
+    v = 6 + _rand(gen, n_rays).double() * (height - 13)
+    pix = torch.stack([u, v, torch.ones_like(u)], dim=-1)
+    d_cam = pix @ torch.inverse(K[:3, :3]).T
+    d = d_cam @ query_c2w[:3, :3].T
+    d = d / d.norm(dim=1, keepdim=True)
+    o = query_c2w[:3, 3].expand(n_rays, 3).clone()
+    b = 2.0 * (o * d).sum(-1, keepdim=True)
+    mid = 0.5 * (-b)
+    uv = torch.stack([2 * u / (width - 1) - 1, 2 * v / (height - 1) - 1], dim=-1)
+    # smooth textures: a few random plane waves per channel, in (0,1)
+    yy, xx = torch.meshgrid(torch.arange(height, dtype=torch.float64), torch.arange(width, dtype=torch.float64),
+                            indexing="ij")
+    imgs = torch.zeros(n_views, 3, height, width, dtype=torch.float64)
+    for k in range(4):
+        fx = (_rand(gen, n_views, 3, 1, 1).double() - 0.5) * 0.6
+        fy = (_rand(gen, n_views, 3, 1, 1).double() - 0.5) * 0.6
+        ph = _rand(gen, n_views, 3, 1, 1).double() * 6.28318
+        imgs = imgs + torch.sin(fx * xx + fy * yy + ph) / 8.0
+    imgs = imgs + 0.5
+    return {"rays_o": o.float(), "rays_d": d.float(), "near": (mid - 1.0).float(), "far": (mid + 1.0).float(),
+            "rays_uv": uv.float(), "color_maps": imgs.float(), "w2cs": w2cs.float(),
+            "intrinsics": K.float().expand(n_views, 4, 4).contiguous(), "query_c2w": query_c2w.float()}

@@ -21,8 +21,8 @@ import torch.nn.functional as F
 
 # scene / shape generators live in the (kernel-free) product utility module so that bench.py's CUDA arm does not
 # import the oracle; re-exported here for the tests.
-from neuraludf_b200.synthetic import (color_cfg, make_color_params, make_nerf_params, make_rays,  # noqa: E402,F401
-                                      make_scalars, make_udf_params, nerf_cfg, udf_cfg)
+from neuraludf_b200.synthetic import (color_cfg, make_blend_views, make_color_params,  # noqa: E402,F401
+                                      make_nerf_params, make_rays, make_scalars, make_udf_params, nerf_cfg, udf_cfg)
 
 
 def to_dtype(params, dtype):

@@ -323,7 +323,7 @@ def test_render_core_vs_reference(golden, case):
     tgt = torch.full((64, 3), 0.4, device=DEV)
     loss = ((ret["color"] - tgt).abs().mean() + 0.01 * (ret["color_base"] - tgt).abs().mean()
             + 0.1 * ret["gradient_error"] + 1e-3 * ret["sparse_error"] + 0.05 * ret["gradient_error_near_surface"]
-            + 0.1 * ((ret["weight_sum"][:, 0] - 0.5) ** 2).mean())
+            + 0.1 * (((ret["weights"][:, :S].sum(-1) if case == "rc" else ret["weight_sum"][:, 0]) - 0.5) ** 2).mean())
     parity(case + ".loss", loss, g.t(case + "_loss_f64"), g.t(case + "_loss_f32"), tol=2e-4)
     loss.backward()
     # parameter gradients: fp64 reference is the arbiter; the fp32 reference itself is only good to ~2e-3 here
