@@ -16,6 +16,7 @@ step driven from pinned HOST buffers through the public module API with the H2D 
 the host cores; under torchrun only rank 0 works.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -99,19 +100,34 @@ def rays(seed, device=None):
 
 
 class Clocks:
+    """nvidia-smi sampler (B200_PROFILING.md clocks line).  Started BEFORE the warm-up (nvidia-smi needs ~0.2 s to come
+    up), every sample is time-stamped, and only the samples inside the [begin(), end()] wall-clock window -- the timed
+    region -- are reported."""
+
     def __init__(self, idx):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.t0 = self.t1 = None
+        q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "10"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def begin(self):
+        deadline = time.time() + 2.0            # the first sample must exist before the timed region starts
+        while self.p is not None and os.path.getsize(self.f.name) == 0 and time.time() < deadline:
+            time.sleep(0.01)
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -120,19 +136,26 @@ class Clocks:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.strip().lower() == "active":
-                        reasons.add(n)
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
+                parsed.append((ts, float(r[1]), float(r[2]), [n for n, v in zip(names, r[3:7])
+                                                               if v.strip().lower() == "active"]))
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        slack = datetime.timedelta(milliseconds=15)
+        inside = [x for x in parsed if self.t0 is not None and self.t0 - slack <= x[0] <= self.t1 + slack]
+        window = "timed region"
+        if not inside and parsed and self.t0 is not None:
+            # region shorter than the sampling period: the sample closest to it
+            inside = [min(parsed, key=lambda x: abs((x[0] - self.t0).total_seconds()))]
+            window = "nearest sample (timed region shorter than the sampling period)"
+        sm = sorted(x[1] for x in inside)
+        reasons = sorted({n for x in inside for n in x[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(x[2] for x in inside) if inside else None,
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def loss_fn(ret, tgt):
@@ -180,18 +203,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = Clocks(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step(o, d, z)
     barrier()
-    clocks = Clocks(local) if rank == 0 else None
     l0 = lib.nudf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if clocks:
+        clocks.begin()
     barrier()
     e0.record()
     for _ in range(args.steps):
         step(o, d, z)
     e1.record()
     barrier()
+    if clocks:
+        clocks.end()
     ms = e0.elapsed_time(e1)
     launches = lib.nudf_launch_count() - l0
     clk = clocks.stop() if clocks else None

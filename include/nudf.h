@@ -28,9 +28,10 @@ const char* nudf_last_error(void);
  * when built with the tensor path).  Small / odd-shaped contractions always use the FFMA engine. */
 int nudf_set_engine(int engine);
 int nudf_get_engine(void);
-/* Which contraction chains may use the tensor engine (bit mask; default 62 = everything but the forward value chain,
- * whose udf head feeds exp(-25000 u) and needs fp32-grade accuracy): 1 forward value, 2 reverse sweep (grad_x udf),
- * 4 tangent, 8 backward, 16 weight gradients, 32 colour network, 64 NeRF. */
+/* Which contraction chains may use the tensor engine (bit mask; default 126 = everything but the forward value chains:
+ * the udf head feeds exp(-25000 u) and needs fp32-grade accuracy, and the ReLU gates of the colour / NeRF++ networks
+ * must not flip more often than under fp32 rounding): 1 UDF forward value, 2 reverse sweep (grad_x udf), 4 tangent,
+ * 8 backward, 16 weight gradients, 32 colour-network backward, 64 NeRF++ backward, 128 colour / NeRF++ forward. */
 int nudf_set_tc_mask(int mask);
 int nudf_get_tc_mask(void);
 /* --- tensor engine building blocks (unit-tested on their own) ---
@@ -44,6 +45,18 @@ int nudf_dense_forward_tc(const float* X, int64_t ldx, const uint16_t* img, int3
 /* dW[n_out, n_in] += dZ[P, n_out]^T X[P, n_in]  (engine 0: fp32 FFMA, 1: tcgen05) */
 int nudf_wgrad(const float* dZ, int64_t ldz, const float* X, int64_t ldx, int32_t n_out, int32_t n_in, int64_t P,
                float* dW, int64_t ldw, int32_t engine, void* stream);
+
+/* Split-bf16 plane tensors (csrc/gemm_pl.cuh): a fp32 matrix [rows x cols] stored as hi = bf16(x), lo = bf16(x - hi) in
+ * 64 x 64 blocks, [row block][col block][plane][64 rows x 128 B SWIZZLE_128B]; 1024-byte aligned; pad rows are zero.
+ * The tcgen05 kernels fetch these blocks with cp.async.bulk and use them as K-major (layer chains) or MN-major
+ * (weight gradients) operands without conversion.  nudf_planes_elems: uint16 elements to allocate. */
+int64_t nudf_planes_elems(int64_t rows, int32_t cols);
+int nudf_pack_planes(const float* X, int64_t ldx, int64_t rows, int32_t cols, uint16_t* planes, void* stream);
+int nudf_unpack_planes(const uint16_t* planes, int64_t rows, int32_t cols, float* X, int64_t ldx, void* stream);
+/* dW[n_out, n_in] += dZ[P, n_out]^T X[P, n_in], both operands plane tensors (replaces the autograd weight gradient of one
+ * nn.Linear, models/fields.py:185; tensor engine only). */
+int nudf_wgrad_planes(const uint16_t* dZ_planes, const uint16_t* X_planes, int32_t n_out, int32_t n_in, int64_t P, float* dW,
+                      int64_t ldw, void* stream);
 /* profiling aid: with NUDF_TC_DEBUG & 16 the persistent tensor kernel records clock64() stamps of CTA 0 (4 roles x 256) */
 int nudf_tc_read_trace(long long* host_buf);
 /* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */

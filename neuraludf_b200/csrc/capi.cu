@@ -21,7 +21,8 @@ void set_error(const char* fmt, ...) {
 }
 
 // NUDF_TC_MASK: which chains may run on the tensor engine (bits: 1 fwd value, 2 reverse sweep, 4 tangent, 8 backward,
-// 16 weight gradients, 32 colour net, 64 NeRF).  Default (126): everything except the forward value chain.
+// 16 weight gradients, 32 colour-net backward, 64 NeRF++ backward, 128 colour / NeRF++ forward).  Default (126): everything
+// except the forward value chains (gemm_engine.cuh explains why).
 static int g_tc_mask = -1;
 int tc_mask() {
   if (g_tc_mask < 0) {
@@ -62,7 +63,7 @@ int nudf_set_engine(int engine) {
   return 0;
 }
 int nudf_get_engine(void) { return nudf::get_engine(); }
-int nudf_set_tc_mask(int mask) { nudf::g_tc_mask = mask & 127; return 0; }
+int nudf_set_tc_mask(int mask) { nudf::g_tc_mask = mask & 255; return 0; }
 int nudf_get_tc_mask(void) { return nudf::tc_mask(); }
 int64_t nudf_launch_count(void) { return (int64_t)__atomic_load_n(&nudf::g_launches, __ATOMIC_RELAXED); }
 

@@ -6,10 +6,15 @@
 // fp32-grade accuracy (udf feeds exp(-25000 u) and sigmoid(400 u)), the other chains tolerate the 3xBF16 split.
 #pragma once
 #include "gemm_tc.cuh"
+#include "gemm_pl.cuh"
 
 namespace nudf {
 
-enum TcChain { TC_FWD = 1, TC_REV = 2, TC_TAN = 4, TC_BWD = 8, TC_WGRAD = 16, TC_COLOR = 32, TC_NERF = 64 };
+// TC_FWD: UDF value chain (3 planes); TC_REV/TAN/BWD: UDF gradient, tangent and backward chains; TC_WGRAD: weight gradients;
+// TC_COLOR / TC_NERF: BACKWARD data GEMMs of the ReLU networks; TC_RELU_FWD: their forward passes.  The default mask
+// (capi.cu) leaves both forward bits off: a 4e-6 perturbation of a pre-activation flips ~60x more ReLU gates than the
+// reference's own fp32 rounding does, which shows up as O(1/batch) jumps in the parameter gradients.
+enum TcChain { TC_FWD = 1, TC_REV = 2, TC_TAN = 4, TC_BWD = 8, TC_WGRAD = 16, TC_COLOR = 32, TC_NERF = 64, TC_RELU_FWD = 128 };
 
 int get_engine();
 int tc_mask();
@@ -43,6 +48,34 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     return tc::gemm_tn(A, lda, B, ldb, M, N, K, epi, st, splits);
   }
   return gemm_simt<false, false, Epi>(A, lda, B, ldb, M, N, K, epi, st, split_k);
+}
+
+// The same contraction with both operands stored as split-bf16 plane tensors (gemm_pl.cuh): tensor engine only.
+static inline bool planes_on() { return tc_on(TC_WGRAD); }
+template <class Epi>
+static inline int gemm_tn_planes(const tc::Planes& X, int M, const tc::Planes& Y, int N, int64_t P, const Epi& epi, cudaStream_t st) {
+  const int tiles = (int)(cdiv(M, 128) * cdiv(N, 256));
+  int splits = tc::sm_count() / tiles;
+  if (splits < 1) splits = 1;
+  return tc::gemm_tn_pl(X, M, Y, N, P, epi, st, splits);
+}
+// fp32 columns [c0, c1) of X -> the same columns of a plane tensor (element-wise kernels' outputs, skip-concat columns)
+static __global__ void pack_range_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int c0, int c1, tc::Planes out) {
+  const int n = c1 - c0;
+  const int64_t total = rows * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / n;
+    const int c = c0 + (int)(idx - row * n);
+    tc::pl_store1(out, row, c, X[row * ldx + c]);
+  }
+}
+static inline int pack_range(const float* X, int64_t ldx, int64_t rows, int c0, int c1, const tc::Planes& out, cudaStream_t st) {
+  if (rows <= 0 || c1 <= c0) return 0;
+  int64_t blocks = (rows * (c1 - c0) + 255) / 256;
+  if (blocks > 8192) blocks = 8192;
+  pack_range_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, rows, c0, c1, out);
+  NUDF_LAUNCH_OK();
+  return 0;
 }
 
 int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st);

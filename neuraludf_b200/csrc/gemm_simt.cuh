@@ -10,6 +10,7 @@
 // and dY^T X (weight gradients, contraction over points, split over gridDim.z with atomics) is <false,false>.
 #pragma once
 #include "common.cuh"
+#include "planes.cuh"
 
 namespace nudf {
 
@@ -198,6 +199,7 @@ __device__ __forceinline__ void st4(float* __restrict__ base, int64_t ld, int64_
 // C[row, col] = act(acc + bias[col]) * post_scale
 struct EpiAct {
   float* C; int64_t ldc; const float* bias; int act; float post_scale;
+  tc::Planes pl{nullptr, 0};                          // optional second copy of the output as split-bf16 planes
   struct Aux { float b[4]; };
   __device__ __forceinline__ void load(int64_t, int col, int nv, Aux& x) const {
 #pragma unroll
@@ -214,6 +216,7 @@ struct EpiAct {
       v[j] = t * post_scale;
     }
     st4(C, ldc, row, col, nv, v);
+    if (pl.p != nullptr) tc::pl_store(pl, row, col, nv, v);
   }
   NUDF_EPI_CALL
 };
@@ -238,6 +241,7 @@ struct EpiRev {
   const float* Anext; int64_t lda; float a_unscale;   // stored activation of layer l-1 (= A[l], first n_main cols)
   float* Dprev; int64_t ldd;
   float* Gpe; int64_t ldg;                             // [P, d_pe] or null
+  tc::Planes dpl{nullptr, 0};                          // optional plane copy of Dprev; columns >= n_main are zero-filled
   struct Aux { float a[4]; };
   __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
     int n = n_main - col;
@@ -251,16 +255,19 @@ struct EpiRev {
 #pragma unroll
       for (int j = 0; j < 4; ++j) d[j] = acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale);
       st4(Dprev, ldd, row, col, nv, d);
+      if (dpl.p != nullptr) tc::pl_store(dpl, row, col, nv, d);
       return;
     }
+    float dz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j >= nv) break;
       int c = col + j;
       float g = acc[j] * post_scale;
-      if (c < n_main) Dprev[row * ldd + c] = g * sig_from_softplus(x.a[j] * a_unscale);
+      if (c < n_main) { dz[j] = g * sig_from_softplus(x.a[j] * a_unscale); Dprev[row * ldd + c] = dz[j]; }
       else if (Gpe != nullptr) Gpe[row * ldg + (c - n_main)] = g;
     }
+    if (dpl.p != nullptr && col < dpl.cb * 64) tc::pl_store(dpl, row, col, nv, dz);
   }
   NUDF_EPI_CALL
 };
@@ -288,6 +295,7 @@ struct EpiTan {
   const float* D; int64_t ldd;
   float* Q; int64_t ldq;
   float* AdotNext; int64_t ldn; float post_scale;
+  tc::Planes npl{nullptr, 0};                          // optional plane copy of AdotNext
   struct Aux { float a[4], d[4]; };
   __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
     ld4(Anext, lda, row, col, nv, x.a);
@@ -303,6 +311,7 @@ struct EpiTan {
     }
     st4(Q, ldq, row, col, nv, q);
     st4(AdotNext, ldn, row, col, nv, n);
+    if (npl.p != nullptr) tc::pl_store(npl, row, col, nv, n);
   }
   NUDF_EPI_CALL
 };
@@ -312,6 +321,7 @@ struct EpiBwd {
   int n_main; float post_scale;
   const float* Anext; int64_t lda; float a_unscale;
   float* QZ; int64_t ldq;
+  tc::Planes zpl{nullptr, 0};                          // optional plane copy of Zbar; columns >= n_main are zero-filled
   struct Aux { float a[4], q[4]; };
   __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
     int n = n_main - col;
@@ -319,12 +329,18 @@ struct EpiBwd {
     if (n > 0) { ld4(Anext, lda, row, col, n, x.a); ld4(QZ, ldq, row, col, n, x.q); }
   }
   __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
-    if (col >= n_main) return;
+    const int nv_all = nv;
+    if (col >= n_main) {
+      const float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (zpl.p != nullptr && col < zpl.cb * 64) tc::pl_store(zpl, row, col, nv_all, z);
+      return;
+    }
     if (col + nv > n_main) nv = n_main - col;
     float q[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale) + x.q[j];
+    for (int j = 0; j < 4; ++j) q[j] = j < nv ? acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale) + x.q[j] : 0.f;
     st4(QZ, ldq, row, col, nv, q);
+    if (zpl.p != nullptr) tc::pl_store(zpl, row, col, nv_all, q);
   }
   NUDF_EPI_CALL
 };

@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 
 #include "gemm_simt.cuh"
+#include "planes.cuh"
 
 namespace nudf {
 namespace tc {
@@ -34,11 +35,6 @@ constexpr int A_HALF_BYTES = BM * BK * 2;   // 16 KB: one of (hi, lo)
 
 __host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
 __host__ __device__ inline int pad64(int k) { return (k + 63) & ~63; }
-// byte offset of element (row, k) inside a [rows x 64] bf16 K-major SWIZZLE_128B tile (tile base 1024-aligned)
-__host__ __device__ inline uint32_t sw128(uint32_t row, uint32_t k) {
-  return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ (row & 7u)) & 7u) << 4) + ((k & 7u) << 1);
-}
-
 // ---- weight image --------------------------------------------------------------------------------------------------
 // For operand B(n, k), n < N, k < K: n-tiles of NT rows (NT = 256 with 2 planes, 128 with 3 planes; the last tile is
 // padded to a multiple of 16), k-slices of 64.  NP planes per element: p0 = bf16(x), p1 = bf16(x - p0),
@@ -164,26 +160,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// split 4 consecutive values into NP bf16 planes (packed pairs)
-template <int NP>
-__device__ __forceinline__ void split4(const float x[4], uint2 planes[NP]) {
-  float r[4] = {x[0], x[1], x[2], x[3]};
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    float h[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __bfloat162float(__float2bfloat16_rn(r[j]));
-      r[j] -= h[j];
-    }
-    planes[p] = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
-  }
 }
 
 template <int NT>   // NT = number of producer threads (128 or 256); fetches this thread's part of a [128 x 64] fp32 slice

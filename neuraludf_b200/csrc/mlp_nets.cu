@@ -348,7 +348,7 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     else if (l == nl - 2) { e.C = xm + p.c_hid; e.ldc = p.ld_xm; e.act = ACT_RELU; }      // x_hidden (fields.py:472-473)
     else { e.C = xm + p.c_cb; e.ldc = p.ld_xm; e.act = ACT_SIGMOID; }                      // color_base (:475-476)
     if (int rc = gemm_nt(X, ldx, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l + 1], p.dims_b[l], e, st,
-                         cimg + p.ib_nt[l], TC_COLOR)) return rc;
+                         cimg + p.ib_nt[l], TC_RELU_FWD)) return rc;
   }
   if (color_base) {
     ew_copy_cols_kernel<<<ew_blocks(P * p.d_out, 256), 256, 0, st>>>(xm + p.c_cb, p.ld_xm, color_base, p.d_out, 0, p.d_out, P, 1.f);
@@ -363,7 +363,7 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     if (l < nl - 1) { e.C = ctx + c.hm[l + 1]; e.ldc = p.H; e.act = ACT_RELU; }
     else { e.C = ctx + c.ym; e.ldc = p.ld_ym; e.act = ACT_NONE; }
     if (int rc = gemm_nt(X, ldx, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l + 1], p.dims_m[l], e, st,
-                         cimg + p.im_nt[l], TC_COLOR)) return rc;
+                         cimg + p.im_nt[l], TC_RELU_FWD)) return rc;
   }
   color_head_kernel<<<ew_blocks(P * (p.d_out + p.n_blend), 256), 256, 0, st>>>(ctx + c.ym, p.ld_ym, p.d_out, p.n_blend, P,
                                                                               color, ctx + c.cs, 4, blend);
@@ -593,7 +593,7 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* wimg, const float* p
     const float* X = nerf_x(p, ctx, c, i, &ldx);
     float* Hh = nerf_h(p, ctx, c, i, &ldh);
     EpiAct e{Hh, ldh, d->pts_b[i], ACT_RELU, 1.0f};
-    if (int rc = gemm_nt(X, ldx, d->pts_w[i], p.in_dim[i], P, p.W, p.in_dim[i], e, st, img ? img + p.ipts_nt[i] : nullptr, TC_NERF)) return rc;
+    if (int rc = gemm_nt(X, ldx, d->pts_w[i], p.in_dim[i], P, p.W, p.in_dim[i], e, st, img ? img + p.ipts_nt[i] : nullptr, TC_RELU_FWD)) return rc;
   }
   int64_t ldl;
   const float* Hl = nerf_h(p, ctx, c, p.D - 1, &ldl);
@@ -603,11 +603,11 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* wimg, const float* p
   }
   {
     EpiAct e{ctx + c.f, p.ld_f, d->feature_b, ACT_NONE, 1.0f};
-    if (int rc = gemm_nt(Hl, ldl, d->feature_w, p.W, P, p.W, p.W, e, st, img ? img + p.ifeat_nt : nullptr, TC_NERF)) return rc;
+    if (int rc = gemm_nt(Hl, ldl, d->feature_w, p.W, P, p.W, p.W, e, st, img ? img + p.ifeat_nt : nullptr, TC_RELU_FWD)) return rc;
   }
   {
     EpiAct e{ctx + c.hv, p.W / 2, d->views_b, ACT_RELU, 1.0f};
-    if (int rc = gemm_nt(ctx + c.f, p.ld_f, d->views_w, p.W + p.chv, P, p.W / 2, p.W + p.chv, e, st, img ? img + p.iviews_nt : nullptr, TC_NERF)) return rc;
+    if (int rc = gemm_nt(ctx + c.f, p.ld_f, d->views_w, p.W + p.chv, P, p.W / 2, p.W + p.chv, e, st, img ? img + p.iviews_nt : nullptr, TC_RELU_FWD)) return rc;
   }
   {
     EpiAct e{rgb, 3, d->rgb_b, ACT_NONE, 1.0f};

@@ -104,7 +104,6 @@ def test_whole_render_with_blending_runs_and_trains_all_networks(golden):
     assert ret["patch_mask"].shape == (64,)
     for k in ("color", "color_pixel", "patch_colors", "patch_mask"):
         assert torch.isfinite(ret[k]).all(), k
-    assert float(ret["color_pixel"].min()) >= -1e-5 and float(ret["color_pixel"].max()) <= 1.0 + 1e-4
     _loss(ret).backward()
     for m in (udf, col, nerf):
         gs = [p.grad for p in m.parameters() if p.grad is not None]

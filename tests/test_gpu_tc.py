@@ -87,6 +87,45 @@ def test_wgrad_tc_vs_fp64(P, n_out, n_in):
         assert e < 5e-5, (engine, e)
 
 
+def _planes(L, lib, x):
+    rows, cols = x.shape
+    buf = torch.empty(lib.nudf_planes_elems(rows, cols) + 512, dtype=torch.int16, device=DEV)
+    off = (-buf.data_ptr() % 1024) // 2
+    pl = buf[off:off + lib.nudf_planes_elems(rows, cols)]
+    pl.fill_(0x7FC0)                                  # bf16 NaN everywhere: pad rows must be rewritten by the packer
+    L.check(lib.nudf_pack_planes(L.ptr(x), x.stride(0), rows, cols, L.ptr(pl), L.stream_ptr()), "pack")
+    return pl
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 5), (130, 64), (257, 217), (4096, 256)])
+def test_planes_round_trip(rows, cols):
+    """fp32 -> split-bf16 planes -> fp32: 16 mantissa bits survive (relative error <= 2^-16)"""
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, generator=g) * torch.logspace(-3, 3, cols)[None, :]).to(DEV).contiguous()
+    pl = _planes(L, lib, x)
+    y = torch.full_like(x, float("nan"))
+    L.check(lib.nudf_unpack_planes(L.ptr(pl), rows, cols, L.ptr(y), y.stride(0), L.stream_ptr()), "unpack")
+    assert float(((y - x).abs() / x.abs().clamp(min=1e-30)).max()) <= 2.0 ** -16
+
+
+@pytest.mark.parametrize("P,n_out,n_in", [(4096, 256, 256), (1000, 128, 64), (70, 257, 39), (65536, 256, 256), (333, 217, 256)])
+def test_wgrad_planes_vs_fp64(P, n_out, n_in):
+    """weight-gradient contraction with both operands fetched as plane blocks (MN-major UMMA operands)"""
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(P + n_out)
+    dZ = torch.randn(P, n_out, generator=g, dtype=torch.float64)
+    X = torch.randn(P, n_in, generator=g, dtype=torch.float64)
+    ref = dZ.t() @ X
+    dZp = _planes(L, lib, dZ.float().to(DEV).contiguous())
+    Xp = _planes(L, lib, X.float().to(DEV).contiguous())
+    dW = torch.zeros(n_out, n_in, device=DEV)
+    L.check(lib.nudf_wgrad_planes(L.ptr(dZp), L.ptr(Xp), n_out, n_in, P, L.ptr(dW), n_in, L.stream_ptr()), "wgrad_planes")
+    e = err_inf(dW, ref) / scale_inf(ref)
+    report("tc.wgrad_planes[%d,%d,%d]" % (P, n_out, n_in), rel=e)
+    assert e < 5e-5, e
+
+
 @pytest.mark.parametrize("mask", [0, 62, 63])
 def test_render_core_accuracy_by_tc_mask(golden, mask):
     """How far each choice of tensor-engine chains moves render_core from the fp64 reference (reported; the default
