@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnudf.so")
+LIB_PATH = os.environ.get("NUDF_LIB_PATH", os.path.join(HERE, "libnudf.so"))   # override: A/B builds of the library
 MAX_LAYERS = 16
 
 c_float_p = ctypes.POINTER(ctypes.c_float)

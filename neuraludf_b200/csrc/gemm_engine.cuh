@@ -5,6 +5,7 @@
 // Which chains may use the tensor engine is a bit mask (NUDF_TC_MASK, see tc_mask()): the forward value chain needs
 // fp32-grade accuracy (udf feeds exp(-25000 u) and sigmoid(400 u)), the other chains tolerate the 3xBF16 split.
 #pragma once
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "gemm_pl.cuh"
 
@@ -35,9 +36,13 @@ static inline int gemm_nn(const float* A, int64_t lda, const float* W, int64_t l
   return gemm_simt<true, false, Epi>(A, lda, W, ldw, M, N, K, epi, st, 1);
 }
 // C[M x N] += A[K x M]^T B[K x N]   (contraction over points)
+int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st);
+
+// colsum_a (optional): colsum_a[m] += sum_k A[k, m] -- the bias gradient that goes with a weight gradient; fused into the
+// tensor-engine kernel's operand staging, a separate reduction kernel on the FFMA path.
 template <class Epi>
 static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K,
-                          const Epi& epi, cudaStream_t st, int split_k, int chain = TC_WGRAD) {
+                          const Epi& epi, cudaStream_t st, int split_k, int chain = TC_WGRAD, float* colsum_a = nullptr) {
   if (tc_on(chain) && M >= 32 && N >= 32 && K >= 128) {
     // split the points so that (M tiles x N tiles x splits) fills the SMs once, with at least 8 slices of 64 points per CTA
     const int tiles = (int)(cdiv(M, 128) * cdiv(N, 256));
@@ -45,39 +50,11 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     const int max_splits = (int)cdiv(K, 512);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    return tc::gemm_tn(A, lda, B, ldb, M, N, K, epi, st, splits);
+    return tc::gemm_tn(A, lda, B, ldb, M, N, K, epi, st, splits, colsum_a);
   }
-  return gemm_simt<false, false, Epi>(A, lda, B, ldb, M, N, K, epi, st, split_k);
-}
-
-// The same contraction with both operands stored as split-bf16 plane tensors (gemm_pl.cuh): tensor engine only.
-static inline bool planes_on() { return tc_on(TC_WGRAD); }
-template <class Epi>
-static inline int gemm_tn_planes(const tc::Planes& X, int M, const tc::Planes& Y, int N, int64_t P, const Epi& epi, cudaStream_t st) {
-  const int tiles = (int)(cdiv(M, 128) * cdiv(N, 256));
-  int splits = tc::sm_count() / tiles;
-  if (splits < 1) splits = 1;
-  return tc::gemm_tn_pl(X, M, Y, N, P, epi, st, splits);
-}
-// fp32 columns [c0, c1) of X -> the same columns of a plane tensor (element-wise kernels' outputs, skip-concat columns)
-static __global__ void pack_range_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int c0, int c1, tc::Planes out) {
-  const int n = c1 - c0;
-  const int64_t total = rows * n;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = idx / n;
-    const int c = c0 + (int)(idx - row * n);
-    tc::pl_store1(out, row, c, X[row * ldx + c]);
-  }
-}
-static inline int pack_range(const float* X, int64_t ldx, int64_t rows, int c0, int c1, const tc::Planes& out, cudaStream_t st) {
-  if (rows <= 0 || c1 <= c0) return 0;
-  int64_t blocks = (rows * (c1 - c0) + 255) / 256;
-  if (blocks > 8192) blocks = 8192;
-  pack_range_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, rows, c0, c1, out);
-  NUDF_LAUNCH_OK();
+  if (int rc = gemm_simt<false, false, Epi>(A, lda, B, ldb, M, N, K, epi, st, split_k)) return rc;
+  if (colsum_a != nullptr) return colsum(A, lda, nullptr, 1.f, K, M, colsum_a, st);
   return 0;
 }
-
-int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st);
 
 }  // namespace nudf

@@ -79,7 +79,7 @@ struct SmemCtlT {
 
 template <class Epi>
 __global__ void __launch_bounds__(TP_THREADS, 1)
-gemm_tn_pl_kernel(Planes X, int M, Planes Y, int N, int64_t P, int64_t blocks_per_split, Epi epi) {
+gemm_tn_pl_kernel(Planes X, int M, Planes Y, int N, int64_t P, int64_t blocks_per_split, Epi epi, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -117,6 +117,7 @@ gemm_tn_pl_kernel(Planes X, int M, Planes Y, int N, int64_t P, int64_t blocks_pe
         uint8_t* ys = xs + TP_X_BYTES;
         const int64_t mb = kb0 + i / (PL_BLOCK / TP_ROWS);
         const int64_t piece = (i % (PL_BLOCK / TP_ROWS)) * (TP_PIECE / 2);        // uint16 offset inside the plane block
+        if (dbg & 1) { mbar_arrive(&ctl->full[s]); continue; }
         mbar_arrive_expect_tx(&ctl->full[s], tx);
         for (int pl = 0; pl < 2; ++pl) {
           for (int c = 0; c < nxb; ++c)
@@ -140,6 +141,7 @@ gemm_tn_pl_kernel(Planes X, int M, Planes Y, int N, int64_t P, int64_t blocks_pe
         for (int j = 0; j < TP_ROWS / 16; ++j) {          // 16 points per MMA = two 8-row atoms = 2048 B
           const uint64_t ah = make_desc_mn(xs + j * 2048u, TP_PIECE), al = make_desc_mn(xs + x_lo + j * 2048u, TP_PIECE);
           const uint64_t bh = make_desc_mn(ys + j * 2048u, TP_PIECE), bl = make_desc_mn(ys + y_lo + j * 2048u, TP_PIECE);
+          if (dbg & 8) continue;
           mma_bf16(tmem_base, al, bh, idesc, (i == 0 && j == 0) ? 0u : 1u);
           mma_bf16(tmem_base, ah, bl, idesc, 1u);
           mma_bf16(tmem_base, ah, bh, idesc, 1u);
@@ -153,8 +155,9 @@ gemm_tn_pl_kernel(Planes X, int M, Planes Y, int N, int64_t P, int64_t blocks_pe
     mbar_wait(&ctl->tmem_full, 0);
     tcgen05_fence_after();
     // the stage buffers are idle now: reuse them as the epilogue's transposition tiles
+    if (!(dbg & 2))
     run_epilogue(tmem_base, warp & 3, lane, 32 * (warp >> 2), 64, 1, 0u, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, n_mma, N,
-                 reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi);
+                 reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi, (int)blockIdx.z);
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -196,7 +199,7 @@ static inline int gemm_tn_pl(const Planes& X, int M, const Planes& Y, int N, int
     attr_set = true;
   }
   dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 256), (unsigned)splits);
-  gemm_tn_pl_kernel<Epi><<<grid, TP_THREADS, smem, st>>>(X, M, Y, N, P, bps, epi);
+  gemm_tn_pl_kernel<Epi><<<grid, TP_THREADS, smem, st>>>(X, M, Y, N, P, bps, epi, tc_debug());
   NUDF_LAUNCH_OK();
   return 0;
 }

@@ -10,7 +10,6 @@
 // and dY^T X (weight gradients, contraction over points, split over gridDim.z with atomics) is <false,false>.
 #pragma once
 #include "common.cuh"
-#include "planes.cuh"
 
 namespace nudf {
 
@@ -199,7 +198,6 @@ __device__ __forceinline__ void st4(float* __restrict__ base, int64_t ld, int64_
 // C[row, col] = act(acc + bias[col]) * post_scale
 struct EpiAct {
   float* C; int64_t ldc; const float* bias; int act; float post_scale;
-  tc::Planes pl{nullptr, 0};                          // optional second copy of the output as split-bf16 planes
   struct Aux { float b[4]; };
   __device__ __forceinline__ void load(int64_t, int col, int nv, Aux& x) const {
 #pragma unroll
@@ -216,7 +214,6 @@ struct EpiAct {
       v[j] = t * post_scale;
     }
     st4(C, ldc, row, col, nv, v);
-    if (pl.p != nullptr) tc::pl_store(pl, row, col, nv, v);
   }
   NUDF_EPI_CALL
 };
@@ -227,9 +224,15 @@ struct EpiAtomicAdd {
   struct Aux {};
   __device__ __forceinline__ void load(int64_t, int, int, Aux&) const {}
   __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux&) const {
+    float* p = C + row * ldc + col;
+    if (nv == 4 && ((ldc & 3) == 0) && ((col & 3) == 0) && aligned16(C)) {     // one 16-byte reduction instead of four
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3])
+                   : "memory");
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (j < nv) atomicAdd(C + row * ldc + col + j, acc[j]);
+      if (j < nv) atomicAdd(p + j, acc[j]);
   }
   NUDF_EPI_CALL
 };
@@ -241,7 +244,6 @@ struct EpiRev {
   const float* Anext; int64_t lda; float a_unscale;   // stored activation of layer l-1 (= A[l], first n_main cols)
   float* Dprev; int64_t ldd;
   float* Gpe; int64_t ldg;                             // [P, d_pe] or null
-  tc::Planes dpl{nullptr, 0};                          // optional plane copy of Dprev; columns >= n_main are zero-filled
   struct Aux { float a[4]; };
   __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
     int n = n_main - col;
@@ -255,19 +257,16 @@ struct EpiRev {
 #pragma unroll
       for (int j = 0; j < 4; ++j) d[j] = acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale);
       st4(Dprev, ldd, row, col, nv, d);
-      if (dpl.p != nullptr) tc::pl_store(dpl, row, col, nv, d);
       return;
     }
-    float dz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j >= nv) break;
       int c = col + j;
       float g = acc[j] * post_scale;
-      if (c < n_main) { dz[j] = g * sig_from_softplus(x.a[j] * a_unscale); Dprev[row * ldd + c] = dz[j]; }
+      if (c < n_main) Dprev[row * ldd + c] = g * sig_from_softplus(x.a[j] * a_unscale);
       else if (Gpe != nullptr) Gpe[row * ldg + (c - n_main)] = g;
     }
-    if (dpl.p != nullptr && col < dpl.cb * 64) tc::pl_store(dpl, row, col, nv, dz);
   }
   NUDF_EPI_CALL
 };
@@ -295,7 +294,6 @@ struct EpiTan {
   const float* D; int64_t ldd;
   float* Q; int64_t ldq;
   float* AdotNext; int64_t ldn; float post_scale;
-  tc::Planes npl{nullptr, 0};                          // optional plane copy of AdotNext
   struct Aux { float a[4], d[4]; };
   __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
     ld4(Anext, lda, row, col, nv, x.a);
@@ -311,7 +309,6 @@ struct EpiTan {
     }
     st4(Q, ldq, row, col, nv, q);
     st4(AdotNext, ldn, row, col, nv, n);
-    if (npl.p != nullptr) tc::pl_store(npl, row, col, nv, n);
   }
   NUDF_EPI_CALL
 };
@@ -321,7 +318,6 @@ struct EpiBwd {
   int n_main; float post_scale;
   const float* Anext; int64_t lda; float a_unscale;
   float* QZ; int64_t ldq;
-  tc::Planes zpl{nullptr, 0};                          // optional plane copy of Zbar; columns >= n_main are zero-filled
   struct Aux { float a[4], q[4]; };
   __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
     int n = n_main - col;
@@ -329,18 +325,39 @@ struct EpiBwd {
     if (n > 0) { ld4(Anext, lda, row, col, n, x.a); ld4(QZ, ldq, row, col, n, x.q); }
   }
   __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
-    const int nv_all = nv;
-    if (col >= n_main) {
-      const float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (zpl.p != nullptr && col < zpl.cb * 64) tc::pl_store(zpl, row, col, nv_all, z);
-      return;
-    }
+    if (col >= n_main) return;
     if (col + nv > n_main) nv = n_main - col;
     float q[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = j < nv ? acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale) + x.q[j] : 0.f;
+    for (int j = 0; j < 4; ++j) q[j] = acc[j] * post_scale * sig_from_softplus(x.a[j] * a_unscale) + x.q[j];
     st4(QZ, ldq, row, col, nv, q);
-    if (zpl.p != nullptr) tc::pl_store(zpl, row, col, nv_all, q);
+  }
+  NUDF_EPI_CALL
+};
+
+// EpiBwd with a rank-1 term: acc += z0[row] * w0[col].  Used at the top of the backward chain, where the 257-wide last
+// layer is split into its 256 feature rows (a K = 256 tensor-engine GEMM) and the udf-head row (this rank-1 update).
+struct EpiBwdR1 {
+  int n_main; float post_scale;
+  const float* Anext; int64_t lda; float a_unscale;
+  float* QZ; int64_t ldq;
+  const float* z0; const float* w0;
+  struct Aux { float a[4], q[4], w[4], z; };
+  __device__ __forceinline__ void load(int64_t row, int col, int nv, Aux& x) const {
+    int n = n_main - col;
+    n = n < nv ? n : nv;
+    if (n > 0) {
+      ld4(Anext, lda, row, col, n, x.a); ld4(QZ, ldq, row, col, n, x.q); ld4(w0, 0, 0, col, n, x.w);
+      x.z = z0[row];
+    }
+  }
+  __device__ __forceinline__ void apply(int64_t row, int col, const float acc[4], int nv, const Aux& x) const {
+    if (col >= n_main) return;
+    if (col + nv > n_main) nv = n_main - col;
+    float q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = fmaf(x.z, x.w[j], acc[j]) * post_scale * sig_from_softplus(x.a[j] * a_unscale) + x.q[j];
+    st4(QZ, ldq, row, col, nv, q);
   }
   NUDF_EPI_CALL
 };

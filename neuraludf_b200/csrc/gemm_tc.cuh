@@ -214,8 +214,10 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
 // (on-the-fly transpose; the contraction index k runs over points).  Lane l owns the m-quad (l & 7) and, in iteration q,
 // the k pair 4q + (l >> 3): every warp-level load covers 4 rows of X x 128 contiguous bytes (4 L1 wavefronts instead of
 // the 32 of a lane-per-row mapping); all 16 loads of a lane are issued before the first conversion.
+template <bool CSUM = false>
 __device__ __forceinline__ void stage_block_t(const float* __restrict__ X, int64_t ld, int m0, int m_total, int r0, int rows,
-                                              int64_t k0, int64_t k_end, uint8_t* s_hi, uint8_t* s_lo, int lane, bool vec_ok) {
+                                              int64_t k0, int64_t k_end, uint8_t* s_hi, uint8_t* s_lo, int lane, bool vec_ok,
+                                              float* csum = nullptr) {
   const int mq = lane & 7, kq = lane >> 3;
   if (r0 + 4 * mq >= rows) return;      // tile rows are padded to 16, blocks cover 32: skip quads beyond the tile
   const int m = m0 + r0 + 4 * mq;
@@ -237,6 +239,13 @@ __device__ __forceinline__ void stage_block_t(const float* __restrict__ X, int64
           if (m + 3 < m_total) v[q][kk].w = p[3];
         }
       }
+    }
+  }
+  if (CSUM) {                             // per-lane partial column sums of X (bias gradients), fp32
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      csum[0] += v[q][0].x + v[q][1].x; csum[1] += v[q][0].y + v[q][1].y;
+      csum[2] += v[q][0].z + v[q][1].z; csum[3] += v[q][0].w + v[q][1].w;
     }
   }
 #pragma unroll
@@ -294,12 +303,65 @@ __device__ __forceinline__ void issue_slice(uint32_t tmem_d, uint32_t a, uint32_
 // the fused epilogues' global loads / stores (activations, saved tensors, outputs) are then fully coalesced float4.
 constexpr int EPI_LD = 36;                       // floats per staged row (32 + 4 pad: conflict-free STS.128 / LDS.128)
 constexpr int EPI_WARP_FLOATS = 16 * EPI_LD;     // the 32x32 block goes through the staging tile in two 16-row passes
-template <class Epi>
+#ifndef NUDF_EPI_DEEP
+#define NUDF_EPI_DEEP 1
+#endif
+struct NoWait {
+  __device__ __forceinline__ void operator()() const {}
+};
+// Software pipeline: the auxiliary global loads of pass p+1 (16 rows x 32 columns per warp) are issued before pass p is
+// computed and stored, and those of the very first pass before `wait()` (the accumulator-ready barrier) returns, so that
+// two passes' worth of loads are in flight per warp -- the epilogues are bound by memory-level parallelism, not by math.
+template <class Epi, class Wait = NoWait>
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int lane, int chunk0, int chunk_step, int n_acc,
                                              uint32_t acc_stride, int64_t row0, int64_t M, int col_base, int n_pad, int n_valid_end,
-                                             float* stg, const Epi& epi) {
+                                             float* stg, const Epi& epi, int rot = 0, Wait wait = Wait()) {
   const int cq = lane & 7, rsub = lane >> 3;
-  for (int c0 = chunk0; c0 < n_pad; c0 += chunk_step) {
+  // rot: start the column chunks at a CTA-dependent position (split-K CTAs would otherwise all reduce into the same
+  // addresses at the same time)
+  const int n_it = n_pad > chunk0 ? (n_pad - chunk0 + chunk_step - 1) / chunk_step : 0;
+  auto chunk_col = [&](int it) { return chunk0 + ((it + rot) % n_it) * chunk_step; };
+  auto load_pass = [&](int it, int h, typename Epi::Aux (&aux)[4]) {
+    const int col = col_base + chunk_col(it) + 4 * cq;
+    int nv = n_valid_end - col;
+    nv = nv < 4 ? nv : 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t row = row0 + 16 * h + rsub + 4 * i;
+      if (row < M && nv > 0) epi.load(row, col, nv, aux[i]);
+    }
+  };
+  auto do_pass = [&](int it, int h, const float (&v)[32], const typename Epi::Aux (&aux)[4]) {
+    const int col = col_base + chunk_col(it) + 4 * cq;
+    int nv = n_valid_end - col;
+    nv = nv < 4 ? nv : 4;
+    if ((lane >> 4) == h) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stg + (lane & 15) * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rsub + 4 * i;
+      const float4 t = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * cq);
+      const int64_t row = row0 + 16 * h + r;
+      if (row < M && nv > 0) {
+        const float x[4] = {t.x, t.y, t.z, t.w};
+        epi.apply(row, col, x, nv, aux[i]);
+      }
+    }
+    __syncwarp();
+  };
+  // Functors with 8 auxiliary floats per group (EpiTan, EpiBwd) do not fit two sets next to the 32 accumulator values in
+  // the 128-register budget of the epilogue warps: they keep one set and load just in time (kDeepPipe = false).
+  constexpr bool kDeep = NUDF_EPI_DEEP && sizeof(typename Epi::Aux) <= 4 * sizeof(float);
+  typename Epi::Aux a0[4], a1[kDeep ? 4 : 1];
+  if (n_it > 0) load_pass(0, 0, a0);
+  wait();
+  for (int it = 0; it < n_it; ++it) {
+    const int c0 = chunk_col(it);
+    if constexpr (kDeep) load_pass(it, 1, a1);
     float v[32];
     tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
     for (int a = 1; a < n_acc; ++a) {          // per-slice partial accumulators are summed here with round-to-nearest adds
@@ -308,35 +370,14 @@ __device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int la
 #pragma unroll
       for (int q = 0; q < 32; ++q) v[q] += w[q];
     }
-    const int col = col_base + c0 + 4 * cq;
-    int nv = n_valid_end - col;
-    nv = nv < 4 ? nv : 4;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if ((lane >> 4) == h) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(stg + (lane & 15) * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-      __syncwarp();
-      // phase 1: put the auxiliary global loads of the 4 row groups in flight; phase 2: compute + store
-      typename Epi::Aux aux[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t row = row0 + 16 * h + rsub + 4 * i;
-        if (row < M && nv > 0) epi.load(row, col, nv, aux[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = rsub + 4 * i;
-        const float4 t = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * cq);
-        const int64_t row = row0 + 16 * h + r;
-        if (row < M && nv > 0) {
-          const float x[4] = {t.x, t.y, t.z, t.w};
-          epi.apply(row, col, x, nv, aux[i]);
-        }
-      }
-      __syncwarp();
+    do_pass(it, 0, v, a0);
+    if constexpr (kDeep) {
+      if (it + 1 < n_it) load_pass(it + 1, 0, a0);
+      do_pass(it, 1, v, a1);
+    } else {
+      load_pass(it, 1, a0);
+      do_pass(it, 1, v, a0);
+      if (it + 1 < n_it) load_pass(it + 1, 0, a0);
     }
   }
 }
@@ -602,7 +643,9 @@ constexpr int WR_MAX_SLICES = 4; // K <= 256
 // Warp-specialised layout of the weights-resident kernel: 20 warps = 5 warpgroups.  LSU streaming rate of a
 // single CTA per SM scales with its number of loading warps (tools/ubench/membw.cu: 4 warps 2.3 TB/s, 8 warps 3.9 TB/s), so both the operand fetch and
 // the epilogue (whose fused functors load 1-2 and store 1-2 tensors) get 8 warps each; registers are re-balanced with
-// setmaxnreg (epilogue 128, MMA / loader warpgroup 32).
+// setmaxnreg (epilogue 128, MMA / loader warpgroup 32).  setmaxnreg.inc draws from the CTA pool, i.e. only from what the
+// MMA / loader warpgroup released with setmaxnreg.dec: (96 - 32) x 128 threads = 8192 registers = +32 for the 256 epilogue
+// threads.  Asking for more (136, 144) spins forever in USETMAXREG.TRY_ALLOC.
 constexpr int RW_THREADS = 640;
 constexpr int RW_PROD = 256;     // warps 0-7   (warpgroups 0-1)
 constexpr int RW_EPI = 256;      // warps 8-15  (warpgroups 2-3): quadrant = warp & 3, column half = (warp >> 2) & 1
@@ -679,10 +722,9 @@ gemm_wr_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int N, int K
     for (int64_t jt = blockIdx.x; jt < n_mtiles; jt += gridDim.x, ++it) {
       const int64_t mt = reverse ? n_mtiles - 1 - jt : jt;
       const uint32_t a = it & 1u, au = it >> 1;
-      mbar_wait(&ctl->tfull[a], au & 1u);
-      tcgen05_fence_after();
+      auto acc_ready = [&]() { mbar_wait(&ctl->tfull[a], au & 1u); tcgen05_fence_after(); };
       run_epilogue(tmem_base + a * acc_cols, ew & 3, lane, 32 * (ew >> 2), 64, 1, 0u, mt * BM + (ew & 3) * 32, M, n0, rows_h, N,
-                   epi_stage + ew * EPI_WARP_FLOATS, epi);
+                   epi_stage + ew * EPI_WARP_FLOATS, epi, 0, acc_ready);
       tcgen05_fence_before();
       mbar_arrive(&ctl->tempty[a]);
     }
@@ -740,7 +782,7 @@ constexpr int TN_THREADS = 416;   // + warp 12: MMA issuer and TMEM owner
 template <class Epi>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int M, int N, int64_t K,
-               int64_t k_chunk, Epi epi) {
+               int64_t k_chunk, Epi epi, float* __restrict__ colsum_a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -768,25 +810,43 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
   if (warp < 12) {
     const bool a_vec = ((lda & 3) == 0) && aligned16(A) && ((m0 & 3) == 0);
     const bool b_vec = ((ldb & 3) == 0) && aligned16(B);
+    // optional fused bias gradient: column sums of A (= sum over points of dZ), taken from the values the A stagers hold
+    // anyway; only the CTAs of the first N tile contribute
+    const bool do_csum = colsum_a != nullptr && blockIdx.y == 0;
+    float csum[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ks = 0; ks < n_slices; ++ks) {
       const int s = ks & 1, u = ks >> 1;
       if (u > 0) mbar_wait(&ctl->empty[s], (uint32_t)((u - 1) & 1));
       uint8_t* st = smem + s * stage_bytes;
       const int64_t k0 = kb + (int64_t)ks * BK;
       if (warp < 4) {
-        stage_block_t(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec);
+        if (do_csum) stage_block_t<true>(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec, csum);
+        else stage_block_t(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec);
       } else if (32 * (warp - 4) < rows_b) {
         stage_block_t(B, ldb, n0, N, 32 * (warp - 4), rows_b, k0, ke, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, lane, b_vec);
       }
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
     }
+    if (do_csum && warp < 4) {            // lanes (mq, kq): reduce over the 4 kq lanes, then one atomic per column
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], 8);
+        csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], 16);
+      }
+      if ((lane >> 3) == 0) {
+        const int m = m0 + 32 * warp + 4 * (lane & 7);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (m + j < M) atomicAdd(colsum_a + m + j, csum[j]);
+      }
+    }
     if (n_slices > 0) {
       mbar_wait(&ctl->tmem_full, 0);
       tcgen05_fence_after();
       // warp w: TMEM quadrant w & 3, 32-column chunks (w >> 2), (w >> 2) + 3, ...
       run_epilogue(tmem_base, warp & 3, lane, 32 * (warp >> 2), 96, 1, 0u, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, rows_b, N,
-                   reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi);
+                   reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi, (int)blockIdx.z);
       tcgen05_fence_before();
     }
   } else {
@@ -892,7 +952,7 @@ static inline int gemm_w(const float* A, int64_t lda, int64_t M, int N, int K, c
 
 template <class Epi>
 static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K, const Epi& epi,
-                          cudaStream_t st, int split_k) {
+                          cudaStream_t st, int split_k, float* colsum_a = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   int64_t k_chunk = round_up(cdiv(K, split_k < 1 ? 1 : split_k), BK);
   int splits = (int)cdiv(K, k_chunk);
@@ -903,7 +963,7 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     attr_set = true;
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, 256), (unsigned)splits);
-  gemm_tn_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi);
+  gemm_tn_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi, colsum_a);
   NUDF_LAUNCH_OK();
   return 0;
 }

@@ -89,18 +89,22 @@ __global__ void pack_pts_feat_kernel(const float* __restrict__ pts, const float*
 }
 
 // Weight gradient of a narrow head (n_out <= 16: colour / density heads): dW[m, n] += sum_p dZ[p, m] X[p, n], db[m] += sum_p dZ[p, m].
-// One thread per input column n, a chunk of points per CTA, n_out accumulators in registers, one atomic per (m, n) per CTA:
-// streams X once (HBM-bound) instead of padding the 3..13 output rows to a 128-wide GEMM tile.
+// Streams X once (HBM-bound) instead of padding the 3..13 output rows to a 128-wide GEMM tile.  CTA = 128 input columns x 4
+// point lanes over a 256-point chunk; the lanes' partial sums meet in shared memory, then one atomic per (m, n) per CTA.
 template <int MAXM>
-__global__ void wgrad_small_kernel(const float* __restrict__ dZ, int64_t ldz, const float* __restrict__ X, int64_t ldx, int n_out,
-                                   int n_in, int64_t P, int64_t chunk, float* __restrict__ dW, int64_t ldw, float* __restrict__ db) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(512)
+wgrad_small_kernel(const float* __restrict__ dZ, int64_t ldz, const float* __restrict__ X, int64_t ldx, int n_out, int n_in, int64_t P,
+                   int64_t chunk, float* __restrict__ dW, int64_t ldw, float* __restrict__ db) {
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  const int n = blockIdx.x * 128 + tx;
   const int64_t p0 = (int64_t)blockIdx.y * chunk;
   const int64_t p1 = p0 + chunk < P ? p0 + chunk : P;
-  float acc[MAXM], bsum[MAXM];
+  float acc[MAXM];
 #pragma unroll
-  for (int m = 0; m < MAXM; ++m) { acc[m] = 0.f; bsum[m] = 0.f; }
+  for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+  float bs = 0.f;
   __shared__ float sdz[64][MAXM];
+  __shared__ float red[3][MAXM][128];
   for (int64_t pb = p0; pb < p1; pb += 64) {
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * MAXM; i += blockDim.x) {
@@ -109,33 +113,40 @@ __global__ void wgrad_small_kernel(const float* __restrict__ dZ, int64_t ldz, co
     }
     __syncthreads();
     const int cnt = (int)((p1 - pb) < 64 ? (p1 - pb) : 64);
-    for (int r = 0; r < cnt; ++r) {
+#pragma unroll 4
+    for (int r = ty; r < cnt; r += 4) {
       const float x = n < n_in ? X[(pb + r) * ldx + n] : 0.f;
 #pragma unroll
-      for (int m = 0; m < MAXM; ++m) { acc[m] = fmaf(sdz[r][m], x, acc[m]); bsum[m] += sdz[r][m]; }
+      for (int m = 0; m < MAXM; ++m) acc[m] = fmaf(sdz[r][m], x, acc[m]);
     }
+    if (threadIdx.x < MAXM)
+      for (int r = 0; r < cnt; ++r) bs += sdz[r][threadIdx.x];
   }
-  if (n < n_in)
-    for (int m = 0; m < n_out; ++m) atomicAdd(dW + (int64_t)m * ldw + n, acc[m]);
-  if (db != nullptr && n == 0)
-    for (int m = 0; m < n_out; ++m) atomicAdd(db + m, bsum[m]);
+  if (ty > 0) {
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) red[ty - 1][m][tx] = acc[m];
+  }
+  __syncthreads();
+  if (ty == 0 && n < n_in) {
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m)
+      if (m < n_out) atomicAdd(dW + (int64_t)m * ldw + n, acc[m] + red[0][m][tx] + red[1][m][tx] + red[2][m][tx]);
+  }
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < n_out) atomicAdd(db + threadIdx.x, bs);
 }
 
 static int wgrad(const float* dZ, int64_t ldz, const float* X, int64_t ldx, int n_out, int n_in, int64_t P, float* dW,
                  int64_t ldw, float* db, cudaStream_t st) {
   if (n_out <= 16 && P > 0) {
-    const int threads = 128;
-    const int64_t chunk = 512;
-    dim3 grid((unsigned)cdiv(n_in, threads), (unsigned)cdiv(P, chunk));
-    wgrad_small_kernel<16><<<grid, threads, 0, st>>>(dZ, ldz, X, ldx, n_out, n_in, P, chunk, dW, ldw, db);
+    const int64_t chunk = 256;
+    dim3 grid((unsigned)cdiv(n_in, 128), (unsigned)cdiv(P, chunk));
+    wgrad_small_kernel<16><<<grid, 512, 0, st>>>(dZ, ldz, X, ldx, n_out, n_in, P, chunk, dW, ldw, db);
     NUDF_LAUNCH_OK();
     return 0;
   }
   int split = (int)cdiv(P, 2048);
   EpiAtomicAdd ew{dW, ldw};
-  if (int rc = gemm_tn(dZ, ldz, X, ldx, n_out, n_in, P, ew, st, split)) return rc;
-  if (db) return colsum(dZ, ldz, nullptr, 1.f, P, n_out, db, st);
-  return 0;
+  return gemm_tn(dZ, ldz, X, ldx, n_out, n_in, P, ew, st, split, TC_WGRAD, db);
 }
 
 // =================================================================================================================

@@ -14,7 +14,7 @@ struct UdfPlan {
   int in_dim[NUDF_MAX_LAYERS], out_dim[NUDF_MAX_LAYERS];
   int64_t w_off[NUDF_MAX_LAYERS], w_ld[NUDF_MAX_LAYERS], w_total;
   int64_t b_off[NUDF_MAX_LAYERS], b_total;
-  int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_nt3[NUDF_MAX_LAYERS], img_total;   // uint16 offsets of the bf16 hi/lo weight images
+  int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_nt3[NUDF_MAX_LAYERS], img_nn1, img_total;   // uint16 offsets of the bf16 hi/lo weight images
   int pe_ld, y_ld;
   int a_ld[NUDF_MAX_LAYERS];    // ld of A[l] (input of layer l), l >= 1
   int o_ld[NUDF_MAX_LAYERS];    // ld of D[l] / Q[l] (out_dim rounded)
@@ -51,6 +51,9 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
     p->img_nn[l] = ioff; ioff += tc::image_elems(p->in_dim[l], p->out_dim[l], 2);   // operand of dY W   (N = in,  K = out)
     p->img_nt3[l] = ioff; ioff += tc::image_elems(p->out_dim[l], p->in_dim[l], 3);  // 3-plane image for the value chain
   }
+  // feature rows 1.. of the last layer as a (N = in, K = d_out - 1) operand: the udf-head row is applied as a rank-1 update
+  p->img_nn1 = ioff;
+  if (p->d_out > 1) ioff += tc::image_elems(p->in_dim[p->n_lin - 1], p->d_out - 1, 2);
   p->img_total = round_up(ioff, 8);
   NUDF_REQUIRE(p->in_dim[0] == p->d_pe, "in_dim[0] must equal the positional-encoding width");
   NUDF_REQUIRE(p->out_dim[p->n_lin - 1] == p->d_out, "last layer width must equal d_out");
@@ -66,14 +69,7 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
 // ---- context / scratch layout (all offsets in floats; every block starts 16B-aligned) -------------------------
 struct UdfCtx {
   int64_t e0, a[NUDF_MAX_LAYERS], y, sgn, d[NUDF_MAX_LAYERS], gpe, ge, total;
-  // split-bf16 plane copies (gemm_pl.cuh) of A[l] (l = 0: the encoding) and D[l]: operands of the weight gradients.
-  // pl_off: float offset of the plane area (aligned to 1024 B at run time); apl / dpl: uint16 offsets inside it.
-  int64_t pl_off, apl[NUDF_MAX_LAYERS], dpl[NUDF_MAX_LAYERS];
 };
-static inline uint16_t* plane_area(float* base, int64_t off) {
-  return reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(base + off) + 1023) & ~(uintptr_t)1023);
-}
-static inline int cb_of(int cols) { return (cols + 63) / 64; }
 static void ctx_layout(const UdfPlan& p, int64_t P, int with_grad, UdfCtx* c) {
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
@@ -85,16 +81,11 @@ static void ctx_layout(const UdfPlan& p, int64_t P, int with_grad, UdfCtx* c) {
     for (int l = 0; l < p.n_lin - 1; ++l) c->d[l] = take(P * p.o_ld[l]);
     c->gpe = take(P * p.pe_ld);
     c->ge = take(P * p.pe_ld);
-    int64_t e = 0;
-    for (int l = 0; l < p.n_lin; ++l) { c->apl[l] = e; e += tc::planes_elems(P, p.in_dim[l]); }
-    for (int l = 0; l < p.n_lin - 1; ++l) { c->dpl[l] = e; e += tc::planes_elems(P, p.out_dim[l]); }
-    c->pl_off = take(e / 2 + 256);
   }
   c->total = off;
 }
 struct UdfScratch {
   int64_t edot, adot[2], q[NUDF_MAX_LAYERS], zlast, total;
-  int64_t pl_off, adpl[NUDF_MAX_LAYERS], zpl[NUDF_MAX_LAYERS];   // plane copies of Adot[l] and Zbar[l]
 };
 static void scratch_layout(const UdfPlan& p, int64_t P, UdfScratch* s) {
   int64_t off = 0;
@@ -104,10 +95,6 @@ static void scratch_layout(const UdfPlan& p, int64_t P, UdfScratch* s) {
   s->adot[1] = take(P * p.max_ld);
   for (int l = 0; l < p.n_lin - 1; ++l) s->q[l] = take(P * p.o_ld[l]);
   s->zlast = take(P * p.y_ld);
-  int64_t e = 0;
-  for (int l = 0; l < p.n_lin; ++l) { s->adpl[l] = e; e += tc::planes_elems(P, p.in_dim[l]); }
-  for (int l = 0; l < p.n_lin; ++l) { s->zpl[l] = e; e += tc::planes_elems(P, p.out_dim[l]); }
-  s->pl_off = take(e / 2 + 256);
   s->total = off;
 }
 
@@ -324,6 +311,18 @@ __global__ void zlast_kernel(const float* __restrict__ ob, int64_t ld_ob, const 
   z[row * y_ld + c] = v;
 }
 
+// Same, split: zf[:, j] = ob[:, 1 + j] (features, ld = F) and z0 = sgn * ob[:, 0] / scale (udf head)
+__global__ void zlast_split_kernel(const float* __restrict__ ob, int64_t ld_ob, const float* __restrict__ sgn, float inv_scale,
+                                   int F, int64_t P, float* __restrict__ zf, float* __restrict__ z0) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t row = idx / (F + 1);
+  int c = (int)(idx - row * (F + 1));
+  if (row >= P) return;
+  float v = ob[row * ld_ob + c];
+  if (c == 0) z0[row] = v * sgn[row] * inv_scale;
+  else zf[row * F + (c - 1)] = v;
+}
+
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)cdiv(n, t); }
 
 // ---- host orchestration -----------------------------------------------------------------------------------------
@@ -341,6 +340,10 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
       if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.in_dim[l], p.out_dim[l], 1, 2, img + p.img_nn[l], st)) return rc;
       if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, 3, img + p.img_nt3[l], st)) return rc;
     }
+    const int last = p.n_lin - 1;
+    if (p.d_out > 1)
+      if (int rc = tc::prep_weights(wfold + p.w_off[last] + p.w_ld[last], p.w_ld[last], p.in_dim[last], p.d_out - 1, 1, 2, img + p.img_nn1, st))
+        return rc;
   }
   return 0;
 }
@@ -349,21 +352,12 @@ static inline const uint16_t* img_base(const UdfPlan& p, const float* wfold) {
 }
 
 static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P,
-                       float* ctx, const UdfCtx& c, cudaStream_t st, bool planes = false) {
+                       float* ctx, const UdfCtx& c, cudaStream_t st) {
   float* e0 = ctx + c.e0;
-  uint16_t* pla = planes ? plane_area(ctx, c.pl_off) : nullptr;
-  auto apl = [&](int l) { return tc::Planes{pla + c.apl[l], cb_of(p.in_dim[l])}; };
   float* askip = nullptr; int askip_ld = 0, askip_col = 0;
   if (p.skip >= 1) { askip = ctx + c.a[p.skip]; askip_ld = p.a_ld[p.skip]; askip_col = p.out_dim[p.skip - 1]; }
   pe_forward_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, P, p.L, p.scale, e0, p.pe_ld, askip, askip_ld, askip_col);
   NUDF_LAUNCH_OK();
-  if (planes) {
-    if (int rc = tc::pack_planes(e0, p.pe_ld, P, p.d_pe, apl(0), st)) return rc;
-    if (askip)
-      if (int rc = pack_range(askip, askip_ld, P, askip_col, askip_col + p.d_pe, apl(p.skip), st)) return rc;
-    for (int l = 1; l < p.n_lin; ++l)
-      if (int rc = tc::zero_pad_rows(P, apl(l), st)) return rc;
-  }
   for (int l = 0; l < p.n_lin; ++l) {
     const float* A = l == 0 ? e0 : ctx + c.a[l];
     int64_t lda = l == 0 ? p.pe_ld : p.a_ld[l];
@@ -371,7 +365,6 @@ static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wf
     int rc;
     if (l < p.n_lin - 1) {
       EpiAct epi{ctx + c.a[l + 1], p.a_ld[l + 1], d->bias[l], ACT_SOFTPLUS100, (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f};
-      if (planes) epi.pl = apl(l + 1);
       rc = gemm_nt(A, lda, W, p.w_ld[l], P, p.out_dim[l], p.in_dim[l], epi, st, img_base(p, wfold) + p.img_nt3[l], TC_FWD, 3);
     } else {
       // the last layer always runs on the exact-fp32 engine: its row 0 is the udf head
@@ -384,12 +377,8 @@ static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wf
 }
 
 static int reverse_chain(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, float* ctx, const UdfCtx& c,
-                         float* grad, cudaStream_t st, bool planes) {
+                         float* grad, cudaStream_t st) {
   const int last = p.n_lin - 1;
-  uint16_t* pla = planes ? plane_area(ctx, c.pl_off) : nullptr;
-  if (planes)
-    for (int l = 0; l < last; ++l)
-      if (int rc = tc::zero_pad_rows(P, tc::Planes{pla + c.dpl[l], cb_of(p.out_dim[l])}, st)) return rc;
   auto make_rev = [&](int l) {  // epilogue that turns G (wrt A[l]) into D[l-1]
     EpiRev e;
     e.n_main = p.out_dim[l - 1];
@@ -397,7 +386,6 @@ static int reverse_chain(const UdfPlan& p, const float* wfold, const float* pts,
     e.Anext = ctx + c.a[l]; e.lda = p.a_ld[l]; e.a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
     e.Dprev = ctx + c.d[l - 1]; e.ldd = p.o_ld[l - 1];
     e.Gpe = (l == p.skip) ? ctx + c.gpe : nullptr; e.ldg = p.pe_ld;
-    if (planes) e.dpl = tc::Planes{pla + c.dpl[l - 1], cb_of(p.out_dim[l - 1])};
     return e;
   };
   {
@@ -470,12 +458,11 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
   cudaStream_t st = (cudaStream_t)stream;
   UdfCtx c;
   ctx_layout(p, P, grad != nullptr, &c);
-  const bool planes = grad != nullptr && planes_on();
-  if (int rc = value_chain(p, d, wfold, pts, P, ctx, c, st, planes)) return rc;
+  if (int rc = value_chain(p, d, wfold, pts, P, ctx, c, st)) return rc;
   udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
                                                               ctx + c.sgn);
   NUDF_LAUNCH_OK();
-  if (grad) return reverse_chain(p, wfold, pts, P, ctx, c, grad, st, planes);
+  if (grad) return reverse_chain(p, wfold, pts, P, ctx, c, grad, st);
   return 0;
 }
 
@@ -516,41 +503,18 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
   scratch_layout(p, P, &s);
   const int last = p.n_lin - 1;
   const int split = (int)cdiv(P, 2048);
-  // weight gradients read both operands as split-bf16 planes (written by the producing epilogues) when the tensor engine
-  // owns them; the choice must be the one nudf_udf_forward made for this ctx (engine / mask unchanged in between).
-  // A null grad_bar also covers a ctx that nudf_udf_forward filled without the gradient part (no plane area).
-  const bool planes = planes_on() && grad_bar != nullptr;
-  uint16_t* cpl = planes ? plane_area(ctx, c.pl_off) : nullptr;
-  uint16_t* spl = planes ? plane_area(scratch, s.pl_off) : nullptr;
-  auto apl = [&](int l) { return tc::Planes{cpl + c.apl[l], cb_of(p.in_dim[l])}; };
-  auto dpl = [&](int l) { return tc::Planes{cpl + c.dpl[l], cb_of(p.out_dim[l])}; };
-  auto adpl = [&](int l) { return tc::Planes{spl + s.adpl[l], cb_of(p.in_dim[l])}; };
-  auto zpl = [&](int l) { return tc::Planes{spl + s.zpl[l], cb_of(p.out_dim[l])}; };
-  if (planes)
-    for (int l = 0; l <= last; ++l) {
-      if (l >= 1 && grad_bar)
-        if (int rc = tc::zero_pad_rows(P, adpl(l), st)) return rc;
-      if (l < last)
-        if (int rc = tc::zero_pad_rows(P, zpl(l), st)) return rc;
-    }
 
   // ---- tangent chain (second-order terms) ----
   if (grad_bar) {
     float* edot = scratch + s.edot;
     pe_jvp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, grad_bar, P, p.L, p.scale, edot, p.pe_ld);
     NUDF_LAUNCH_OK();
-    if (planes)
-      if (int rc = tc::pack_planes(edot, p.pe_ld, P, p.d_pe, adpl(0), st)) return rc;
     const float* adot = edot;
     int64_t ld_adot = p.pe_ld;
     for (int l = 0; l < last; ++l) {
       // dW_l += D_l^T Adot_l
       EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
-      if (planes) {
-        if (int rc = gemm_tn_planes(dpl(l), p.out_dim[l], adpl(l), p.in_dim[l], P, ew, st)) return rc;
-      } else {
-        if (int rc = gemm_tn(ctx + c.d[l], p.o_ld[l], adot, ld_adot, p.out_dim[l], p.in_dim[l], P, ew, st, split)) return rc;
-      }
+      if (int rc = gemm_tn(ctx + c.d[l], p.o_ld[l], adot, ld_adot, p.out_dim[l], p.in_dim[l], P, ew, st, split)) return rc;
       float* nxt = scratch + s.adot[l & 1];
       int64_t ld_nxt = p.a_ld[l + 1];
       EpiTan et;
@@ -559,7 +523,6 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
       et.D = ctx + c.d[l]; et.ldd = p.o_ld[l];
       et.Q = scratch + s.q[l]; et.ldq = p.o_ld[l];
       et.AdotNext = nxt; et.ldn = ld_nxt; et.post_scale = (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
-      if (planes) et.npl = adpl(l + 1);
       if (int rc = gemm_nt(adot, ld_adot, wfold + p.w_off[l], p.w_ld[l], P, p.out_dim[l], p.in_dim[l], et, st,
                            img_base(p, wfold) + p.img_nt[l], TC_TAN))
         return rc;
@@ -567,8 +530,6 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
         copy_cols_kernel<<<nblk(P * p.d_pe, 256), 256, 0, st>>>(edot, p.pe_ld, nxt, ld_nxt, p.out_dim[l], p.d_pe, P,
                                                                  NUDF_SQRT1_2);
         NUDF_LAUNCH_OK();
-        if (planes)
-          if (int rc = pack_range(nxt, ld_nxt, P, p.out_dim[l], p.out_dim[l] + p.d_pe, adpl(l + 1), st)) return rc;
       }
       adot = nxt; ld_adot = ld_nxt;
     }
@@ -582,22 +543,40 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
     for (int l = 0; l < last; ++l)
       NUDF_CUDA_OK(cudaMemsetAsync(scratch + s.q[l], 0, sizeof(float) * P * p.o_ld[l], st));
   float* zl = scratch + s.zlast;
-  if (out_bar) {
+  const int F = p.d_out - 1;
+  const bool split_head = out_bar != nullptr && tc_on(TC_BWD) && F >= 64 && (F % 4) == 0 && tc::pad64(F) <= 64 * tc::WR_MAX_SLICES;
+  if (split_head) {
+    // 257 = 1 udf-head row + 256 feature rows: the feature block is a K = 256 contraction for the weights-resident tensor
+    // kernel, the head row a rank-1 update in its epilogue (and a weighted column sum for its weight gradient).
+    float* zf = zl;
+    float* z0 = zl + P * F;
+    zlast_split_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
+    NUDF_LAUNCH_OK();
+    const float* Wl = wfold + p.w_off[last];
+    float* dWl = dwfold + p.w_off[last];
+    EpiAtomicAdd ew{dWl + p.w_ld[last], p.w_ld[last]};
+    if (int rc = gemm_tn(zf, F, ctx + c.a[last], p.a_ld[last], F, p.in_dim[last], P, ew, st, split, TC_WGRAD, dbias + p.b_off[last] + 1))
+      return rc;
+    if (int rc = colsum(ctx + c.a[last], p.a_ld[last], z0, 1.0f, P, p.in_dim[last], dWl, st)) return rc;
+    if (int rc = colsum(z0, 1, nullptr, 1.0f, P, 1, dbias + p.b_off[last], st)) return rc;
+    EpiBwdR1 eb;
+    eb.n_main = p.out_dim[last - 1]; eb.post_scale = (last == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+    eb.Anext = ctx + c.a[last]; eb.lda = p.a_ld[last]; eb.a_unscale = (last == p.skip) ? 1.41421356237309504880f : 1.0f;
+    eb.QZ = scratch + s.q[last - 1]; eb.ldq = p.o_ld[last - 1];
+    eb.z0 = z0; eb.w0 = Wl;
+    if (int rc = gemm_nn(zf, F, Wl + p.w_ld[last], p.w_ld[last], P, p.in_dim[last], F, eb, st, img_base(p, wfold) + p.img_nn1, TC_BWD))
+      return rc;
+  } else if (out_bar) {
     zlast_kernel<<<nblk(P * p.y_ld, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, p.d_out, p.y_ld, P, zl);
     NUDF_LAUNCH_OK();
     EpiAtomicAdd ew{dwfold + p.w_off[last], p.w_ld[last]};
-    if (planes) {
-      if (int rc = tc::pack_planes(zl, p.y_ld, P, p.out_dim[last], zpl(last), st)) return rc;
-      if (int rc = gemm_tn_planes(zpl(last), p.out_dim[last], apl(last), p.in_dim[last], P, ew, st)) return rc;
-    } else {
-      if (int rc = gemm_tn(zl, p.y_ld, ctx + c.a[last], p.a_ld[last], p.out_dim[last], p.in_dim[last], P, ew, st, split)) return rc;
-    }
-    if (int rc = colsum(zl, p.y_ld, nullptr, 1.f, P, p.out_dim[last], dbias + p.b_off[last], st)) return rc;
+    if (int rc = gemm_tn(zl, p.y_ld, ctx + c.a[last], p.a_ld[last], p.out_dim[last], p.in_dim[last], P, ew, st, split, TC_WGRAD,
+                         dbias + p.b_off[last]))
+      return rc;
     EpiBwd eb;
     eb.n_main = p.out_dim[last - 1]; eb.post_scale = (last == p.skip) ? NUDF_SQRT1_2 : 1.0f;
     eb.Anext = ctx + c.a[last]; eb.lda = p.a_ld[last]; eb.a_unscale = (last == p.skip) ? 1.41421356237309504880f : 1.0f;
     eb.QZ = scratch + s.q[last - 1]; eb.ldq = p.o_ld[last - 1];
-    if (planes) eb.zpl = zpl(last - 1);
     if (int rc = gemm_nn(zl, p.y_ld, wfold + p.w_off[last], p.w_ld[last], P, p.in_dim[last], p.out_dim[last], eb, st,
                          img_base(p, wfold) + p.img_nn[last], TC_BWD))
       return rc;
@@ -607,18 +586,12 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
     const float* A = l == 0 ? ctx + c.e0 : ctx + c.a[l];
     int64_t lda = l == 0 ? p.pe_ld : p.a_ld[l];
     EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
-    if (planes && out_bar) {
-      if (int rc = gemm_tn_planes(zpl(l), p.out_dim[l], apl(l), p.in_dim[l], P, ew, st)) return rc;
-    } else {
-      if (int rc = gemm_tn(zb, p.o_ld[l], A, lda, p.out_dim[l], p.in_dim[l], P, ew, st, split)) return rc;
-    }
-    if (int rc = colsum(zb, p.o_ld[l], nullptr, 1.f, P, p.out_dim[l], dbias + p.b_off[l], st)) return rc;
+    if (int rc = gemm_tn(zb, p.o_ld[l], A, lda, p.out_dim[l], p.in_dim[l], P, ew, st, split, TC_WGRAD, dbias + p.b_off[l])) return rc;
     if (l > 0) {
       EpiBwd eb;
       eb.n_main = p.out_dim[l - 1]; eb.post_scale = (l == p.skip) ? NUDF_SQRT1_2 : 1.0f;
       eb.Anext = ctx + c.a[l]; eb.lda = p.a_ld[l]; eb.a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
       eb.QZ = scratch + s.q[l - 1]; eb.ldq = p.o_ld[l - 1];
-      if (planes) eb.zpl = zpl(l - 1);
       if (int rc = gemm_nn(zb, p.o_ld[l], wfold + p.w_off[l], p.w_ld[l], P, p.in_dim[l], p.out_dim[l], eb, st,
                            img_base(p, wfold) + p.img_nn[l], TC_BWD))
         return rc;

@@ -195,15 +195,22 @@ def test_nerf_and_color_on_tensor_engine_vs_oracle(golden):
         dirs = dirs / dirs.norm(dim=1, keepdim=True)
         ab = torch.randn(P, 1, generator=gen, dtype=torch.float64)
         rb = torch.randn(P, 3, generator=gen, dtype=torch.float64)
-        p64 = oracle_params(g, "nerf", torch.float64, True)
-        oa, orgb = O.nerf_mlp(p64, g.nerf_c, pts4, dirs)
-        gr = dict(zip(p64.keys(), torch.autograd.grad((oa * ab).sum() + (orgb * rb).sum(), list(p64.values()))))
+        # the 2^9 positional-encoding frequency amplifies fp32 input rounding to ~1e-4, which flips ReLU gates: the fp32
+        # run of the oracle is the yardstick for that noise (parity protocol), the fp64 run the arbiter
+        res = {}
+        for dt in (torch.float64, torch.float32):
+            pd = oracle_params(g, "nerf", dt, True)
+            oa, orgb = O.nerf_mlp(pd, g.nerf_c, pts4.to(dt), dirs.to(dt))
+            gr = dict(zip(pd.keys(), torch.autograd.grad((oa * ab.to(dt)).sum() + (orgb * rb.to(dt)).sum(), list(pd.values()))))
+            res[dt] = (oa.detach(), orgb.detach(), gr)
+        oa, orgb, gr = res[torch.float64]
+        oa32, orgb32, gr32 = res[torch.float32]
         a, rgb = nerf(pts4.float().to(DEV), dirs.float().to(DEV))
-        parity("tc.nerf.alpha", a, oa, None, tol=1e-4)
-        parity("tc.nerf.rgb", rgb, orgb, None, tol=1e-4)
+        parity("tc.nerf.alpha", a, oa, oa32, tol=1e-4)
+        parity("tc.nerf.rgb", rgb, orgb, orgb32, tol=1e-4)
         ((a * ab.float().to(DEV)).sum() + (rgb * rb.float().to(DEV)).sum()).backward()
         for k, v in nerf.named_parameters():
-            parity("tc.nerf.dparam." + k, v.grad, gr[k], None, tol=5e-3)   # the fp32 reference itself is ~2e-3 here
+            parity("tc.nerf.dparam." + k, v.grad, gr[k], gr32[k], tol=5e-4, noise_mult=3.0)
         # colour network
         pts = g.t("col_pts").to(DEV); d3 = g.t("col_dirs").to(DEV); feat = g.t("col_feat").to(DEV).requires_grad_(True)
         cb, c, bl = col(pts, None, d3, feat)

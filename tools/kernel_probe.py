@@ -31,6 +31,14 @@ def planes(x):
 
 
 Xp, Yp = planes(X), planes(Y)
+if len(sys.argv) > 1 and sys.argv[1] == "ablate":
+    import os
+    import subprocess
+    for dbg in (0, 1, 2, 8, 3, 10, 9):
+        env = dict(os.environ, NUDF_TC_DEBUG=str(dbg))
+        out = subprocess.run([sys.executable, __file__, "time", "wgrad_tc_plane_operands"], env=env, capture_output=True, text=True)
+        print("NUDF_TC_DEBUG=%d (1 no copies, 2 no epilogue, 8 no MMAs):" % dbg, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "time":
     flush = torch.empty(64 * 1024 * 1024, device=dev)
     calls = {
@@ -39,6 +47,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
         "pack_planes": lambda: lib.nudf_pack_planes(L.ptr(X), 256, P, 256, L.ptr(Xp), st),
     }
     for name, call in calls.items():
+        if len(sys.argv) > 2 and name != sys.argv[2]:
+            continue
         for _ in range(3):
             call()
         t = 0.0
