@@ -374,7 +374,7 @@ def render_core_outside(nerf_fn, o, d, z, sample_dist, n_outside):
 
 
 # ----------------------------------------------------------------------------------------------
-# a13: render_core, models/udf_renderer_blending.py:327-584 (blending inputs = None) --------------
+# a13: render_core, models/udf_renderer_blending.py:327-584 (blending branch: a16 below) ----------
 # ----------------------------------------------------------------------------------------------
 
 def composite(d, pts, mid, dists, udf, grads, scb, sc_, inv_s, beta, gamma, cos_anneal_ratio=None,
@@ -436,7 +436,8 @@ def composite(d, pts, mid, dists, udf, grads, scb, sc_, inv_s, beta, gamma, cos_
 def render_core(udf_p, udf_c, col_p, col_c, sc, o, d, z, sample_dist, cos_anneal_ratio=None,
                 background_rgb=None, background_alpha=None, background_sampled_color=None,
                 flip_saturation=0.0, sparse_scale_factor=25000.0, use_norm_grad_for_cosine=False,
-                beta_min=5e-5):
+                beta_min=5e-5, blending=None):
+    """blending: None or dict(color_maps, w2cs, intrinsics, query_c2w, rays_uv) (rays_uv may be None)."""
     n_rays, n = z.shape
     dists = _append_last(z[..., 1:] - z[..., :-1], sample_dist)
     mid = z + dists * 0.5
@@ -464,7 +465,125 @@ def render_core(udf_p, udf_c, col_p, col_c, sc, o, d, z, sample_dist, cos_anneal
     ret["beta"] = 1.0 / beta
     ret["gamma"] = gamma
     ret["blending_weights"] = blend.reshape(n_rays, n, -1)
+    if blending is not None:
+        ret.update(blend_outputs(ret, pts, d, blending["color_maps"], blending["w2cs"], blending["intrinsics"],
+                                 blending["query_c2w"], blending.get("rays_uv"), background_sampled_color))
     return ret
+
+
+# ----------------------------------------------------------------------------------------------
+# a16: pixel / patch blending of the fine-tuning stage ------------------------------------------
+#   models/udf_renderer_blending.py:431-480, 503-524; models/patch_projector.py:21-166;
+#   models/projector_utils.py:8-85; models/fields.py:498-537.  Written per source view (V is small).
+# ----------------------------------------------------------------------------------------------
+
+def pixel_warp(pts, imgs, intrinsics, w2cs):
+    """pts [N,S,3], imgs [V,3,H,W] -> colours [N,S,V,3], in-image mask [N,S,V]  (patch_projector.py:21-43)."""
+    n_views, _, h, w = imgs.shape
+    cols, masks = [], []
+    for v in range(n_views):
+        pm = intrinsics[v, :3, :3] @ w2cs[v, :3, :]                       # projector_utils.py:69-70
+        cam = pts @ pm[:, :3].T + pm[:, 3]
+        zc = cam[..., 2].clamp(min=1e-3)
+        gx = 2 * (cam[..., 0] / zc) / (w - 1) - 1
+        gy = 2 * (cam[..., 1] / zc) / (h - 1) - 1
+        gx = torch.where((gx > 1) | (gx < -1), torch.full_like(gx, 2.0), gx)      # :36-40, padding 'zeros'
+        gy = torch.where((gy > 1) | (gy < -1), torch.full_like(gy, 2.0), gy)
+        grid = torch.stack([gx, gy], dim=-1)[None]
+        masks.append((gx.abs() < 1.0) & (gy.abs() < 1.0))
+        cols.append(F.grid_sample(imgs[v:v + 1], grid, padding_mode="zeros", align_corners=True)[0].permute(1, 2, 0))
+    return torch.stack(cols, dim=2), torch.stack(masks, dim=2)
+
+
+def patch_warp(pts, uv, normals, imgs, ref_intrinsic, src_intrinsics, ref_c2w, src_c2ws, h_patch_size=3,
+               plane_dist_thresh=0.001):
+    """Plane-induced homographies of the reference patch into every source view (patch_projector.py:45-150).
+    pts, normals [N,S,3]; uv [N,2] in (-1,1) -> colours [N,S,V,Npx,3], mask [N,S,V,Npx]."""
+    normals = normals.detach()                                            # detach_normal=True at the call site (:455)
+    n_rays, n_samples, _ = pts.shape
+    n_views, _, h, w = imgs.shape
+    px = torch.stack([(uv[:, 0] + 1) / 2.0 * (w - 1), (uv[:, 1] + 1) / 2.0 * (h - 1)], dim=-1)
+    r = torch.arange(-h_patch_size, h_patch_size + 1, dtype=pts.dtype)
+    oy, ox = torch.meshgrid(r, r, indexing="ij")
+    offs = torch.stack([ox.reshape(-1), oy.reshape(-1)], dim=-1)          # (dx, dy), dx fastest (:212-214)
+    pix = px[:, None, :] + offs[None]                                     # [N,Npx,2]
+    hom_pix = torch.cat([pix, torch.ones_like(pix[..., :1])], dim=-1)     # [N,Npx,3]
+    k_ref_inv = torch.inverse(ref_intrinsic[:3, :3])
+    w2c_ref = torch.inverse(ref_c2w)
+    dist_to_cam = torch.linalg.norm(pts - ref_c2w[:3, 3], dim=-1)         # [N,S]
+    cols, masks = [], []
+    with torch.no_grad():
+        n_cam = normals @ w2c_ref[:3, :3].T                               # plane normal in the reference camera frame
+        p_cam = pts @ w2c_ref[:3, :3].T + w2c_ref[:3, 3]
+        d1 = (n_cam * p_cam).sum(-1)                                      # plane distance to the reference camera
+        sgn = torch.sign(d1)
+        sgn[sgn == 0] = 1
+        d_safe = torch.clamp(d1.abs(), 1e-8) * sgn
+    for v in range(n_views):
+        with torch.no_grad():
+            rel = torch.inverse(src_c2ws[v]) @ ref_c2w
+            r_rel, t_rel = rel[:3, :3], rel[:3, 3]
+            c_src = -(r_rel.T @ t_rel)                                    # source camera centre in the reference frame
+            d2 = (n_cam * c_src).sum(-1)
+            ok = (d1.abs() > plane_dist_thresh) & ((d1 - d2).abs() > plane_dist_thresh) & ((d2 / d1) < 1)
+            k_src = src_intrinsics[v, :3, :3]
+            hom = k_src @ (r_rel + t_rel[:, None] * n_cam[..., None, :] / d_safe[..., None, None]) @ k_ref_inv
+            zax = torch.tensor([0.0, 0.0, 1.0], dtype=pts.dtype)
+            hom_fp = k_src @ (r_rel + t_rel[:, None] * zax[None, :] / dist_to_cam[..., None, None]) @ k_ref_inv
+            hom = torch.where(ok[..., None, None], hom, hom_fp)           # fronto-parallel fallback (:120-129)
+        wp = torch.einsum("nsik,npk->nspi", hom, hom_pix)                 # [N,S,Npx,3]
+        g = wp[..., :2] / torch.clamp(wp[..., 2:], 1e-8)
+        m = (wp[..., 2] > 0) & (g[..., 0] < (w - h_patch_size)) & (g[..., 1] < (h - h_patch_size)) & \
+            (g >= h_patch_size).all(dim=-1)
+        gn = torch.stack([2 * g[..., 0] / (w - 1) - 1, 2 * g[..., 1] / (h - 1) - 1], dim=-1).clamp(-10, 10)
+        c = F.grid_sample(imgs[v:v + 1], gn.reshape(1, -1, 1, 2), align_corners=True)[0, :, :, 0].T
+        cols.append(c.reshape(n_rays, n_samples, -1, 3))
+        masks.append(m)
+    return torch.stack(cols, dim=2), torch.stack(masks, dim=2)
+
+
+def color_blend(blend_logits, pix_col, pix_mask, pat_col=None, pat_mask=None):
+    """Masked-softmax fusion over the source views (fields.py:498-537, img_index=None)."""
+    n_views = pix_col.shape[-2]
+    sm = torch.softmax(blend_logits[..., :n_views], dim=-1)
+    wp = sm * pix_mask
+    wp = wp / (wp.sum(dim=-1, keepdim=True) + 1e-8)
+    c_pix = (pix_col * wp[..., None]).sum(dim=-2)
+    c_pat, m_pat = None, None
+    if pat_col is not None:
+        full = pat_mask.sum(dim=-1) > pat_col.shape[3] - 1                # every pixel of the patch lands inside
+        wq = sm * full
+        wq = wq / (wq.sum(dim=-1, keepdim=True) + 1e-8)
+        c_pat = (pat_col * wq[..., None, None]).sum(dim=-3)
+        m_pat = full.sum(dim=-1) > 0
+    return c_pix, c_pat, m_pat
+
+
+def blend_outputs(ret, pts, d, color_maps, w2cs, intrinsics, query_c2w, rays_uv, background_sampled_color=None,
+                  h_patch_size=3):
+    """color_pixel / patch_colors / patch_mask of render_core (:431-480, 503-524) from a composite() result."""
+    n_rays, n = ret["udf"].shape
+    p3 = pts.reshape(n_rays, n, 3)
+    pix_col, pix_mask = pixel_warp(p3, color_maps, intrinsics, w2cs)
+    pat_col, pat_mask = None, None
+    if rays_uv is not None:
+        g = ret["gradients"].reshape(n_rays, n, 3).detach()
+        gn = g / (torch.linalg.norm(g, ord=2, dim=-1, keepdim=True) + 1e-5)
+        flip = -torch.sign((d[:, None, :] * gn).sum(-1, keepdim=True))
+        flip[flip == 0] = 1
+        pat_col, pat_mask = patch_warp(p3, rays_uv, flip * gn, color_maps, intrinsics[0], intrinsics, query_c2w,
+                                       torch.inverse(w2cs), h_patch_size)
+    c_pix, c_pat, m_pat = color_blend(ret["blending_weights"], pix_col, pix_mask, pat_col, pat_mask)
+    w = ret["weights"]
+    if background_sampled_color is not None:
+        inside = ret["inside_sphere"][:, :, None]
+        c_pix = c_pix * inside + background_sampled_color[:, :n] * (1.0 - inside)
+        c_pix = torch.cat([c_pix, background_sampled_color[:, n:]], dim=1)
+    out = {"color_pixel": (c_pix * w[:, :c_pix.shape[1], None]).sum(dim=1), "patch_colors": None, "patch_mask": None}
+    if c_pat is not None:
+        out["patch_colors"] = (c_pat * w[:, :n, None, None]).sum(dim=1)
+        out["patch_mask"] = (m_pat.to(w.dtype) * w[:, :n]).sum(dim=1)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

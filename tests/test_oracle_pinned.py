@@ -162,3 +162,52 @@ def test_whole_render_dtu(golden, dtype, tag):
             assert rel_err(npar[pn].grad.reshape(-1)[::GRAD_STRIDE], g.t(key + "_sub")) < 1e-7, key
     key = "render_grad.udf.lin4.weight_v_f64"
     assert rel_err(up["lin4.weight_v"].grad.reshape(-1)[::GRAD_STRIDE], g.t(key + "_sub")) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a16: pixel / patch blending (fixtures of oracle/make_golden_blend.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _blend_fx():
+    import os
+    import numpy as np
+    from tests.golden_util import GOLDEN
+    return np.load(os.path.join(GOLDEN, "blend_outputs.npz"))
+
+
+def test_oracle_patch_projector_matches_reference():
+    fx = _blend_fx()
+    v = O.make_blend_views(16, n_views=6, seed=0)
+    pts, nrm = torch.from_numpy(fx["proj_pts"]), torch.from_numpy(fx["proj_normals"])
+    c, m = O.pixel_warp(pts, v["color_maps"], v["intrinsics"], v["w2cs"])
+    assert torch.equal(m, torch.from_numpy(fx["proj_pixel_mask"]))
+    assert (c - torch.from_numpy(fx["proj_pixel_color"])).abs().max() < 2e-6
+    c, m = O.patch_warp(pts, v["rays_uv"], nrm, v["color_maps"], v["intrinsics"][0], v["intrinsics"], v["query_c2w"],
+                        torch.inverse(v["w2cs"]))
+    assert (m != torch.from_numpy(fx["proj_patch_mask"])).float().mean() < 1e-4
+    assert (c - torch.from_numpy(fx["proj_patch_color"])).abs().max() < 2e-4      # fp32, pixel coordinates up to 64
+
+
+def test_oracle_render_core_with_blending_matches_reference_fp64(golden):
+    fx = _blend_fx()
+    g = golden
+    dt = torch.float64
+    v = {k: t.to(dt) for k, t in O.make_blend_views(16, n_views=6, seed=0).items()}
+    udf_p, col_p, nerf_p = (O.to_dtype(g.params[k], dt) for k in ("udf", "color", "nerf"))
+    sc = O.to_dtype(g.params["sc"], dt)
+    z = torch.from_numpy(fx["blend_z"]).to(dt)
+    z_feed = torch.from_numpy(fx["blend_z_feed"]).to(dt)
+    # the reference takes sample_dist from its fp64 run; the fixture stores the fp32 run's value
+    sd = ((v["far"] - v["near"]) / 32).mean().item()
+    z64 = v["near"] + (v["far"] - v["near"]) * torch.linspace(0.0, 1.0, 32, dtype=dt)[None, :]
+    zo = torch.linspace(1e-3, 1.0 - 1.0 / 9.0, 8, dtype=dt)
+    zo = v["far"] / torch.flip(zo, dims=[-1]) + 1.0 / 32
+    zf64, _ = torch.sort(torch.cat([z64, zo], dim=-1), dim=-1)
+    assert rel_err(z64, z) < 1e-6 and rel_err(zf64, z_feed) < 1e-6
+    bg = O.render_core_outside(lambda p, d: O.nerf_mlp(nerf_p, g.nerf_c, p, d), v["rays_o"], v["rays_d"], zf64, sd, 8)
+    ret = O.render_core(udf_p, g.udf_c, col_p, g.col_c, sc, v["rays_o"], v["rays_d"], z64, sd, cos_anneal_ratio=0.8,
+                        background_alpha=bg["alpha"], background_sampled_color=bg["sampled_color"], flip_saturation=0.1,
+                        blending=dict(color_maps=v["color_maps"], w2cs=v["w2cs"], intrinsics=v["intrinsics"],
+                                      query_c2w=v["query_c2w"], rays_uv=v["rays_uv"]))
+    for k in ("color_base", "color", "color_pixel", "patch_colors", "patch_mask", "weights", "depth"):
+        ref = torch.from_numpy(fx["blend_%s_f64" % k])
+        assert rel_err(ret[k].reshape(ref.shape), ref) < 2e-7, k        # the warps run through fp64 grid_sample
