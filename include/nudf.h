@@ -34,6 +34,11 @@ int nudf_get_engine(void);
  * 8 backward, 16 weight gradients, 32 colour-network backward, 64 NeRF++ backward, 128 colour / NeRF++ forward. */
 int nudf_set_tc_mask(int mask);
 int nudf_get_tc_mask(void);
+/* Plane-fed reverse-sweep / tangent chains (engine 1 only): intermediate tensors of those chains are kept as split-bf16
+ * plane tensors (see nudf_pack_planes) and fetched with cp.async.bulk.  Default 0 (env NUDF_PLANES).  Like the engine
+ * and the mask it must not change between a forward call and its backward (the ctx layout depends on it). */
+int nudf_set_chain_planes(int on);
+int nudf_get_chain_planes(void);
 /* --- tensor engine building blocks (unit-tested on their own) ---
  * weight image: bf16 hi/lo split of B(n,k) in UMMA shared-memory order; `transposed` selects B(n,k) = W[k*ldw+n]. */
 /* planes: 2 = hi/lo (3 products, ~4e-6 vs fp64), 3 = hi/mid/lo (6 products, fp32-grade; used by the value chain) */
@@ -53,6 +58,10 @@ int nudf_wgrad(const float* dZ, int64_t ldz, const float* X, int64_t ldx, int32_
 int64_t nudf_planes_elems(int64_t rows, int32_t cols);
 int nudf_pack_planes(const float* X, int64_t ldx, int64_t rows, int32_t cols, uint16_t* planes, void* stream);
 int nudf_unpack_planes(const uint16_t* planes, int64_t rows, int32_t cols, float* X, int64_t ldx, void* stream);
+/* Y = act(X W^T + b), X given as a plane tensor allocated for round_up(M, 128) rows, W as a 2-plane weight image
+ * (nudf_tc_prepare_weights, transposed = 0), K <= 256: the plane-fed weights-resident chain kernel on one layer. */
+int nudf_dense_forward_planes(const uint16_t* X_planes, const uint16_t* img, const float* bias, float* Y, int64_t ldy, int64_t M,
+                              int32_t N, int32_t K, int32_t act, void* stream);
 /* dW[n_out, n_in] += dZ[P, n_out]^T X[P, n_in], both operands plane tensors (replaces the autograd weight gradient of one
  * nn.Linear, models/fields.py:185; tensor engine only). */
 int nudf_wgrad_planes(const uint16_t* dZ_planes, const uint16_t* X_planes, int32_t n_out, int32_t n_in, int64_t P, float* dW,

@@ -79,9 +79,13 @@ _SIGNATURES = {
                                              c_void_p]),
     "nudf_wgrad": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                   ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int32, c_void_p]),
+    "nudf_set_chain_planes": (ctypes.c_int, [ctypes.c_int]),
+    "nudf_get_chain_planes": (ctypes.c_int, []),
     "nudf_planes_elems": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32]),
     "nudf_pack_planes": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, c_void_p, c_void_p]),
     "nudf_unpack_planes": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int32, c_void_p, ctypes.c_int64, c_void_p]),
+    "nudf_dense_forward_planes": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                 ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_void_p]),
     "nudf_wgrad_planes": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, c_void_p,
                                          ctypes.c_int64, c_void_p]),
     "nudf_dense_forward": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p, c_void_p,

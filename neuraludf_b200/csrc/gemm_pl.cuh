@@ -167,6 +167,183 @@ gemm_tn_pl_kernel(Planes X, int M, Planes Y, int N, int64_t P, int64_t blocks_pe
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// C[M x N] = epi( A[M x K] * B^T )  with A a plane tensor, B the pre-split weight image (weights-resident, K <= 256).
+// Same structure as gemm_wr_kernel (gemm_tc.cuh) but the A operand is never touched by a thread: one lane issues 8 KB
+// cp.async.bulk copies of plane blocks into a 3-slot ring of single-plane K slices (hi(ks), lo(ks), hi(ks+1), ...) and the
+// MMAs of each slot as it lands.  The 8 producer warps of gemm_wr become 8 more epilogue warps: 16 warps drain the
+// double-buffered TMEM accumulator, one 32x32 block each per tile (112 registers per epilogue thread via setmaxnreg).
+// Plane tensors passed here must be allocated with their rows padded to 128 (planes_elems(round_up(M, 128), K)).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PW_SLOTS = 3;
+constexpr int PW_EPI_WARPS = 16;
+constexpr int PW_THREADS = (PW_EPI_WARPS + 4) * 32;      // + warpgroup 4: warp 16 MMA issuer / TMEM owner, warp 17 loader, 2 idle
+struct SmemCtlW {
+  uint64_t full[PW_SLOTS];
+  uint64_t empty[PW_SLOTS];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint64_t wfull;
+  uint32_t tmem_addr;
+};
+
+template <class Epi>
+__global__ void __launch_bounds__(PW_THREADS, 1)
+gemm_wrp_kernel(Planes A, int64_t M, int N, int K, const uint16_t* __restrict__ img, Epi epi, int reverse, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * WR_N;
+  const int t = n0 / 256;
+  const int rows_t = tile_rows(N, t, 2);
+  const int row_in_tile = n0 - t * 256;
+  int rows_h = rows_t - row_in_tile; rows_h = rows_h < WR_N ? rows_h : WR_N;
+  const int n_slices = pad64(K) / 64;
+  const uint32_t w_plane_bytes = (uint32_t)rows_h * 128u;
+  uint8_t* w_smem = smem;                                                    // [slice][plane][rows_h x 128 B]
+  uint8_t* a_smem = smem + (size_t)n_slices * 2 * w_plane_bytes;             // PW_SLOTS x 16 KB (1024-aligned: rows_h % 16 == 0)
+  float* epi_stage = reinterpret_cast<float*>(a_smem + PW_SLOTS * A_HALF_BYTES);
+  SmemCtlW* ctl = reinterpret_cast<SmemCtlW*>(reinterpret_cast<uint8_t*>(epi_stage) + PW_EPI_WARPS * EPI_WARP_FLOATS * sizeof(float));
+  const uint16_t* img_t = img + tile_offset(N, K, t, 2);
+  const int64_t n_mtiles = (M + BM - 1) / BM;
+  const uint32_t acc_cols = tmem_cols_for(rows_h);
+
+  if (tid == 0) {
+    for (int s = 0; s < PW_SLOTS; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&ctl->tfull[a], 1); mbar_init(&ctl->tempty[a], PW_EPI_WARPS * 32); }
+    mbar_init(&ctl->wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == PW_EPI_WARPS) tmem_alloc(&ctl->tmem_addr, 2 * acc_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = ctl->tmem_addr;
+
+  if (warp < PW_EPI_WARPS) {
+    // 5 warps per scheduler cap the kernel at 96 registers per thread; the MMA / loader warpgroup hands 64 x 128 back and
+    // the 512 epilogue threads take +16 each (setmaxnreg.inc only draws from the CTA's own released registers)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    uint32_t it = 0;
+    for (int64_t jt = blockIdx.x; jt < n_mtiles; jt += gridDim.x, ++it) {
+      const int64_t mt = reverse ? n_mtiles - 1 - jt : jt;
+      const uint32_t a = it & 1u, au = it >> 1;
+      auto acc_ready = [&]() { mbar_wait(&ctl->tfull[a], au & 1u); tcgen05_fence_after(); };
+      if (dbg & 2) acc_ready();
+      else
+      run_epilogue<Epi, decltype(acc_ready), 2>(tmem_base + a * acc_cols, warp & 3, lane, 32 * (warp >> 2), 128, 1, 0u,
+                                                mt * BM + (warp & 3) * 32, M, n0, rows_h, N, epi_stage + warp * EPI_WARP_FLOATS, epi, 0,
+                                                acc_ready);
+      tcgen05_fence_before();
+      mbar_arrive(&ctl->tempty[a]);
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    const int64_t my_tiles = n_mtiles > (int64_t)blockIdx.x ? (n_mtiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int pieces_per_tile = 2 * n_slices;
+    const int64_t total = my_tiles * pieces_per_tile;
+    if (warp == PW_EPI_WARPS) {
+      // ---- warp 16, lane 0: MMA issuer.  It only ever waits for data (full[]) and for a free accumulator (tempty[]),
+      //      never for the completion of its own MMAs: a commit -> mbarrier -> poll round trip per piece would serialise
+      //      issue and completion (measured: ~0.8 us per piece, a 45 us floor per launch). ----
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc((uint32_t)rows_h);
+        const uint32_t w_addr = smem_u32(w_smem);
+        mbar_wait(&ctl->wfull, 0);
+        int64_t p = 0;
+        for (int64_t lt = 0; lt < my_tiles; ++lt) {
+          const uint32_t a = (uint32_t)(lt & 1), au = (uint32_t)(lt >> 1);
+          if (au > 0) mbar_wait(&ctl->tempty[a], (au - 1) & 1u);
+          tcgen05_fence_after();
+          const uint32_t acc = tmem_base + a * acc_cols;
+          for (int r = 0; r < pieces_per_tile; ++r, ++p) {
+            const int slot = (int)(p % PW_SLOTS);
+            mbar_wait(&ctl->full[slot], (uint32_t)((p / PW_SLOTS) & 1));
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(a_smem + slot * A_HALF_BYTES);
+            const uint32_t w_hi = w_addr + (uint32_t)(r >> 1) * 2u * w_plane_bytes, w_lo = w_hi + w_plane_bytes;
+            if (dbg & 8) {
+            } else if ((r & 1) == 0) {                // hi plane of the slice: hi * lo(W), hi * hi(W)
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j) {
+                mma_bf16(acc, make_desc(a_addr + j * 32), make_desc(w_lo + j * 32), idesc, (r == 0 && j == 0) ? 0u : 1u);
+                mma_bf16(acc, make_desc(a_addr + j * 32), make_desc(w_hi + j * 32), idesc, 1u);
+              }
+            } else {                                  // lo plane: lo * hi(W)
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j) mma_bf16(acc, make_desc(a_addr + j * 32), make_desc(w_hi + j * 32), idesc, 1u);
+            }
+            mma_commit(&ctl->empty[slot]);
+            if (r == pieces_per_tile - 1) mma_commit(&ctl->tfull[a]);
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == PW_EPI_WARPS + 1) {
+      // ---- warp 17: weight fetch (one 16 KB copy per lane), then lane 0 streams the A pieces through the ring ----
+      if (lane == 0) mbar_arrive_expect_tx(&ctl->wfull, (uint32_t)n_slices * 2u * w_plane_bytes);
+      __syncwarp();
+      if (lane < 2 * n_slices) {
+        const int ks = lane >> 1, pl = lane & 1;
+        const uint16_t* src = img_t + (int64_t)ks * 2 * rows_t * 64 + (int64_t)pl * rows_t * 64 + (int64_t)row_in_tile * 64;
+        bulk_g2s(w_smem + (size_t)(ks * 2 + pl) * w_plane_bytes, src, w_plane_bytes, &ctl->wfull);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        // piece p -> (local tile p / ppt, slice (p % ppt) / 2, plane p % 2); two 8 KB copies (row blocks 2 mt, 2 mt + 1)
+        for (int64_t p = 0; p < total; ++p) {
+          const int slot = (int)(p % PW_SLOTS);
+          const int64_t u = p / PW_SLOTS;
+          if (u > 0) mbar_wait(&ctl->empty[slot], (uint32_t)((u - 1) & 1));
+          if (dbg & 1) { mbar_arrive(&ctl->full[slot]); continue; }
+          const int64_t lt = p / pieces_per_tile;
+          const int r = (int)(p - lt * pieces_per_tile);
+          const int64_t jt = (int64_t)blockIdx.x + lt * gridDim.x;
+          const int64_t mt = reverse ? n_mtiles - 1 - jt : jt;
+          uint8_t* dst = a_smem + slot * A_HALF_BYTES;
+          mbar_arrive_expect_tx(&ctl->full[slot], (uint32_t)A_HALF_BYTES);
+          bulk_g2s(dst, pl_block(A, 2 * mt, r >> 1, r & 1), PL_PLANE_BYTES, &ctl->full[slot]);
+          bulk_g2s(dst + PL_PLANE_BYTES, pl_block(A, 2 * mt + 1, r >> 1, r & 1), PL_PLANE_BYTES, &ctl->full[slot]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == PW_EPI_WARPS) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 2 * acc_cols);
+  }
+}
+
+template <class Epi>
+static inline int gemm_wrp(const Planes& A, int64_t M, int N, int K, const uint16_t* img, const Epi& epi, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  const int n_slices = pad64(K) / 64;
+  if (n_slices > WR_MAX_SLICES || A.cb < n_slices) {
+    set_error("gemm_wrp: K = %d does not fit the weights-resident plane kernel", K);
+    return -1;
+  }
+  const size_t smem = (size_t)n_slices * 2 * WR_N * 128 + (size_t)PW_SLOTS * A_HALF_BYTES + PW_EPI_WARPS * EPI_WARP_FLOATS * sizeof(float) +
+                      sizeof(SmemCtlW) + 1024 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_wrp_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int64_t n_mtiles = cdiv(M, BM);
+  const int nh = (int)cdiv(pad16(N), WR_N);
+  int64_t gx = sm_count() / nh;
+  if (gx < 1) gx = 1;
+  if (gx > n_mtiles) gx = n_mtiles;
+  dim3 grid((unsigned)gx, (unsigned)nh);
+  static int flip = 0;
+  flip ^= 1;
+  gemm_wrp_kernel<Epi><<<grid, PW_THREADS, smem, st>>>(A, M, N, K, img, epi, flip, tc_debug());
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
 static inline int pack_planes(const float* X, int64_t ldx, int64_t rows, int cols, const Planes& out, cudaStream_t st) {
   if (rows <= 0) return 0;
   const int64_t total = ((rows + 63) & ~(int64_t)63) * out.cb * 16;

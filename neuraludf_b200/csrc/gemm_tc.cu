@@ -79,6 +79,17 @@ int nudf_unpack_planes(const uint16_t* planes, int64_t rows, int32_t cols, float
   return 0;
 }
 
+// Y = act(X W^T + b) with X a plane tensor of round_up(M, 128) rows (weights-resident plane-fed kernel, K <= 256)
+int nudf_dense_forward_planes(const uint16_t* Xp, const uint16_t* img, const float* bias, float* Y, int64_t ldy, int64_t M, int32_t N,
+                              int32_t K, int32_t act, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  NUDF_REQUIRE(Xp && img && Y, "null pointer");
+  NUDF_REQUIRE((reinterpret_cast<uintptr_t>(Xp) & 1023) == 0, "plane tensors must be 1024-byte aligned");
+  NUDF_REQUIRE(act >= 0 && act <= 3, "bad act");
+  EpiAct e{Y, ldy, bias, act, 1.0f};
+  return tc::gemm_wrp(tc::Planes{const_cast<uint16_t*>(Xp), (K + 63) / 64}, M, N, K, img, e, (cudaStream_t)stream);
+}
+
 // dW[n_out, n_in] += dZ^T X with both operands given as plane tensors of P rows (pad rows zero)
 int nudf_wgrad_planes(const uint16_t* dZp, const uint16_t* Xp, int32_t n_out, int32_t n_in, int64_t P, float* dW, int64_t ldw,
                       void* stream) {

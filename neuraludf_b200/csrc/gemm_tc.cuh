@@ -312,11 +312,59 @@ struct NoWait {
 // Software pipeline: the auxiliary global loads of pass p+1 (16 rows x 32 columns per warp) are issued before pass p is
 // computed and stored, and those of the very first pass before `wait()` (the accumulator-ready barrier) returns, so that
 // two passes' worth of loads are in flight per warp -- the epilogues are bound by memory-level parallelism, not by math.
-template <class Epi, class Wait = NoWait>
+// G = row groups (of 4 rows x 32 columns per warp instruction) whose auxiliary loads are in flight together: 4 with 8
+// epilogue warps; 2 for the 16-warp plane-fed kernel, whose threads have 112 registers (same bytes in flight per SM).
+template <class Epi, class Wait = NoWait, int G = 4>
 __device__ __forceinline__ void run_epilogue(uint32_t tmem_acc, int quad, int lane, int chunk0, int chunk_step, int n_acc,
                                              uint32_t acc_stride, int64_t row0, int64_t M, int col_base, int n_pad, int n_valid_end,
                                              float* stg, const Epi& epi, int rot = 0, Wait wait = Wait()) {
   const int cq = lane & 7, rsub = lane >> 3;
+  if constexpr (G != 4) {
+    const int n_it2 = n_pad > chunk0 ? (n_pad - chunk0 + chunk_step - 1) / chunk_step : 0;
+    wait();
+    for (int it = 0; it < n_it2; ++it) {
+      const int c0 = chunk0 + ((it + rot) % n_it2) * chunk_step;
+      const int col = col_base + c0 + 4 * cq;
+      int nv = n_valid_end - col;
+      nv = nv < 4 ? nv : 4;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        {
+          // the accumulator block is re-read from TMEM for each 16-row pass (cheap) so that its 32 values are not live
+          // across the functor's loads and stores: this path runs with 112 registers per thread
+          float v[32];
+          tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+          if ((lane >> 4) == h) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(stg + (lane & 15) * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int sub = 0; sub < 4 / G; ++sub) {
+          typename Epi::Aux aux[G];
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int64_t row = row0 + 16 * h + rsub + 4 * (sub * G + i);
+            if (row < M && nv > 0) epi.load(row, col, nv, aux[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int r = rsub + 4 * (sub * G + i);
+            const float4 t = *reinterpret_cast<const float4*>(stg + r * EPI_LD + 4 * cq);
+            const int64_t row = row0 + 16 * h + r;
+            if (row < M && nv > 0) {
+              const float x[4] = {t.x, t.y, t.z, t.w};
+              epi.apply(row, col, x, nv, aux[i]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
   // rot: start the column chunks at a CTA-dependent position (split-K CTAs would otherwise all reduce into the same
   // addresses at the same time)
   const int n_it = n_pad > chunk0 ? (n_pad - chunk0 + chunk_step - 1) / chunk_step : 0;

@@ -109,6 +109,33 @@ def test_planes_round_trip(rows, cols):
     assert float(((y - x).abs() / x.abs().clamp(min=1e-30)).max()) <= 2.0 ** -16
 
 
+@pytest.mark.parametrize("M,N,K,act", [(4096, 256, 256, 2), (300, 217, 256, 0), (129, 256, 39, 0), (1000, 39, 217, 0), (65536, 256, 256, 2)])
+def test_dense_planes_vs_fp64(M, N, K, act):
+    """one layer on the plane-fed weights-resident kernel (A operand fetched as plane blocks by cp.async.bulk)"""
+    L, lib = _lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn(M, K, generator=g, dtype=torch.float64) * 0.5
+    W = torch.randn(N, K, generator=g, dtype=torch.float64) / K ** 0.5
+    b = torch.randn(N, generator=g, dtype=torch.float64) * 0.1
+    ref = X @ W.t() + b
+    if act == 2:
+        ref = torch.nn.functional.softplus(ref, beta=100)
+    Xd = X.float().to(DEV).contiguous()
+    rows_pad = (M + 127) // 128 * 128
+    buf = torch.empty(lib.nudf_planes_elems(rows_pad, K) + 512, dtype=torch.int16, device=DEV)
+    off = (-buf.data_ptr() % 1024) // 2
+    pl = buf[off:off + lib.nudf_planes_elems(rows_pad, K)]
+    pl.fill_(0x7FC0)                                  # NaN in the rows beyond M: they must not leak into valid rows
+    L.check(lib.nudf_pack_planes(L.ptr(Xd), K, M, K, L.ptr(pl), L.stream_ptr()), "pack")
+    img = _image(W.float().to(DEV).contiguous(), N, K, 0)
+    Y = torch.full((M, N), float("nan"), device=DEV)
+    bd = b.float().to(DEV)
+    L.check(lib.nudf_dense_forward_planes(L.ptr(pl), L.ptr(img), L.ptr(bd), L.ptr(Y), N, M, N, K, act, L.stream_ptr()), "dense_planes")
+    e = err_inf(Y, ref) / scale_inf(ref)
+    report("tc.dense_planes[%d,%d,%d]" % (M, N, K), rel=e)
+    assert e < 3e-5, e
+
+
 @pytest.mark.parametrize("P,n_out,n_in", [(4096, 256, 256), (1000, 128, 64), (70, 257, 39), (65536, 256, 256), (333, 217, 256)])
 def test_wgrad_planes_vs_fp64(P, n_out, n_in):
     """weight-gradient contraction with both operands fetched as plane blocks (MN-major UMMA operands)"""

@@ -36,7 +36,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "ablate":
     import subprocess
     for dbg in (0, 1, 2, 8, 3, 10, 9):
         env = dict(os.environ, NUDF_TC_DEBUG=str(dbg))
-        out = subprocess.run([sys.executable, __file__, "time", "wgrad_tc_plane_operands"], env=env, capture_output=True, text=True)
+        out = subprocess.run([sys.executable, __file__, "time", sys.argv[2] if len(sys.argv) > 2 else "wgrad_tc_plane_operands"], env=env,
+                             capture_output=True, text=True)
         print("NUDF_TC_DEBUG=%d (1 no copies, 2 no epilogue, 8 no MMAs):" % dbg, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
     sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "time":
@@ -44,6 +45,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
     calls = {
         "wgrad_tc_fp32_operands": lambda: lib.nudf_wgrad(L.ptr(Y), 256, L.ptr(X), 256, 256, 256, P, L.ptr(dW), 256, 1, st),
         "wgrad_tc_plane_operands": lambda: lib.nudf_wgrad_planes(L.ptr(Yp), L.ptr(Xp), 256, 256, P, L.ptr(dW), 256, st),
+        "dense_tc_fp32_operand": lambda: lib.nudf_dense_forward_tc(L.ptr(X), 256, L.ptr(imgs[2]), 2, L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st),
+        "dense_tc_plane_operand": lambda: lib.nudf_dense_forward_planes(L.ptr(Xp), L.ptr(imgs[2]), L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st),
         "pack_planes": lambda: lib.nudf_pack_planes(L.ptr(X), 256, P, 256, L.ptr(Xp), st),
     }
     for name, call in calls.items():
