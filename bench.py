@@ -432,7 +432,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    n_rays = 128
+    n_rays = 256          # the same bounded sample as the cpu_baseline leg of the CUDA arm
     cpu = cpu_baseline(steps=args.steps, warmup=max(1, min(args.warmup, 2)), n_rays=n_rays)
     return {"impl": "reference", "metric": "ray-samples/sec (render_core fwd+bwd)", "value": cpu["value"],
             "unit": "ray-samples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
