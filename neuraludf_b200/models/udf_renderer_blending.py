@@ -12,6 +12,8 @@ Differences that are deliberate (DESIGN.md "boundary"):
 Pixel / patch blending (fine-tuning stage, :431-480) warps and blends with torch ops on the GPU (patch_projector.py,
 fields.color_blend) and composites with the differentiable ray weights of the CUDA compositing kernel.
 """
+import itertools
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -21,39 +23,32 @@ from .fields import color_blend
 from .patch_projector import PatchProjector
 
 
+GRID_BLOCK = 64     # the reference queries dense grids in 64^3 blocks (:16-49); 262 144 points per kernel chain here
+
+
+def _grid_query(bound_min, bound_max, resolution, query_func, device, channels):
+    """Evaluate query_func on the resolution^3 lattice spanned by the bounds, block by block; returns a float32 numpy
+    array [R, R, R] (channels == 0) or [R, R, R, channels].  Each block is one device call plus one D2H copy."""
+    axes = [torch.linspace(float(bound_min[a]), float(bound_max[a]), resolution) for a in range(3)]
+    out = np.zeros([resolution] * 3 + ([channels] if channels else []), dtype=np.float32)
+    starts = range(0, resolution, GRID_BLOCK)
+    for i0, j0, k0 in itertools.product(starts, starts, starts):
+        blk = [axes[0][i0:i0 + GRID_BLOCK], axes[1][j0:j0 + GRID_BLOCK], axes[2][k0:k0 + GRID_BLOCK]]
+        pts = torch.cartesian_prod(*blk).to(device)                    # x slowest, z fastest (meshgrid 'ij' order)
+        shape = [len(b) for b in blk] + ([channels] if channels else [])
+        out[i0:i0 + shape[0], j0:j0 + shape[1], k0:k0 + shape[2]] = query_func(pts).reshape(shape).detach().cpu().numpy()
+    return out
+
+
 def extract_fields(bound_min, bound_max, resolution, query_func, device):
-    """Dense grid query in 64^3 blocks (reference :16-31); the per-block .cpu() copy is kept (numpy output)."""
-    N = 64
-    X = torch.linspace(bound_min[0], bound_max[0], resolution).split(N)
-    Y = torch.linspace(bound_min[1], bound_max[1], resolution).split(N)
-    Z = torch.linspace(bound_min[2], bound_max[2], resolution).split(N)
-    u = np.zeros([resolution, resolution, resolution], dtype=np.float32)
+    """Dense scalar grid query (API of the reference's extract_fields, :16-31)."""
     with torch.no_grad():
-        for xi, xs in enumerate(X):
-            for yi, ys in enumerate(Y):
-                for zi, zs in enumerate(Z):
-                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
-                    pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1).to(device)
-                    val = query_func(pts).reshape(len(xs), len(ys), len(zs)).detach().cpu().numpy()
-                    u[xi * N: xi * N + len(xs), yi * N: yi * N + len(ys), zi * N: zi * N + len(zs)] = val
-    return u
+        return _grid_query(bound_min, bound_max, resolution, query_func, device, 0)
 
 
 def extract_gradient_fields(bound_min, bound_max, resolution, query_func, device):
-    """reference :34-49"""
-    N = 64
-    X = torch.linspace(bound_min[0], bound_max[0], resolution).split(N)
-    Y = torch.linspace(bound_min[1], bound_max[1], resolution).split(N)
-    Z = torch.linspace(bound_min[2], bound_max[2], resolution).split(N)
-    u = np.zeros([resolution, resolution, resolution, 3], dtype=np.float32)
-    for xi, xs in enumerate(X):
-        for yi, ys in enumerate(Y):
-            for zi, zs in enumerate(Z):
-                xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
-                pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1).to(device)
-                val = query_func(pts).reshape(len(xs), len(ys), len(zs), 3).detach().cpu().numpy()
-                u[xi * N: xi * N + len(xs), yi * N: yi * N + len(ys), zi * N: zi * N + len(zs)] = val
-    return u
+    """Dense 3-vector grid query (API of the reference's extract_gradient_fields, :34-49)."""
+    return _grid_query(bound_min, bound_max, resolution, query_func, device, 3)
 
 
 def extract_geometry(bound_min, bound_max, resolution, threshold, query_func, device):

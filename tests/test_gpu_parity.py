@@ -444,3 +444,49 @@ def test_full_size_properties(golden):
     rel = err_inf(ga + gb, gfull) / scale_inf(gfull)
     report("full_size.grad_additivity", rel=rel)
     assert rel < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C5: dense grid queries for mesh extraction (extract_fields / extract_gradient_fields over udf_values / gradient)
+# ---------------------------------------------------------------------------------------------------------------
+def test_grid_query_vs_oracle_and_throughput(golden):
+    import time
+    from neuraludf_b200.models.udf_renderer_blending import extract_fields, extract_gradient_fields
+    g = golden
+    udf = build_modules(g, DEV)[0]
+    lo, hi = torch.tensor([-0.9, -0.9, -0.9]), torch.tensor([0.9, 0.9, 0.9])
+    R = 20
+    u = extract_fields(lo, hi, R, lambda p: udf.udf_values(p), DEV)
+    gr = extract_gradient_fields(lo, hi, R, lambda p: udf.gradient(p).squeeze(1), DEV)
+    ax = torch.linspace(-0.9, 0.9, R)
+    pts = torch.cartesian_prod(ax, ax, ax)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        p = oracle_params(g, "udf", dt)
+        x = pts.to(dt).requires_grad_(True)
+        out = O.udf_mlp(p, g.udf_c, x)[:, 0]
+        res[dt] = (out.detach().reshape(R, R, R), torch.autograd.grad(out.sum(), x)[0].reshape(R, R, R, 3))
+    parity("grid.udf", torch.from_numpy(u), res[torch.float64][0], res[torch.float32][0])
+    parity("grid.gradient", torch.from_numpy(gr), res[torch.float64][1], res[torch.float32][1])
+    # throughput of the value-only chain on one 64^3 block (the unit of the reference's 256^3 sweep); reported, not asserted
+    blk = (torch.rand(64 ** 3, 3, device=DEV) * 1.8 - 0.9).contiguous()
+    for _ in range(2):
+        udf.udf_values(blk)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        v = udf.udf_values(blk)
+    torch.cuda.synchronize()
+    dt_v = (time.perf_counter() - t0) / 5
+    with torch.no_grad():
+        for _ in range(2):
+            udf.gradient(blk)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            udf.gradient(blk)
+        torch.cuda.synchronize()
+        dt_g = (time.perf_counter() - t0) / 5
+    report("grid.throughput", udf_values_Mpts_s=64 ** 3 / dt_v / 1e6, value_and_gradient_Mpts_s=64 ** 3 / dt_g / 1e6,
+           sweep_256cubed_s=(dt_v) * 64)
+    assert torch.isfinite(v).all()
