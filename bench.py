@@ -183,6 +183,8 @@ def run_ours(args):
                               up_sample_steps=1, perturb=0.0)
     if args.workload == "c4":
         return run_c4(args, dev, lib, udf, col, var, beta, rank, world)
+    if args.workload == "c3":
+        return run_c3(args, dev, lib, udf, col, var, beta, rank, world)
     o, d, z, sd = rays(seed=rank, device=dev)
     tgt = torch.full((N_RAYS, 3), 0.4, device=dev)
     from neuraludf_b200.dp import GradBucket
@@ -386,6 +388,59 @@ def run_c4(args, dev, lib, udf, col, var, beta, rank, world):
     return None
 
 
+def run_c3(args, dev, lib, udf, col, var, beta, rank, world):
+    """Whole render() of the fine-tuning stage on open-surface shapes: 1024 rays x (64 + 64 importance)
+    samples, no outside samples, pixel + patch blending on (8 source views of 1024 x 1024, 7 x 7 patches), forward +
+    backward.  Secondary number; printed as a reduced JSON line."""
+    import torch.distributed as dist
+    from neuraludf_b200 import synthetic as O
+    from neuraludf_b200.dp import GradBucket
+    from neuraludf_b200.models.udf_renderer_blending import UDFRendererBlending
+    n_rays = 1024
+    ren = UDFRendererBlending(None, udf, var, col, beta, n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4,
+                              perturb=1.0, upsampling_type="classical", h_patch_size=3, use_norm_grad_for_cosine=True)
+    params = [p for m in (udf, col, var, beta) for p in m.parameters() if p.requires_grad]
+    bucket = GradBucket(params)
+    v = {k: t.to(dev) for k, t in O.make_blend_views(n_rays, n_views=8, height=1024, width=1024, seed=rank).items()}
+    tgt = torch.full((n_rays, 3), 0.4, device=dev)
+
+    def step():
+        for p in params:
+            p.grad = None
+        ret = ren.render(v["rays_o"], v["rays_d"], v["near"], v["far"], cos_anneal_ratio=1.0, flip_saturation=0.0,
+                         color_maps=v["color_maps"], w2cs=v["w2cs"], intrinsics=v["intrinsics"], query_c2w=v["query_c2w"],
+                         rays_uv=v["rays_uv"])
+        pm = ret["patch_mask"].detach()
+        loss = (loss_fn(ret, tgt) + 0.5 * (ret["color_pixel"] - tgt).abs().mean()
+                + 0.5 * ((ret["patch_colors"] - 0.4).abs().mean(dim=(1, 2)) * pm).sum() / (pm.sum() + 1e-5))
+        loss.backward()
+        if world > 1:
+            bucket.allreduce_mean()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = lib.nudf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if rank == 0:
+        print(json.dumps({"workload": "c3: render() fwd+bwd with pixel + patch blending, 1024 rays x (64+64) samples, "
+                                      "8 views 1024x1024, 49-pixel patches", "ms_per_step": ms,
+                          "rays_per_s": world * n_rays / (ms * 1e-3),
+                          "fine_ray_samples_per_s": world * n_rays * 128 / (ms * 1e-3), "n_gpus": world,
+                          "gpu_launches_per_step": (lib.nudf_launch_count() - l0) / args.steps}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return None
+
+
 def cpu_baseline(steps, warmup, n_rays):
     """The oracle port (pinned restatement of the reference's PyTorch code) on the host cores: a bounded sample of the
     same workload (n_rays of the 512 rays x 128 samples, forward + backward)."""
@@ -452,9 +507,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                     help="c2 (default, the BASELINE.json headline): render_core fwd+bwd on 512x128 uniform samples; "
-                         "c4: whole render() of confs/udf_dtu_blending.conf (64+50 samples, 32 outside, perturb) fwd+bwd")
+                         "c4: whole render() of confs/udf_dtu_blending.conf (64+50 samples, 32 outside, perturb) fwd+bwd; "
+                         "c3: whole render() with pixel + patch blending on, 1024 rays x (64+64) samples, 8 views")
     ap.add_argument("--quick", action="store_true", help="main timed loop only (for profiler runs): no e2e leg, no "
                     "single-kernel probes, no CPU baseline; prints a reduced JSON line")
     args = ap.parse_args()
