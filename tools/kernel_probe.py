@@ -45,6 +45,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
     calls = {
         "wgrad_tc_fp32_operands": lambda: lib.nudf_wgrad(L.ptr(Y), 256, L.ptr(X), 256, 256, 256, P, L.ptr(dW), 256, 1, st),
         "wgrad_tc_plane_operands": lambda: lib.nudf_wgrad_planes(L.ptr(Yp), L.ptr(Xp), 256, 256, P, L.ptr(dW), 256, st),
+        "dense_fp32_ffma2": lambda: lib.nudf_dense_forward(L.ptr(X), 256, L.ptr(W), 256, L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st),
+        "wgrad_fp32_ffma2": lambda: lib.nudf_wgrad(L.ptr(Y), 256, L.ptr(X), 256, 256, 256, P, L.ptr(dW), 256, 0, st),
         "dense_tc_fp32_operand": lambda: lib.nudf_dense_forward_tc(L.ptr(X), 256, L.ptr(imgs[2]), 2, L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st),
         "dense_tc_plane_operand": lambda: lib.nudf_dense_forward_planes(L.ptr(Xp), L.ptr(imgs[2]), L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st),
         "pack_planes": lambda: lib.nudf_pack_planes(L.ptr(X), 256, P, 256, L.ptr(Xp), st),
