@@ -53,7 +53,7 @@ def ncu_traffic(kernel_substr):
         for line in open(f):
             if line.startswith("== "):
                 cur, rd, wr = line, None, None
-            elif cur and kernel_substr in cur:
+            elif cur and kernel_substr.replace("nudf::", "").replace("tc::", "") in cur.replace("nudf::", "").replace("tc::", ""):
                 parts = line.split()
                 if parts and parts[0] == "dram__bytes_read.sum":
                     rd = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e3 if parts[2].startswith("Kbyte") else 1e9 if parts[2].startswith("Gbyte") else 1)

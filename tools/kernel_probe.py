@@ -66,6 +66,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
     sys.exit(0)
 for _ in range(2):
     lib.nudf_wgrad_planes(L.ptr(Yp), L.ptr(Xp), 256, 256, P, L.ptr(dW), 256, st)
+    lib.nudf_dense_forward_planes(L.ptr(Xp), L.ptr(imgs[2]), L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st)
     lib.nudf_dense_forward(L.ptr(X), 256, L.ptr(W), 256, L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st)
     lib.nudf_dense_forward_tc(L.ptr(X), 256, L.ptr(imgs[2]), 2, L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st)
     lib.nudf_dense_forward_tc(L.ptr(X), 256, L.ptr(imgs[3]), 3, L.ptr(b), L.ptr(Y), 256, P, 256, 256, 2, st)
