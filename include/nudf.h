@@ -266,6 +266,27 @@ int nudf_points_on_rays(const float* rays_o, const float* rays_d, const float* z
 int nudf_outside_points(const float* rays_o, const float* rays_d, const float* z, int32_t n_rays, int32_t n,
                         int32_t col0, float sample_dist, float* pts4, float* dists, void* stream);
 
+/* --- pixel / patch blending of the fine-tuning stage (replaces patch_projector.pixel_warp / patch_warp +
+ * fields.color_blend, models/patch_projector.py:21-166, models/projector_utils.py:8-85, models/fields.py:498-537, as used by
+ * render_core, models/udf_renderer_blending.py:431-480).  One call fuses, for every sample point, the projection into each
+ * source view, the bilinear gathers (pixel colour and homography-warped patch) and the masked-softmax fusion over views.
+ *   pts    [P,3]  sample points (P = n_rays * n_samples, ray-major)
+ *   proj   [V,12] row-major 3x4 matrices K[:3,:3] @ w2c[:3,:] of the source views
+ *   hom    [V,P,9] row-major plane-induced homographies query pixel -> source pixel, or NULL (pixel blending only)
+ *   px     [n_rays,2] pixel coordinates of each ray in the query image (patch centre)
+ *   imgs   [V,3,H,W] source images;  logits [P, ld_logits]: blending logits, the first V columns are used
+ *   c_pix  [P,3] blended pixel colour;  c_pat [P,(2h+1)^2,3] blended patch colours;  m_pat [P] 1 if any view sees the
+ *   whole patch.  Backward: gradients w.r.t. the logits only ([P,V]); everything else is a constant of the graph. */
+typedef struct {
+  int32_t n_rays, n_samples, n_views, height, width, h_patch;
+} nudf_blend_cfg;
+int nudf_blend_forward(const nudf_blend_cfg* cfg, const float* pts, const float* proj, const float* hom, const float* px,
+                       const float* imgs, const float* logits, int64_t ld_logits, float* c_pix, float* c_pat, float* m_pat,
+                       void* stream);
+int nudf_blend_backward(const nudf_blend_cfg* cfg, const float* pts, const float* proj, const float* hom, const float* px,
+                        const float* imgs, const float* logits, int64_t ld_logits, const float* g_pix, const float* g_pat,
+                        float* g_logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

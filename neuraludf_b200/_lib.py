@@ -55,6 +55,10 @@ class RenderOut(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in RENDER_OUT_FIELDS]
 
 
+class BlendCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_rays", "n_samples", "n_views", "height", "width", "h_patch")]
+
+
 class RenderBar(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("color_base", "color", "depth", "weight_sum", "weight_sum_fg_bg", "weights",
                                         "ray_sums")]
@@ -79,6 +83,8 @@ _SIGNATURES = {
                                              c_void_p]),
     "nudf_wgrad": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                   ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int32, c_void_p]),
+    "nudf_blend_forward": (ctypes.c_int, [c_void_p] * 7 + [ctypes.c_int64] + [c_void_p] * 4),
+    "nudf_blend_backward": (ctypes.c_int, [c_void_p] * 7 + [ctypes.c_int64] + [c_void_p] * 4),
     "nudf_set_chain_planes": (ctypes.c_int, [ctypes.c_int]),
     "nudf_get_chain_planes": (ctypes.c_int, []),
     "nudf_planes_elems": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32]),

@@ -9,8 +9,9 @@ Differences that are deliberate (DESIGN.md "boundary"):
   * `render()` evaluates the NeRF++ background only on the n_outside samples render_core consumes (:493-501);
   * per-sample outputs (`gradients`, `alpha*`, ...) are returned detached -- the trainer only uses them after
     .detach() or for logging (exp_runner_blending.py:309-371, 641-668); `weights` is differentiable.
-Pixel / patch blending (fine-tuning stage, :431-480) warps and blends with torch ops on the GPU (patch_projector.py,
-fields.color_blend) and composites with the differentiable ray weights of the CUDA compositing kernel.
+Pixel / patch blending (fine-tuning stage, :431-480): one fused CUDA kernel per pass (csrc/blend.cu: projection, bilinear
+gathers of pixel and homography-warped patch colours, masked-softmax fusion over views), composited with the
+differentiable ray weights of the CUDA compositing kernel; patch_projector.py / fields.color_blend keep the op-by-op form.
 """
 import itertools
 
@@ -262,17 +263,33 @@ class UDFRendererBlending:
                              "fields.py:505)")
         batch_size, n_samples = g3.shape[:2]
         p3 = pts.reshape(batch_size, n_samples, 3)
-        pix_col, pix_mask = self.patch_projector.pixel_warp(p3, color_maps, intrinsics, w2cs, img_wh=None)
-        pat_col, pat_mask = None, None
-        if rays_uv is not None:
+        normals = None
+        if rays_uv is not None:                                  # flipped unit normals of the local surface plane (:446-448)
             gn = g3 / (torch.linalg.norm(g3, ord=2, dim=-1, keepdim=True) + 1e-5)
             cos = (rays_d[:, None, :] * gn).sum(-1, keepdim=True)
-            flip_sign = torch.where(cos == 0, torch.ones_like(cos), -torch.sign(cos))
-            pat_col, pat_mask = self.patch_projector.patch_warp(
-                p3, rays_uv, flip_sign * gn, color_maps, intrinsics[0], intrinsics, query_c2w, torch.inverse(w2cs),
-                img_wh=None, detach_normal=True)
-        c_pix, _, c_pat, m_pat = color_blend(blending_weights, img_index=img_index, pts_pixel_color=pix_col,
-                                             pts_pixel_mask=pix_mask, pts_patch_color=pat_col, pts_patch_mask=pat_mask)
+            normals = torch.where(cos == 0, torch.ones_like(cos), -torch.sign(cos)) * gn
+        if img_index is None and self.h_patch_size <= 3:
+            # fused kernel: projection + bilinear gathers + masked-softmax fusion per point (csrc/blend.cu); the small
+            # per-point homographies come from torch (3x3 algebra on [V, P] matrices, no gradient)
+            n_views = color_maps.shape[0]
+            proj = (intrinsics[:, :3, :3] @ w2cs[:, :3, :]).reshape(n_views, 12)
+            hom, px = None, None
+            if rays_uv is not None:
+                hom, px = self.patch_projector.homographies(p3, rays_uv, normals, color_maps.shape[2:], intrinsics[0],
+                                                            intrinsics, query_c2w, torch.inverse(w2cs))
+                hom = hom.reshape(n_views, -1, 9)
+            c_pix, c_pat, m_pat = ops.blend_views(blending_weights.reshape(batch_size * n_samples, -1), p3.reshape(-1, 3), proj,
+                                                  hom, px, color_maps, batch_size, n_samples, self.h_patch_size)
+        else:
+            # op-by-op path: img_index selection (never used by the runner) and patches larger than 7 x 7
+            pix_col, pix_mask = self.patch_projector.pixel_warp(p3, color_maps, intrinsics, w2cs, img_wh=None)
+            pat_col, pat_mask = None, None
+            if rays_uv is not None:
+                pat_col, pat_mask = self.patch_projector.patch_warp(
+                    p3, rays_uv, normals, color_maps, intrinsics[0], intrinsics, query_c2w, torch.inverse(w2cs),
+                    img_wh=None, detach_normal=True)
+            c_pix, _, c_pat, m_pat = color_blend(blending_weights, img_index=img_index, pts_pixel_color=pix_col,
+                                                 pts_pixel_mask=pix_mask, pts_patch_color=pat_col, pts_patch_mask=pat_mask)
         c_pix = c_pix.view(batch_size, n_samples, 3)
         if background_sampled_color is not None:
             inside = (torch.linalg.norm(p3, ord=2, dim=-1) < 1.0).float()[:, :, None]

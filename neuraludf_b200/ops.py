@@ -486,6 +486,58 @@ def composite(udf, grads, scb, sc, bg_alpha, bg_color, heads, geom, cfg, want_di
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# pixel / patch blending (fine-tuning stage)
+# ---------------------------------------------------------------------------------------------------------------
+class _BlendFunction(torch.autograd.Function):
+    """Fused projection + bilinear gathers + masked-softmax view fusion (nudf_blend_forward / _backward).  Differentiable
+    w.r.t. the blending logits only; points, projections, homographies and images are constants of the graph."""
+
+    @staticmethod
+    def forward(ctx, logits, pts, proj, hom, px, imgs, n_rays, n_samples, h_patch):
+        lib = L.lib()
+        P = n_rays * n_samples
+        V, _, H, W = imgs.shape
+        cfg = L.BlendCfg(n_rays, n_samples, V, H, W, h_patch)
+        logits = logits.contiguous()
+        c_pix = torch.empty(P, 3, device=pts.device)
+        npx = (2 * h_patch + 1) ** 2
+        c_pat = torch.empty(P, npx, 3, device=pts.device) if hom is not None else None
+        m_pat = torch.empty(P, device=pts.device) if hom is not None else None
+        L.check(lib.nudf_blend_forward(ctypes.byref(cfg), L.ptr(pts), L.ptr(proj), L.ptr(hom), L.ptr(px), L.ptr(imgs), L.ptr(logits),
+                                       logits.stride(0), L.ptr(c_pix), L.ptr(c_pat), L.ptr(m_pat), L.stream_ptr()),
+                "nudf_blend_forward")
+        ctx.cfg, ctx.has_patch, ctx.n_logits = cfg, hom is not None, logits.shape[1]
+        ctx.save_for_backward(logits, pts, proj, hom, px, imgs)
+        if hom is None:
+            return c_pix, None, None
+        ctx.mark_non_differentiable(m_pat)
+        return c_pix, c_pat, m_pat
+
+    @staticmethod
+    def backward(ctx, g_pix, g_pat, _g_mask):
+        lib = L.lib()
+        logits, pts, proj, hom, px, imgs = ctx.saved_tensors
+        V = ctx.cfg.n_views
+        P = pts.shape[0]
+        g_pix = g_pix.contiguous() if g_pix is not None else None
+        g_pat = g_pat.contiguous() if (g_pat is not None and ctx.has_patch) else None
+        g_log = torch.zeros(P, ctx.n_logits, device=pts.device)
+        g_v = torch.empty(P, V, device=pts.device)
+        L.check(lib.nudf_blend_backward(ctypes.byref(ctx.cfg), L.ptr(pts), L.ptr(proj), L.ptr(hom), L.ptr(px), L.ptr(imgs),
+                                        L.ptr(logits), logits.stride(0), L.ptr(g_pix), L.ptr(g_pat), L.ptr(g_v), L.stream_ptr()),
+                "nudf_blend_backward")
+        g_log[:, :V] = g_v
+        return g_log, None, None, None, None, None, None, None, None
+
+
+def blend_views(logits, pts, proj, hom, px, imgs, n_rays, n_samples, h_patch):
+    """logits [P, >=V] (grad), pts [P,3], proj [V,12], hom [V,P,9] or None, px [n_rays,2] or None, imgs [V,3,H,W] ->
+    blended pixel colour [P,3], blended patch colours [P,Npx,3] or None, patch-visible mask [P] (0/1) or None."""
+    f = lambda t: None if t is None else t.detach().float().contiguous()
+    return _BlendFunction.apply(logits, f(pts), f(proj), f(hom), f(px), f(imgs), int(n_rays), int(n_samples), int(h_patch))
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # sampling
 # ---------------------------------------------------------------------------------------------------------------
 _U_CACHE = {}

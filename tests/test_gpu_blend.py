@@ -116,3 +116,59 @@ def test_whole_render_with_blending_runs_and_trains_all_networks(golden):
     ret2 = ren.render(v["rays_o"], v["rays_d"], v["near"], v["far"], cos_anneal_ratio=1.0, perturb_overwrite=0,
                       color_maps=v["color_maps"], w2cs=v["w2cs"], intrinsics=v["intrinsics"], query_c2w=v["query_c2w"])
     assert ret2["color_pixel"] is not None and ret2["patch_colors"] is None and ret2["patch_mask"] is None
+
+
+@pytest.mark.parametrize("with_patch", [True, False])
+def test_fused_blend_kernel_vs_op_by_op(with_patch):
+    """ops.blend_views (csrc/blend.cu) against PatchProjector.pixel_warp / patch_warp + color_blend on the same device:
+    blended colours, patch mask and the gradient w.r.t. the blending logits; a size that does not divide the block."""
+    from neuraludf_b200 import ops
+    from neuraludf_b200.models.fields import color_blend
+    from neuraludf_b200.models.patch_projector import PatchProjector
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    N, S, V, h = 37, 19, 5, 3
+    v = {k: t.to(DEV) for k, t in make_blend_views(N, n_views=V, height=96, width=128, seed=9).items()}
+    g = torch.Generator().manual_seed(3)
+    z = v["near"] + (v["far"] - v["near"]) * torch.linspace(0.0, 1.0, S, device=DEV)[None, :]
+    pts = (v["rays_o"][:, None, :] + v["rays_d"][:, None, :] * z[..., None]).contiguous()
+    nrm = -v["rays_d"][:, None, :] + 0.6 * torch.randn(N, S, 3, generator=g).to(DEV)
+    nrm = nrm / nrm.norm(dim=-1, keepdim=True)
+    logits = (torch.randn(N, S, 10, generator=g) * 1.5).to(DEV).requires_grad_(True)
+    pp = PatchProjector(h)
+    pix_col, pix_mask = pp.pixel_warp(pts, v["color_maps"], v["intrinsics"], v["w2cs"])
+    pat_col = pat_mask = None
+    if with_patch:
+        pat_col, pat_mask = pp.patch_warp(pts, v["rays_uv"], nrm, v["color_maps"], v["intrinsics"][0], v["intrinsics"],
+                                          v["query_c2w"], torch.inverse(v["w2cs"]))
+    c_pix, _, c_pat, m_pat = color_blend(logits, None, pix_col, pix_mask, pat_col, pat_mask)
+    g_pix = torch.randn(N, S, 3, generator=g).to(DEV)
+    g_pat = torch.randn(N, S, 49, 3, generator=g).to(DEV)
+    loss = (c_pix * g_pix).sum() + ((c_pat * g_pat).sum() if with_patch else 0.0)
+    loss.backward()
+    ref_grad = logits.grad.clone()
+    logits.grad = None
+
+    proj = (v["intrinsics"][:, :3, :3] @ v["w2cs"][:, :3, :]).reshape(V, 12)
+    hom = px = None
+    if with_patch:
+        hom, px = pp.homographies(pts, v["rays_uv"], nrm, (96, 128), v["intrinsics"][0], v["intrinsics"], v["query_c2w"],
+                                  torch.inverse(v["w2cs"]))
+        hom = hom.reshape(V, -1, 9)
+    f_pix, f_pat, f_m = ops.blend_views(logits.reshape(N * S, 10), pts.reshape(-1, 3), proj, hom, px, v["color_maps"], N, S, h)
+    loss2 = (f_pix.view(N, S, 3) * g_pix).sum() + ((f_pat.view(N, S, 49, 3) * g_pat).sum() if with_patch else 0.0)
+    loss2.backward()
+    e_pix = float((f_pix.view(N, S, 3) - c_pix).abs().max())
+    e_grad = float((logits.grad - ref_grad).abs().max()) / max(1.0, float(ref_grad.abs().max()))
+    report("blend.fused.%s" % ("patch" if with_patch else "pixel"), pix=e_pix, grad_rel=e_grad)
+    assert e_pix < 5e-6 and e_grad < 5e-5
+    assert float(logits.grad[..., V:].abs().max()) == 0.0
+    if with_patch:
+        ref_m = m_pat.reshape(-1).float()
+        same = f_m == ref_m
+        assert float((~same).float().mean()) < 2e-3 and 0.2 < float(ref_m.mean()) < 1.0
+        e_pat = float((f_pat.view(N, S, 49, 3) - c_pat).abs().reshape(N * S, -1).max(-1).values[same].max())
+        report("blend.fused.patch_colors", err=e_pat)
+        assert e_pat < 1e-5
+    else:
+        assert f_pat is None and f_m is None
