@@ -29,16 +29,17 @@ GRID_BLOCK = 64     # the reference queries dense grids in 64^3 blocks (:16-49);
 
 def _grid_query(bound_min, bound_max, resolution, query_func, device, channels):
     """Evaluate query_func on the resolution^3 lattice spanned by the bounds, block by block; returns a float32 numpy
-    array [R, R, R] (channels == 0) or [R, R, R, channels].  Each block is one device call plus one D2H copy."""
-    axes = [torch.linspace(float(bound_min[a]), float(bound_max[a]), resolution) for a in range(3)]
-    out = np.zeros([resolution] * 3 + ([channels] if channels else []), dtype=np.float32)
+    array [R, R, R] (channels == 0) or [R, R, R, channels].  The grid is assembled on the device and copied to the host
+    once (the reference copies and synchronises after every block)."""
+    axes = [torch.linspace(float(bound_min[a]), float(bound_max[a]), resolution, device=device) for a in range(3)]
+    out = torch.zeros([resolution] * 3 + ([channels] if channels else []), dtype=torch.float32, device=device)
     starts = range(0, resolution, GRID_BLOCK)
     for i0, j0, k0 in itertools.product(starts, starts, starts):
         blk = [axes[0][i0:i0 + GRID_BLOCK], axes[1][j0:j0 + GRID_BLOCK], axes[2][k0:k0 + GRID_BLOCK]]
-        pts = torch.cartesian_prod(*blk).to(device)                    # x slowest, z fastest (meshgrid 'ij' order)
+        pts = torch.cartesian_prod(*blk)                               # x slowest, z fastest (meshgrid 'ij' order)
         shape = [len(b) for b in blk] + ([channels] if channels else [])
-        out[i0:i0 + shape[0], j0:j0 + shape[1], k0:k0 + shape[2]] = query_func(pts).reshape(shape).detach().cpu().numpy()
-    return out
+        out[i0:i0 + shape[0], j0:j0 + shape[1], k0:k0 + shape[2]] = query_func(pts).detach().reshape(shape).float()
+    return out.cpu().numpy()
 
 
 def extract_fields(bound_min, bound_max, resolution, query_func, device):
