@@ -269,7 +269,7 @@ class UDFRendererBlending:
             gn = g3 / (torch.linalg.norm(g3, ord=2, dim=-1, keepdim=True) + 1e-5)
             cos = (rays_d[:, None, :] * gn).sum(-1, keepdim=True)
             normals = torch.where(cos == 0, torch.ones_like(cos), -torch.sign(cos)) * gn
-        if img_index is None and self.h_patch_size <= 3:
+        if img_index is None and self.h_patch_size <= 3 and color_maps.shape[0] <= 32:
             # fused kernel: projection + bilinear gathers + masked-softmax fusion per point (csrc/blend.cu); the small
             # per-point homographies come from torch (3x3 algebra on [V, P] matrices, no gradient)
             n_views = color_maps.shape[0]
@@ -282,7 +282,7 @@ class UDFRendererBlending:
             c_pix, c_pat, m_pat = ops.blend_views(blending_weights.reshape(batch_size * n_samples, -1), p3.reshape(-1, 3), proj,
                                                   hom, px, color_maps, batch_size, n_samples, self.h_patch_size)
         else:
-            # op-by-op path: img_index selection (never used by the runner) and patches larger than 7 x 7
+            # op-by-op path: img_index selection (never used by the runner), patches larger than 7 x 7, > 32 source views
             pix_col, pix_mask = self.patch_projector.pixel_warp(p3, color_maps, intrinsics, w2cs, img_wh=None)
             pat_col, pat_mask = None, None
             if rays_uv is not None:
