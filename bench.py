@@ -303,7 +303,7 @@ def run_ours(args):
         dom = "dense_tcgen05_3xbf16" if lib.nudf_get_engine() == 1 else "dense_fp32_ffma"
         ach = ktimes[dom]["algorithmic_tflops"]
         engine = lib.nudf_get_engine()
-        cpu = cpu_baseline(steps=2, warmup=1, n_rays=256)
+        cpu = cpu_baseline(steps=2, warmup=1, n_rays=256) if world == 1 else None      # host baseline: N = 1 only
         out = {
             "metric": "ray-samples/sec (render_core fwd+bwd)", "value": value, "unit": "ray-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
