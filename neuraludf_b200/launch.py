@@ -2,9 +2,9 @@
 
     python -m neuraludf_b200.launch /path/to/NeuralUDF/exp_runner_blending.py [runner args ...]
 
-`models.fields`, `models.embedder` and `models.udf_renderer_blending` are bound to the nudf mirrors before the runner
-is executed from the reference root; everything else the runner imports (`models.patch_projector`, `dataset`, `loss`,
-...) still resolves from the reference checkout (its `models/` directory is a namespace package).
+`models.fields`, `models.embedder`, `models.udf_renderer_blending` and `models.patch_projector` are bound to the nudf
+mirrors before the runner is executed from the reference root; everything else the runner imports (`dataset`, `loss`, ...)
+still resolves from the reference checkout (its `models/` directory is a namespace package).
 """
 import importlib
 import os
@@ -15,7 +15,7 @@ import types
 
 def install_shadow_modules(reference_root=None):
     """Registers the mirrors under the names the reference imports. Returns the `models` namespace module."""
-    from neuraludf_b200.models import embedder, fields, udf_renderer_blending
+    from neuraludf_b200.models import embedder, fields, patch_projector, udf_renderer_blending
     pkg = sys.modules.get("models")
     if pkg is None:
         pkg = types.ModuleType("models")
@@ -25,7 +25,8 @@ def install_shadow_modules(reference_root=None):
         p = os.path.join(reference_root, "models")
         if os.path.isdir(p) and p not in list(pkg.__path__):
             pkg.__path__ = list(pkg.__path__) + [p]
-    for name, mod in (("fields", fields), ("embedder", embedder), ("udf_renderer_blending", udf_renderer_blending)):
+    for name, mod in (("fields", fields), ("embedder", embedder), ("udf_renderer_blending", udf_renderer_blending),
+                      ("patch_projector", patch_projector)):
         sys.modules["models." + name] = mod
         setattr(pkg, name, mod)
     return pkg
