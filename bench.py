@@ -3,19 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1], "C2" in SURVEY.md 8(d)): 512 rays x 128 uniform samples per GPU, UDF 8x256 +
-ResidualRenderingNetwork 2x(4x128) (reference conf dims), synthetic seeded sphere scene, one step =
-render_core forward + backward of  L1 colour + 0.01 L1 base colour + 0.1 eikonal  (exp_runner_blending.py:330-371).
-For N > 1 (torchrun, one rank per GPU) rays are sharded (weak scaling: 512 rays per GPU) and the step ends with one
-NCCL all-reduce of the flat gradient bucket.
+Headline workload (BASELINE.json configs[1], "C2" in SURVEY.md 8(d)): 512 rays x 128 uniform samples per GPU, UDF 8x256 +
+ResidualRenderingNetwork 2x(4x128) (reference conf dims), synthetic seeded sphere scene.  One step = what one training
+iteration of the reference does on this path: render_core forward, backward of  L1 colour + 0.01 L1 base colour + 0.1 eikonal
+(exp_runner_blending.py:330-371), and the Adam update (exp_runner_blending.py:373-375) -- so the per-step weight-norm fold
+and tensor-engine weight-image build are INSIDE the timed region.  For N > 1 (torchrun, one rank per GPU) rays are sharded
+(weak scaling: 512 rays per GPU) and the gradients are all-reduced over NCCL before the update.
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks); `e2e` = the same
-step driven from pinned HOST buffers through the public module API with the H2D / D2H copies inside the timed region;
-`roofline` = the dominant kernel (the 256x256 dense layer) timed alone; `cpu_baseline` = the oracle port on host cores.
-`--impl reference` times the oracle port (the reference is pure Python/PyTorch and cannot travel to the GPU box) on
-the host cores; under torchrun only rank 0 works.
+Prints ONE JSON line (rank 0):
+  value      device-resident throughput (CUDA events on the launching stream, max over ranks);
+  e2e        the same step driven from pinned HOST buffers through the public module API, H2D / D2H inside the timed region;
+  families   per-kernel-family device time of the SAME step (cudaEvent pairs recorded by the library around each of its
+             launches, nudf_set_launch_timing), share of the step, algorithmic TFLOP/s, fraction of the measured bf16 peak;
+  roofline   the family with the largest share (i.e. picked from what the step actually launches);
+  cpu_baseline  the UNMODIFIED reference's render_core (staged copy oracle/_ref, see oracle/make_ref.py) on the host cores,
+             all 512 rays, thread count swept at the timed size; falls back to the pinned oracle port if no staged copy exists;
+  workloads  the other BASELINE.json configs (C1 forward, C3 blending step, C4 whole training step incl. strong-scaling size,
+             C5 256^3 grid sweep) so that the driver records them as well.
+`--impl reference` times the same CPU arm alone; under torchrun only rank 0 works.
 """
 import argparse
+import ctypes
 import datetime
 import json
 import os
@@ -33,6 +41,17 @@ N_RAYS, N_SAMPLES = 512, 128
 FLOP_FWD = 2274560           # per ray-sample, SURVEY 8(d): UDF value 1 049 088 + input-gradient sweep 918 016 + colour 307 456
 FLOP_FWD_BWD = 6823680       # forward + backward (data-grad + weight-grad of every contraction)
 
+# algorithmic MACs per sample point of the C2 step, by kernel family (layer dims of SURVEY App. B):
+#   F value chain = all 9 layers; R reverse sweep / T tangent chain = layers 0..7; B backward chain = layers 8..1;
+#   weight gradients = D^T Adot (layers 0..7) + Zbar^T A (layers 0..8); colour net: forward + data-grad + weight-grad
+_UDF_MAC = [256 * 39, 256 * 256, 256 * 256, 217 * 256, 256 * 256, 256 * 256, 256 * 256, 256 * 256, 257 * 256]
+_MAC_F = sum(_UDF_MAC)
+_MAC_R = sum(_UDF_MAC[:8])
+_MAC_B = sum(_UDF_MAC[1:])
+_MAC_COL = 153728
+FAMILY_MAC = {"udf_fwd_chain_fused": _MAC_F, "tc_layer_reverse_sweep": _MAC_R, "tc_layer_tangent": _MAC_R,
+              "tc_layer_backward": _MAC_B, "tc_weight_gradient": _MAC_R + _MAC_F + _MAC_COL}
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -44,21 +63,26 @@ def peaks():
 
 
 def ncu_traffic(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the dominant kernel from the committed
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of a kernel from the newest committed
     `ncu --set full` summary under profiles/ (None if not captured)."""
     import glob
     best = None
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_kernels.txt"))):
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    norm = lambda t: t.replace("nudf::", "").replace("tc::", "").replace(" ", "")
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_kernels.txt")) +
+                    glob.glob(os.path.join(ROOT, "profiles", "r*_kernels.txt"))):
         cur, rd, wr = None, None, None
         for line in open(f):
             if line.startswith("== "):
                 cur, rd, wr = line, None, None
-            elif cur and kernel_substr.replace("nudf::", "").replace("tc::", "") in cur.replace("nudf::", "").replace("tc::", ""):
+            elif cur and norm(kernel_substr) in norm(cur):
                 parts = line.split()
-                if parts and parts[0] == "dram__bytes_read.sum":
-                    rd = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e3 if parts[2].startswith("Kbyte") else 1e9 if parts[2].startswith("Gbyte") else 1)
-                if parts and parts[0] == "dram__bytes_write.sum":
-                    wr = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e3 if parts[2].startswith("Kbyte") else 1e9 if parts[2].startswith("Gbyte") else 1)
+                if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v = float(parts[1].replace(",", "")) * unit.get(parts[2], 1.0)
+                    if parts[0].endswith("read.sum"):
+                        rd = v
+                    else:
+                        wr = v
                 if rd is not None and wr is not None:
                     best = rd + wr
                     cur = None
@@ -73,13 +97,14 @@ def nerf_module(device):
     return nerf.to(device)
 
 
-def scene(device):
+def scene(device, small_udf=False):
     from neuraludf_b200 import synthetic as O
     from neuraludf_b200.models import fields as F
-    udf_c, col_c = O.udf_cfg(), O.color_cfg()
-    udf = F.UDFNetwork(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, bias=0.5, scale=1.0,
-                       geometric_init=True, weight_norm=True, udf_type="abs")
-    udf.load_state_dict(O.make_udf_params(udf_c, seed=0))
+    udf_c = O.udf_cfg(d_hidden=128, n_layers=4) if small_udf else O.udf_cfg()
+    col_c = O.color_cfg()
+    udf = F.UDFNetwork(d_in=3, d_out=257, d_hidden=udf_c["d_hidden"], n_layers=udf_c["n_layers"], skip_in=(4,), multires=6,
+                       bias=0.5, scale=1.0, geometric_init=True, weight_norm=True, udf_type="abs")
+    udf.load_state_dict(O.make_udf_params(udf_c, seed=3 if small_udf else 0))
     col = F.ResidualRenderingNetwork(d_feature=256, mode="no_normal", d_in=6, d_out=3, d_hidden=128, n_layers=4,
                                      weight_norm=True, multires_view=4, squeeze_out=True, blending_cand_views=10)
     col.load_state_dict(O.make_color_params(col_c, seed=1))
@@ -89,11 +114,21 @@ def scene(device):
     return [m.to(device) for m in (udf, col, var, beta)]
 
 
-def rays(seed, device=None):
+def make_optimizer(udf, others, fused=True):
+    """Adam with the reference's parameter groups and learning rates (exp_runner_blending.py:130-139, confs: 5e-4 / geo 1e-4)."""
+    groups = [{"params": [p for p in udf.parameters() if p.requires_grad], "lr": 1e-4},
+              {"params": [p for m in others for p in m.parameters() if p.requires_grad], "lr": 5e-4}]
+    try:
+        return torch.optim.Adam(groups, fused=fused)
+    except Exception:
+        return torch.optim.Adam(groups)
+
+
+def rays(seed, device=None, n_rays=N_RAYS, n_samples=N_SAMPLES):
     from neuraludf_b200 import synthetic as O
-    o, d, near, far = O.make_rays(N_RAYS, seed=seed)
-    z = near + (far - near) * torch.linspace(0.0, 1.0, N_SAMPLES)[None, :]
-    sd = float(((far - near) / N_SAMPLES).mean())
+    o, d, near, far = O.make_rays(n_rays, seed=seed)
+    z = near + (far - near) * torch.linspace(0.0, 1.0, n_samples)[None, :]
+    sd = float(((far - near) / n_samples).mean())
     if device is not None:
         o, d, z = o.to(device), d.to(device), z.to(device).contiguous()
     return o, d, z, sd
@@ -163,6 +198,47 @@ def loss_fn(ret, tgt):
             + 0.1 * ret["gradient_error"])
 
 
+def _timed(fn, steps, warmup):
+    """ms per call of fn(), CUDA events on the current stream, after `warmup` untimed calls."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def read_families(lib, n_steps, ms_step, P, pk):
+    """Per-family table from the library's event pairs (see the module docstring)."""
+    from neuraludf_b200 import _lib
+    nf = lib.nudf_launch_family_count()
+    ms = (ctypes.c_float * nf)()
+    cnt = (ctypes.c_int32 * nf)()
+    _lib.check(lib.nudf_read_launch_timing(ms, cnt), "nudf_read_launch_timing")
+    fam = {}
+    tot = 0.0
+    for i, name in enumerate(_lib.LAUNCH_FAMILIES[:nf]):
+        if cnt[i] == 0:
+            continue
+        us = ms[i] * 1e3 / n_steps
+        tot += us
+        row = {"launches_per_step": cnt[i] / n_steps, "us_per_step": us, "share": us / (ms_step * 1e3)}
+        if name in FAMILY_MAC:
+            fl = 2.0 * FAMILY_MAC[name] * P
+            row["algorithmic_tflops"] = fl / (us * 1e-6) / 1e12
+            row["frac_of_bf16_sustained"] = row["algorithmic_tflops"] / pk["bf16_sustained"]
+            row["us_per_launch"] = us / (cnt[i] / n_steps)
+        fam[name] = row
+    fam["torch_glue_and_idle"] = {"us_per_step": ms_step * 1e3 - tot, "share": 1.0 - tot / (ms_step * 1e3),
+                                  "note": "step time minus the library's kernels: torch element-wise / reduction / optimiser "
+                                          "kernels, launch gaps"}
+    return fam
+
+
 def run_ours(args):
     import torch.distributed as dist
     from neuraludf_b200 import _lib
@@ -178,26 +254,33 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
     udf, col, var, beta = scene(dev)
+    if args.workload in ("c3", "c4", "c5", "c1"):
+        fn = {"c3": run_c3, "c4": run_c4, "c5": run_c5, "c1": run_c1}[args.workload]
+        res = fn(args, dev, lib, rank, world)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return None
     params = [p for m in (udf, col, var, beta) for p in m.parameters() if p.requires_grad]
     ren = UDFRendererBlending(None, udf, var, col, beta, n_samples=N_SAMPLES, n_importance=0, n_outside=0,
                               up_sample_steps=1, perturb=0.0)
-    if args.workload == "c4":
-        return run_c4(args, dev, lib, udf, col, var, beta, rank, world)
-    if args.workload == "c3":
-        return run_c3(args, dev, lib, udf, col, var, beta, rank, world)
+    ren.want_diagnostics = False      # per-sample debug tensors are only consumed by validate() / visualize_one_ray()
     o, d, z, sd = rays(seed=rank, device=dev)
     tgt = torch.full((N_RAYS, 3), 0.4, device=dev)
     from neuraludf_b200.dp import GradBucket
-    bucket = GradBucket(params)
+    bucket = GradBucket(params, modules=(udf, col))      # backward kernels write dg / dv / db straight into the flat bucket
+    opt = make_optimizer(udf, (col, var, beta))
 
     def step(o_, d_, z_):
-        for p in params:
-            p.grad = None
+        opt.zero_grad(set_to_none=True)
         ret = ren.render_core(o_, d_, z_, sd, udf, var, col, beta_network=beta, cos_anneal_ratio=0.5)
         loss = loss_fn(ret, tgt)
         loss.backward()
         if world > 1:
-            bucket.allreduce_mean()                    # ONE NCCL all-reduce of the flat bucket (0.69 M floats) over NVLink
+            bucket.allreduce_mean()                    # NCCL all-reduce of the flat gradient bucket over NVLink
+        opt.step()                                     # Adam: parameters change => fold + weight images rebuilt next step
         return loss
 
     def barrier():
@@ -234,10 +317,21 @@ def run_ours(args):
             dist.destroy_process_group()
         return None
 
+    # ---- the same steps again with the library's per-family event pairs switched on ----
+    fam = None
+    if rank == 0:
+        n_fam_steps = min(args.steps, 10)
+        lib.nudf_set_launch_timing(1)
+        for _ in range(n_fam_steps):
+            step(o, d, z)
+        torch.cuda.synchronize()
+        fam = read_families(lib, n_fam_steps, ms / args.steps, N_RAYS * N_SAMPLES, peaks())
+        lib.nudf_set_launch_timing(0)
+    barrier()
+
     # ---- end-to-end: host (pinned) inputs, H2D + D2H inside the timed region, through the public module API ----
     ho, hd, hz, _ = rays(seed=rank)
     ho, hd, hz = ho.pin_memory(), hd.pin_memory(), hz.contiguous().pin_memory()
-    hres = torch.empty(N_RAYS, 3).pin_memory()
     for _ in range(2):
         l = step(ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True), hz.to(dev, non_blocking=True))
     barrier()
@@ -258,82 +352,70 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(times[0]), float(times[1])
 
+    # ---- the other BASELINE.json configs (short runs) ----
+    extra = {}
+    if not args.no_extra:
+        del ren, bucket, opt
+        torch.cuda.empty_cache()
+        sub = argparse.Namespace(steps=5, warmup=3)
+        for name, fn in (("c1", run_c1), ("c3", run_c3), ("c4", run_c4), ("c5", run_c5)):
+            try:
+                extra[name] = fn(sub, dev, lib, rank, world)
+            except Exception as e:                     # a secondary workload must never take the headline down with it
+                extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
+
     out = None
     if rank == 0:
         pk = peaks()
         samples = world * N_RAYS * N_SAMPLES * args.steps
         value = samples / (ms * 1e-3)
-        # ---- dominant kernels alone: one 256x256 dense layer (softplus epilogue) over the step's 65 536 points, on each
-        #      engine, and the matching weight-gradient contraction; L2 flushed between timed launches ----
-        import ctypes
-        P = N_RAYS * N_SAMPLES
-        X = torch.randn(P, 256, device=dev) * 0.1
-        W = torch.randn(256, 256, device=dev) * 0.06
-        b = torch.zeros(256, device=dev)
-        Y = torch.empty(P, 256, device=dev)
-        dW = torch.zeros(256, 256, device=dev)
-        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        imgs = {}
-        for npl in (2, 3):
-            im = torch.zeros(lib.nudf_tc_image_elems(256, 256, npl), dtype=torch.int16, device=dev)
-            lib.nudf_tc_prepare_weights(_lib.ptr(W), 256, 256, 256, 0, npl, _lib.ptr(im), st)
-            imgs[npl] = im
-        calls = {
-            "dense_fp32_ffma": lambda: lib.nudf_dense_forward(_lib.ptr(X), 256, _lib.ptr(W), 256, _lib.ptr(b), _lib.ptr(Y), 256, P, 256, 256, 2, st),
-            "dense_tcgen05_3xbf16": lambda: lib.nudf_dense_forward_tc(_lib.ptr(X), 256, _lib.ptr(imgs[2]), 2, _lib.ptr(b), _lib.ptr(Y), 256, P, 256, 256, 2, st),
-            "dense_tcgen05_6xbf16": lambda: lib.nudf_dense_forward_tc(_lib.ptr(X), 256, _lib.ptr(imgs[3]), 3, _lib.ptr(b), _lib.ptr(Y), 256, P, 256, 256, 2, st),
-            "wgrad_tcgen05_3xbf16": lambda: lib.nudf_wgrad(_lib.ptr(Y), 256, _lib.ptr(X), 256, 256, 256, P, _lib.ptr(dW), 256, 1, st),
-            "wgrad_fp32_ffma": lambda: lib.nudf_wgrad(_lib.ptr(Y), 256, _lib.ptr(X), 256, 256, 256, P, _lib.ptr(dW), 256, 0, st),
-        }
-        kflops = 2.0 * P * 256 * 256
-        ktimes = {}
-        for name, call in calls.items():
-            for _ in range(3):
-                call()
-            tk = 0.0
-            reps = 10
-            for _ in range(reps):
-                flush.zero_()                          # evict L2 between timed launches
-                a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); call(); bb.record()
-                torch.cuda.synchronize()
-                tk += a.elapsed_time(bb)
-            ktimes[name] = {"us": tk / reps * 1e3, "algorithmic_tflops": kflops / (tk / reps * 1e-3) / 1e12}
-        dom = "dense_tcgen05_3xbf16" if lib.nudf_get_engine() == 1 else "dense_fp32_ffma"
-        ach = ktimes[dom]["algorithmic_tflops"]
         engine = lib.nudf_get_engine()
-        cpu = cpu_baseline(steps=2, warmup=1, n_rays=256) if world == 1 else None      # host baseline: N = 1 only
+        step_tflops = value * FLOP_FWD_BWD / 1e12 / world
+        # roofline: the kernel family with the largest share of the step's device time
+        tens = {k: v for k, v in fam.items() if "algorithmic_tflops" in v}
+        dom = max(tens, key=lambda k: tens[k]["share"]) if tens else None
+        kernel_of = {"udf_fwd_chain_fused": "udf_chain_kernel", "tc_layer_reverse_sweep": "gemm_wr_kernel<nudf::EpiRev>",
+                     "tc_layer_tangent": "gemm_wr_kernel<nudf::EpiTan>", "tc_layer_backward": "gemm_wr_kernel<nudf::EpiBwd>",
+                     "tc_weight_gradient": "gemm_tn_kernel"}
+        roof = None
+        if dom is not None:
+            r = tens[dom]
+            roof = {"bound": "tensor", "kernel": "%s (%s): %.1f launches/step, %.1f us each" % (
+                        dom, kernel_of[dom], r["launches_per_step"], r["us_per_launch"]),
+                    "achieved": r["algorithmic_tflops"], "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": r["algorithmic_tflops"] / pk["bf16_sustained"], "share_of_step": r["share"],
+                    "traffic": ncu_traffic(kernel_of[dom]),
+                    "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/)",
+                    "peak_source": pk["source"] + ", bf16 sustained (kernel timed inside the step)",
+                    "how": "largest-share family of the timed step; duration = cudaEvent pairs recorded by the library on the "
+                           "launching stream around each launch of the family, in %d extra steps identical to the timed ones" % min(args.steps, 10),
+                    "note": "algorithmic FLOPs (2 x MACs of the family's contractions); the tensor engine executes 3x that "
+                            "(3-product bf16/fp16 split) or 5x (exact value chain)",
+                    "step_level": {"algorithmic_tflops": step_tflops, "frac_of_bf16_sustained": step_tflops / pk["bf16_sustained"]}}
+        cpu = cpu_baseline(steps=2, warmup=1) if world == 1 else None      # host baseline: N = 1 only
         out = {
             "metric": "ray-samples/sec (render_core fwd+bwd)", "value": value, "unit": "ray-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded geometric-init sphere scene, random-perturbed weights)",
             "config": {"workload": "C2: 512 rays x 128 uniform samples per GPU, UDF 8x256 + colour 2x(4x128), "
-                                   "render_core forward+backward", "rays_per_gpu": N_RAYS, "samples_per_ray": N_SAMPLES,
+                                   "render_core forward + backward + Adam update (fold / weight images rebuilt every step)",
+                       "rays_per_gpu": N_RAYS, "samples_per_ray": N_SAMPLES,
                        "parallelism": "dp%d (rays sharded, NCCL all-reduce of the flat gradient bucket)" % world,
-                       "l2": "per-step working set (~2.7 GB of saved activations) exceeds the 126 MB L2",
-                       "engine": ("tcgen05 3xBF16 on chains mask %d + fp32 FFMA elsewhere" % lib.nudf_get_tc_mask())
+                       "l2": "per-step working set (> 1 GB of saved activations) exceeds the 126 MB L2",
+                       "engine": ("tcgen05 (fused exact fp16-split value chain + 3xBF16 gradient chains), chain mask %d" % lib.nudf_get_tc_mask())
                        if engine == 1 else "fp32 FFMA",
                        "algorithmic_flop_per_sample": FLOP_FWD_BWD,
-                       "step_algorithmic_tflops": value * FLOP_FWD_BWD / 1e12 / world},
+                       "step_algorithmic_tflops": step_tflops},
             "clocks": clk,
             "e2e": {"value": world * N_RAYS * N_SAMPLES * args.steps / (ms_e2e * 1e-3), "unit": "ray-samples/s",
                     "h2d_bytes_per_step": int((ho.numel() + hd.numel() + hz.numel()) * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
-            "kernels": ktimes,
-            "roofline": {"bound": "tensor", "kernel": dom + ": dense 65536x256x256 + bias + softplus epilogue (UDF hidden layer)",
-                         "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
-                         "traffic": ncu_traffic("gemm_wr_kernel<nudf::EpiAct>" if dom.startswith("dense_tc") else "gemm_simt_kernel<1, 1, nudf::EpiAct>"),
-                         "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/)", "peak_source": pk["source"] + ", bf16 burst",
-                         "note": "algorithmic FLOPs (2MNK); the tensor engine executes 3x that (3xBF16 split)",
-                         # the same launch seen from the memory side: it reads A and writes Y once (fp32, 128 MiB); at the
-                         # measured peaks the tensor bound (3 x 8.6 GFLOP) and the HBM bound are both ~16-20 us
-                         "hbm_view": {"algorithmic_bytes": 2 * 65536 * 256 * 4,
-                                      "achieved_gbs": 2 * 65536 * 256 * 4 / (ktimes[dom]["us"] * 1e-6) / 1e9,
-                                      "peak_gbs": pk["hbm"],
-                                      "frac": 2 * 65536 * 256 * 4 / (ktimes[dom]["us"] * 1e-6) / 1e9 / pk["hbm"]}},
+            "families": fam,
+            "roofline": roof,
             "cpu_baseline": cpu,
+            "workloads": extra,
         }
     if world > 1:
         dist.barrier()
@@ -341,72 +423,101 @@ def run_ours(args):
     return out
 
 
-def run_c4(args, dev, lib, udf, col, var, beta, rank, world):
-    """Whole render() of the DTU conf (one rank's 512 rays): sampling + NeRF++ background + fine pass,
-    forward + backward.  Secondary number (not the BASELINE.json headline); printed as a reduced JSON line."""
+# ---------------------------------------------------------------------------------------------------------------
+# secondary workloads (the other BASELINE.json configs); each returns a small dict
+# ---------------------------------------------------------------------------------------------------------------
+def run_c1(args, dev, lib, rank, world):
+    """BASELINE configs[0]: 512 rays x 64 uniform samples, 4-layer / 128-wide UDF, render_core FORWARD."""
+    from neuraludf_b200.models.udf_renderer_blending import UDFRendererBlending
+    udf, col, var, beta = scene(dev, small_udf=True)
+    ren = UDFRendererBlending(None, udf, var, col, beta, n_samples=64, n_importance=0, n_outside=0, up_sample_steps=1,
+                              perturb=0.0)
+    ren.want_diagnostics = False
+    o, d, z, sd = rays(seed=rank, device=dev, n_samples=64)
+
+    def fwd():
+        with torch.no_grad():
+            return ren.render_core(o, d, z, sd, udf, var, col, beta_network=beta, cos_anneal_ratio=None)
+
+    ms = _timed(fwd, max(args.steps, 10), max(args.warmup, 3))
+    return {"workload": "c1: render_core forward, 512 rays x 64 samples, UDF 4x128", "ms_per_step": ms,
+            "ray_samples_per_s": world * N_RAYS * 64 / (ms * 1e-3), "n_gpus": world}
+
+
+def run_c4(args, dev, lib, rank, world):
+    """BASELINE configs[3]: whole training step of confs/udf_dtu_blending.conf -- render() (64 + 50 importance samples, 32
+    outside samples, perturb) forward + backward + gradient all-reduce + Adam.  Two sizes: 512 rays per GPU (weak) and
+    4096 rays in total sharded over the ranks (strong; the conf's batch on 8 GPUs)."""
     import torch.distributed as dist
     from neuraludf_b200 import synthetic as O
     from neuraludf_b200.dp import GradBucket
     from neuraludf_b200.models.udf_renderer_blending import UDFRendererBlending
+    udf, col, var, beta = scene(dev)
     nerf = nerf_module(dev)
     ren = UDFRendererBlending(nerf, udf, var, col, beta, n_samples=64, n_importance=50, n_outside=32, up_sample_steps=5,
                               perturb=1.0)
+    ren.want_diagnostics = False
     params = [p for m in (udf, col, var, beta, nerf) for p in m.parameters() if p.requires_grad]
-    bucket = GradBucket(params)
-    o, d, near, far = [t.to(dev) for t in O.make_rays(N_RAYS, seed=rank)]
-    tgt = torch.full((N_RAYS, 3), 0.4, device=dev)
+    bucket = GradBucket(params, modules=(udf, col, nerf))
+    opt = make_optimizer(udf, (col, var, beta, nerf))
+    res = {"workload": "c4: render() fwd+bwd + all-reduce + Adam, confs/udf_dtu_blending.conf shapes", "n_gpus": world}
+    for tag, n_rays in (("weak_512_per_gpu", N_RAYS), ("strong_4096_total", 4096 // world)):
+        o, d, near, far = [t.to(dev) for t in O.make_rays(n_rays, seed=rank)]
+        tgt = torch.full((n_rays, 3), 0.4, device=dev)
 
-    def step():
-        for p in params:
-            p.grad = None
-        ret = ren.render(o, d, near, far, cos_anneal_ratio=0.5, flip_saturation=0.1)
-        loss = loss_fn(ret, tgt)
-        loss.backward()
+        def step():
+            opt.zero_grad(set_to_none=True)
+            ret = ren.render(o, d, near, far, cos_anneal_ratio=0.5, flip_saturation=0.1)
+            loss = loss_fn(ret, tgt)
+            loss.backward()
+            if world > 1:
+                bucket.allreduce_mean()
+            opt.step()
+            return loss
+
+        l0 = None
+        for _ in range(max(args.warmup, 3)):
+            step()
         if world > 1:
-            bucket.allreduce_mean()
-        return loss
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    l0 = lib.nudf_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    if rank == 0:
-        print(json.dumps({"workload": "c4: render() fwd+bwd, confs/udf_dtu_blending.conf shapes, 512 rays per GPU",
-                          "ms_per_step": ms, "rays_per_s": world * N_RAYS / (ms * 1e-3),
-                          "fine_ray_samples_per_s": world * N_RAYS * 114 / (ms * 1e-3), "n_gpus": world,
-                          "gpu_launches_per_step": (lib.nudf_launch_count() - l0) / args.steps}), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return None
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = lib.nudf_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        res[tag] = {"rays_per_gpu": n_rays, "ms_per_step": ms, "rays_per_s": world * n_rays / (ms * 1e-3),
+                    "fine_ray_samples_per_s": world * n_rays * 114 / (ms * 1e-3),
+                    "gpu_launches_per_step": (lib.nudf_launch_count() - l0) / args.steps}
+    return res
 
 
-def run_c3(args, dev, lib, udf, col, var, beta, rank, world):
-    """Whole render() of the fine-tuning stage on open-surface shapes: 1024 rays x (64 + 64 importance)
-    samples, no outside samples, pixel + patch blending on (8 source views of 1024 x 1024, 7 x 7 patches), forward +
-    backward.  Secondary number; printed as a reduced JSON line."""
+def run_c3(args, dev, lib, rank, world):
+    """BASELINE configs[2]: whole render() of the fine-tuning stage on open-surface shapes: 1024 rays x (64 + 64 importance)
+    samples, no outside samples, pixel + patch blending on (8 source views of 1024 x 1024, 7 x 7 patches), fwd + bwd + Adam."""
     import torch.distributed as dist
     from neuraludf_b200 import synthetic as O
     from neuraludf_b200.dp import GradBucket
     from neuraludf_b200.models.udf_renderer_blending import UDFRendererBlending
+    udf, col, var, beta = scene(dev)
     n_rays = 1024
     ren = UDFRendererBlending(None, udf, var, col, beta, n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4,
                               perturb=1.0, upsampling_type="classical", h_patch_size=3, use_norm_grad_for_cosine=True)
+    ren.want_diagnostics = False
     params = [p for m in (udf, col, var, beta) for p in m.parameters() if p.requires_grad]
-    bucket = GradBucket(params)
+    bucket = GradBucket(params, modules=(udf, col))
+    opt = make_optimizer(udf, (col, var, beta))
     v = {k: t.to(dev) for k, t in O.make_blend_views(n_rays, n_views=8, height=1024, width=1024, seed=rank).items()}
     tgt = torch.full((n_rays, 3), 0.4, device=dev)
 
     def step():
-        for p in params:
-            p.grad = None
+        opt.zero_grad(set_to_none=True)
         ret = ren.render(v["rays_o"], v["rays_d"], v["near"], v["far"], cos_anneal_ratio=1.0, flip_saturation=0.0,
                          color_maps=v["color_maps"], w2cs=v["w2cs"], intrinsics=v["intrinsics"], query_c2w=v["query_c2w"],
                          rays_uv=v["rays_uv"])
@@ -416,34 +527,131 @@ def run_c3(args, dev, lib, udf, col, var, beta, rank, world):
         loss.backward()
         if world > 1:
             bucket.allreduce_mean()
+        opt.step()
         return loss
 
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     l0 = lib.nudf_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    if rank == 0:
-        print(json.dumps({"workload": "c3: render() fwd+bwd with pixel + patch blending, 1024 rays x (64+64) samples, "
-                                      "8 views 1024x1024, 49-pixel patches", "ms_per_step": ms,
-                          "rays_per_s": world * n_rays / (ms * 1e-3),
-                          "fine_ray_samples_per_s": world * n_rays * 128 / (ms * 1e-3), "n_gpus": world,
-                          "gpu_launches_per_step": (lib.nudf_launch_count() - l0) / args.steps}), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return None
+    ms = _timed(step, args.steps, 0)
+    return {"workload": "c3: render() fwd+bwd + Adam with pixel + patch blending, 1024 rays x (64+64) samples, 8 views 1024x1024, "
+                        "49-pixel patches", "ms_per_step": ms, "rays_per_s": world * n_rays / (ms * 1e-3),
+            "fine_ray_samples_per_s": world * n_rays * 128 / (ms * 1e-3), "n_gpus": world,
+            "gpu_launches_per_step": (lib.nudf_launch_count() - l0) / max(args.steps, 1)}
 
 
-def cpu_baseline(steps, warmup, n_rays):
-    """The oracle port (pinned restatement of the reference's PyTorch code) on the host cores: a bounded sample of the
-    same workload (n_rays of the 512 rays x 128 samples, forward + backward)."""
+def run_c5(args, dev, lib, rank, world):
+    """BASELINE configs[4]: 256^3 lattice on [-1,1]^3 -- UDF value at every point, then the normalised gradient where
+    udf < 2 voxels (the reference's get_udf_normals_grid_slow, extract_mesh.py:18-105) and, as an upper bound, at every
+    point.  With N ranks the lattice is slab-partitioned along x (replicas only, no exchange)."""
+    import torch.distributed as dist
+    udf, _, _, _ = scene(dev)
+    R = 256
+    lo, hi = rank * R // world, (rank + 1) * R // world
+    ax = torch.linspace(-1.0, 1.0, R, device=dev)
+    voxel = 2.0 / (R - 1)
+    chunk = 1 << 21
+
+    def slab_points():
+        for i0 in range(lo, hi, 8):
+            i1 = min(i0 + 8, hi)
+            yield torch.cartesian_prod(ax[i0:i1], ax, ax)
+
+    def sweep_values():
+        out = []
+        for pts in slab_points():
+            for c in range(0, pts.shape[0], chunk):
+                out.append(udf.udf_values(pts[c:c + chunk]))
+        return torch.cat(out)
+
+    def sweep_grads(mask=None):
+        n = 0
+        off = 0
+        for pts in slab_points():
+            if mask is not None:
+                pts = pts[mask[off:off + pts.shape[0]]]
+            off += (8 * R * R)
+            for c in range(0, pts.shape[0], chunk):
+                with torch.no_grad():
+                    g = udf.gradient(pts[c:c + chunk]).squeeze(1)
+                    g = g / (g.norm(dim=-1, keepdim=True) + 1e-12)
+                n += g.shape[0]
+        return n
+
+    def timed(fn):
+        fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), r
+
+    t_val, u = timed(sweep_values)
+    near = u < 2 * voxel
+    t_gn, n_near = timed(lambda: sweep_grads(near))
+    t_ga, n_all = timed(lambda: sweep_grads(None))
+    pk = peaks()
+    n_pts = R ** 3
+    return {"workload": "c5: 256^3 grid query (value everywhere; normalised gradient near the surface / everywhere)",
+            "n_gpus": world, "value_sweep_s": t_val, "value_Mpts_per_s": n_pts / t_val / 1e6,
+            "value_algorithmic_tflops": n_pts * 918016 / t_val / 1e12,
+            "value_hbm_gbs": n_pts * 16 / t_val / 1e9, "value_hbm_frac": n_pts * 16 / t_val / 1e9 / pk["hbm"],
+            "near_surface_points_this_rank": int(n_near), "near_surface_gradient_sweep_s": t_gn,
+            "all_points_gradient_sweep_s": t_ga, "all_points_value_and_gradient_Mpts_per_s": n_pts / t_ga / 1e6,
+            "note": "compute-bound by construction (0.9-1.8 MFLOP per point vs 16 B of HBM traffic per point): the HBM "
+                    "fraction is small and is not the bound (SURVEY 8(d))"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation of the path on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def _reference_step_fn(n_rays):
+    """one training step of the UNMODIFIED reference (staged copy, oracle/_ref) on the CPU, or None if it is not staged"""
+    from oracle import refshim
+    if not refshim.available():
+        return None
+    from neuraludf_b200 import synthetic as S
+    F, R = refshim.load()
+    torch.set_default_dtype(torch.float32)
+    udf_c, col_c = S.udf_cfg(), S.color_cfg()
+    udf = F.UDFNetwork(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=(4,), multires=6, scale=1.0, bias=0.5,
+                       geometric_init=False, weight_norm=True, udf_type="abs")
+    udf.load_state_dict(S.make_udf_params(udf_c, seed=0))
+    col = F.ResidualRenderingNetwork(d_feature=256, mode="no_normal", d_in=6, d_out=3, d_hidden=128, n_layers=4,
+                                     weight_norm=True, multires_view=4, squeeze_out=True, blending_cand_views=10)
+    col.load_state_dict(S.make_color_params(col_c, seed=1))
+    var = F.SingleVarianceNetwork(init_val=0.6)
+    beta = F.BetaNetwork(init_var_beta=0.5, init_var_gamma=0.3, init_var_zeta=0.3, beta_min=5e-5, requires_grad_beta=True,
+                         requires_grad_gamma=False, requires_grad_zeta=False)
+    ren = R.UDFRendererBlending(None, udf, var, col, beta, n_samples=N_SAMPLES, n_importance=0, n_outside=0,
+                                up_sample_steps=1, perturb=0.0)
+    opt = make_optimizer(udf, (col, var, beta), fused=False)
+    o, d, z, sd = rays(seed=0)
+    o, d, z = o[:n_rays], d[:n_rays], z[:n_rays]
+    tgt = torch.full((n_rays, 3), 0.4)
+
+    def one():
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        ret = ren.render_core(o, d, z, sd, udf, var, col, beta_network=beta, cos_anneal_ratio=0.5)
+        loss_fn(ret, tgt).backward()
+        opt.step()
+        return time.perf_counter() - t0
+    return one
+
+
+def _ref_origin():
+    from oracle import refshim
+    return "staged byte-for-byte copy oracle/_ref" if refshim.is_staged_copy() else "checkout " + refshim.REFERENCE_ROOT
+
+
+def _port_step_fn(n_rays):
     from oracle import oracle_torch as O
     udf_c, col_c = O.udf_cfg(), O.color_cfg()
     up = {k: v.clone().requires_grad_(True) for k, v in O.make_udf_params(udf_c, seed=0).items()}
@@ -452,34 +660,48 @@ def cpu_baseline(steps, warmup, n_rays):
     o, d, z, sd = rays(seed=0)
     o, d, z = o[:n_rays], d[:n_rays], z[:n_rays]
     tgt = torch.full((n_rays, 3), 0.4)
+    leaves = list(up.values()) + list(cp.values()) + [sc["variance"], sc["beta"]]
+    opt = torch.optim.Adam(leaves, lr=1e-4)
 
-    def one(nr):
+    def one():
         t0 = time.perf_counter()
-        ret = O.render_core(up, udf_c, cp, col_c, sc, o[:nr], d[:nr], z[:nr], sd, cos_anneal_ratio=0.5)
-        loss = loss_fn(ret, tgt[:nr])
-        torch.autograd.grad(loss, list(up.values()) + list(cp.values()) + [sc["variance"], sc["beta"]])
+        opt.zero_grad()
+        ret = O.render_core(up, udf_c, cp, col_c, sc, o, d, z, sd, cos_anneal_ratio=0.5)
+        loss_fn(ret, tgt).backward()
+        opt.step()
         return time.perf_counter() - t0
+    return one
 
-    # give the CPU path its best thread count (oversubscribing a 128-thread host makes torch 10x slower)
+
+def cpu_baseline(steps, warmup, n_rays=N_RAYS):
+    """The reference's render_core training step on the host cores, on the SAME configuration as the CUDA arm (all 512 rays x
+    128 samples, forward + backward + Adam).  The thread count is swept at the timed size."""
+    one = _reference_step_fn(n_rays)
+    kind = "reference"
+    if one is None:
+        one, kind = _port_step_fn(n_rays), "port"
     ncpu = os.cpu_count() or 1
-    cands = sorted(set(c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu))
-    best, best_t = cands[0], float("inf")
+    cands = sorted(set(c for c in (8, 16, 32, 64, ncpu) if c <= ncpu)) or [ncpu]
+    sweep = {}
+    one()                                               # first call pays allocator / thread-pool start-up
     for c in cands:
         torch.set_num_threads(c)
-        one(16)
-        t = one(16)
-        if t < best_t:
-            best, best_t = c, t
+        sweep[c] = one()
+    best = min(sweep, key=sweep.get)
     torch.set_num_threads(best)
     ts = []
     for i in range(warmup + steps):
-        dt = one(n_rays)
+        dt = one()
         if i >= warmup:
             ts.append(dt)
     per = sum(ts) / len(ts)
-    return {"value": n_rays * N_SAMPLES / per, "unit": "ray-samples/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": "%d of 512 rays x 128 samples, render_core fwd+bwd, %d timed steps after %d warm-up; "
-                                      "thread count chosen as the fastest of %s on this host" % (n_rays, steps, warmup, cands),
+    what = ("the unmodified reference (xxlong0/NeuralUDF models/udf_renderer_blending.py render_core, %s)" % _ref_origin()
+            if kind == "reference" else "the pinned oracle port of the reference's render_core (no staged reference copy found)")
+    return {"value": n_rays * N_SAMPLES / per, "unit": "ray-samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "host_cpus": ncpu,
+            "sample": "%s: all %d rays x %d samples, forward + backward + Adam, %d timed steps after %d warm-up; thread count = "
+                      "fastest of a sweep at this size %s" % (what, n_rays, N_SAMPLES, steps, warmup,
+                                                             {k: round(v, 3) for k, v in sweep.items()}),
             "s_per_step": per}
 
 
@@ -487,16 +709,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    n_rays = 256          # the same bounded sample as the cpu_baseline leg of the CUDA arm
-    cpu = cpu_baseline(steps=args.steps, warmup=max(1, min(args.warmup, 2)), n_rays=n_rays)
+    steps = max(1, min(args.steps, 8))                  # bounded: ~1 s per step on the host
+    cpu = cpu_baseline(steps=steps, warmup=max(1, min(args.warmup, 2)))
     return {"impl": "reference", "metric": "ray-samples/sec (render_core fwd+bwd)", "value": cpu["value"],
-            "unit": "ray-samples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "unit": "ray-samples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps,
             "warmup": args.warmup, "ms_per_step": cpu["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (same seeded scene as the CUDA arm)",
-            "config": {"workload": "C2 sample: %d of 512 rays x 128 uniform samples, UDF 8x256 + colour 2x(4x128), "
-                                   "render_core forward+backward on the host CPU (oracle port of the reference's "
-                                   "PyTorch code; the reference itself is not installable: no setup.py, imports absent "
-                                   "modules)" % n_rays},
+            "config": {"workload": "C2: 512 rays x 128 uniform samples, UDF 8x256 + colour 2x(4x128), render_core forward + "
+                                   "backward + Adam update on the host CPU (%s)" % cpu["kind"],
+                       "rays_per_gpu": N_RAYS, "samples_per_ray": N_SAMPLES, "requested_steps": args.steps},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
@@ -507,12 +728,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
-                    help="c2 (default, the BASELINE.json headline): render_core fwd+bwd on 512x128 uniform samples; "
-                         "c4: whole render() of confs/udf_dtu_blending.conf (64+50 samples, 32 outside, perturb) fwd+bwd; "
-                         "c3: whole render() with pixel + patch blending on, 1024 rays x (64+64) samples, 8 views")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="c2 (default, the BASELINE.json headline; also runs short versions of the others and reports them "
+                         "under `workloads`); c1 / c3 / c4 / c5: that workload alone, reduced JSON line")
     ap.add_argument("--quick", action="store_true", help="main timed loop only (for profiler runs): no e2e leg, no "
-                    "single-kernel probes, no CPU baseline; prints a reduced JSON line")
+                    "family table, no CPU baseline, no secondary workloads; prints a reduced JSON line")
+    ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:

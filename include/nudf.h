@@ -20,7 +20,11 @@ extern "C" {
 #endif
 
 #define NUDF_MAX_LAYERS 16
-#define NUDF_ABI_VERSION 1
+#define NUDF_ABI_VERSION 2
+/* bits of the device-side status word (nudf_render_out.status, `status` of the sampling entry points): set by the kernels,
+ * never cleared by the library; the caller reads it at a host synchronisation point of its choice */
+#define NUDF_STATUS_NONFINITE_SAMPLES 1   /* sample_pdf / up_sample produced a non-finite sample position (:97-101, 265-269) */
+#define NUDF_STATUS_NONFINITE_RENDER 2    /* compositing produced a non-finite per-ray result (:543-544) */
 
 int nudf_abi_version(void);
 const char* nudf_last_error(void);
@@ -34,6 +38,7 @@ int nudf_get_engine(void);
  * 8 backward, 16 weight gradients, 32 colour-network backward, 64 NeRF++ backward, 128 colour / NeRF++ forward. */
 int nudf_set_tc_mask(int mask);
 int nudf_get_tc_mask(void);
+int nudf_default_tc_mask(void);   /* the mask the library ships (what bench.py times and the parity suite pins) */
 /* Plane-fed reverse-sweep / tangent chains (engine 1 only): intermediate tensors of those chains are kept as split-bf16
  * plane tensors (see nudf_pack_planes) and fetched with cp.async.bulk.  Default 0 (env NUDF_PLANES).  Like the engine
  * and the mask it must not change between a forward call and its backward (the ctx layout depends on it). */
@@ -70,6 +75,14 @@ int nudf_wgrad_planes(const uint16_t* dZ_planes, const uint16_t* X_planes, int32
 int nudf_tc_read_trace(long long* host_buf);
 /* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 int64_t nudf_launch_count(void);
+/* Per-kernel-family device times for the benchmark's roofline table: while enabled, the library brackets its launches with
+ * cudaEvent pairs on the launching stream.  nudf_read_launch_timing synchronises, writes the summed milliseconds and the
+ * launch counts per family (host arrays of nudf_launch_family_count() entries; order: fused UDF value chain, tcgen05
+ * reverse-sweep / tangent / backward / other layers, tcgen05 weight gradients, fp32 FFMA GEMMs, ray kernels, element-wise)
+ * and clears the record. */
+int nudf_launch_family_count(void);
+int nudf_set_launch_timing(int on);
+int nudf_read_launch_timing(float* ms_per_family, int32_t* launches_per_family);
 /* One fused dense layer Y[M,N] = act(X[M,K] W[N,K]^T + bias), act: 0 none, 1 relu, 2 softplus(beta=100), 3 sigmoid.
  * The building block of every network below (an nn.Linear + activation of the reference, e.g. fields.py:205-208). */
 int nudf_dense_forward(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* Y, int64_t ldy,
@@ -211,6 +224,8 @@ typedef struct nudf_render_out {
   float* gradient_mag; float* true_cos; float* vis_prob; float* alpha; float* alpha_plus; float* alpha_minus;
   float* alpha_occ; float* raw_occ; float* inside_sphere;        /* [N,S] each */
   float* gradients_flip;                                         /* [N,S,3] */
+  int32_t* status;  /* DEVICE int or NULL: NUDF_STATUS_NONFINITE_RENDER is OR-ed in when a ray's colour / depth / weight sum /
+                     * regulariser sums are not finite (the reference traps this with pdb, :543-544) */
 } nudf_render_out;
 
 /* alpha compositing with the visibility-weighted UDF density (:364-553 minus the networks).
@@ -249,13 +264,13 @@ int nudf_render_composite_backward(const nudf_render_cfg* cfg, const float* head
  * mode 0 = up_sample_unbias (:197-272), 1 = up_sample_no_occ_aware (:834-866).  Scans are accumulated in fp64 and
  * rounded to fp32 per element, like torch's CPU cumsum/cumprod, so that indices are reproducible.
  * u_lin: DEVICE float[m] = torch.linspace(0.5/m, 1-0.5/m, m) (:76), supplied by the caller so that its rounding is
- * exactly torch's. */
+ * exactly torch's.  status: DEVICE int or NULL, see NUDF_STATUS_NONFINITE_SAMPLES. */
 int nudf_up_sample(int32_t mode, const float* rays_o, const float* rays_d, const float* z, const float* udf,
                    int32_t n_rays, int32_t n, int32_t m, float sample_dist, float inv_s, float beta, float gamma,
-                   const float* u_lin, float* new_z, int64_t* inds, void* stream);
+                   const float* u_lin, float* new_z, int64_t* inds, int32_t* status, void* stream);
 /* sample_pdf(det=True) alone (:66-104): bins [N,n], weights [N,n-1] -> samples [N,m], inds [N,m] */
 int nudf_sample_pdf(const float* bins, const float* weights, int32_t n_rays, int32_t n, int32_t m, const float* u_lin,
-                    float* samples, int64_t* inds, void* stream);
+                    float* samples, int64_t* inds, int32_t* status, void* stream);
 /* cat_z_vals merge (:274-290): z_out[N,n+m] sorted union, udf_out gathered likewise (udf/new_udf/udf_out may be
  * NULL for the `last` round).  new_pts[N*m,3] <- o + d*new_z (points to evaluate before the merge), optional. */
 int nudf_merge_z(const float* z, const float* new_z, const float* udf, const float* new_udf, int32_t n_rays, int32_t n,

@@ -48,7 +48,8 @@ class RenderCfg(ctypes.Structure):
 
 RENDER_OUT_FIELDS = ["color_base", "color", "depth", "normals", "weights", "weight_sum", "weight_sum_fg_bg",
                      "ray_sums", "gradient_mag", "true_cos", "vis_prob", "alpha", "alpha_plus", "alpha_minus",
-                     "alpha_occ", "raw_occ", "inside_sphere", "gradients_flip"]
+                     "alpha_occ", "raw_occ", "inside_sphere", "gradients_flip", "status"]
+STATUS_NONFINITE_SAMPLES, STATUS_NONFINITE_RENDER = 1, 2
 
 
 class RenderOut(ctypes.Structure):
@@ -64,6 +65,9 @@ class RenderBar(ctypes.Structure):
                                         "ray_sums")]
 
 
+LAUNCH_FAMILIES = ["udf_fwd_chain_fused", "tc_layer_reverse_sweep", "tc_layer_tangent", "tc_layer_backward", "tc_layer_other",
+                   "tc_weight_gradient", "ffma_gemm", "ray_kernels", "elementwise"]
+
 _lib = None
 
 _SIGNATURES = {
@@ -72,9 +76,13 @@ _SIGNATURES = {
     "nudf_set_engine": (ctypes.c_int, [ctypes.c_int]),
     "nudf_get_engine": (ctypes.c_int, []),
     "nudf_launch_count": (ctypes.c_int64, []),
+    "nudf_launch_family_count": (ctypes.c_int, []),
+    "nudf_set_launch_timing": (ctypes.c_int, [ctypes.c_int]),
+    "nudf_read_launch_timing": (ctypes.c_int, [c_void_p, c_void_p]),
     "nudf_tc_read_trace": (ctypes.c_int, [c_void_p]),
     "nudf_set_tc_mask": (ctypes.c_int, [ctypes.c_int]),
     "nudf_get_tc_mask": (ctypes.c_int, []),
+    "nudf_default_tc_mask": (ctypes.c_int, []),
     "nudf_tc_image_elems": (ctypes.c_int64, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "nudf_tc_prepare_weights": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                ctypes.c_int32, c_void_p, c_void_p]),
@@ -131,9 +139,9 @@ _SIGNATURES = {
     "nudf_render_composite_backward": (ctypes.c_int, [c_void_p] * 2 + [c_void_p] * 5 + [ctypes.c_int64] + [c_void_p] * 14),
     "nudf_up_sample": (ctypes.c_int, [ctypes.c_int32, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int32,
                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                      ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nudf_sample_pdf": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_void_p,
-                                       c_void_p, c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "nudf_merge_z": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32,
                                     ctypes.c_int32, c_void_p, c_void_p, c_void_p]),
     "nudf_points_on_rays": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32, c_void_p,
@@ -160,7 +168,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.nudf_abi_version() != 1:
+        if L.nudf_abi_version() != 2:
             raise RuntimeError("libnudf.so ABI version mismatch")
         _lib = L
     return _lib

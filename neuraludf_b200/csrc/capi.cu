@@ -13,6 +13,27 @@ static int g_engine = -1;
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
+// ---- per-family launch timing (bench.py) ----
+static bool g_timing = false;
+static const int kMaxTimed = 8192;
+static cudaEvent_t g_ev[kMaxTimed][2];
+static int g_ev_family[kMaxTimed];
+static int g_ev_created = 0, g_ev_used = 0;
+bool launch_timing_on() { return g_timing; }
+int launch_timer_begin(int family, cudaStream_t st) {
+  if (g_ev_used >= kMaxTimed) return -1;
+  const int slot = g_ev_used;
+  if (slot >= g_ev_created) {
+    if (cudaEventCreate(&g_ev[slot][0]) != cudaSuccess || cudaEventCreate(&g_ev[slot][1]) != cudaSuccess) return -1;
+    g_ev_created = slot + 1;
+  }
+  g_ev_family[slot] = family;
+  if (cudaEventRecord(g_ev[slot][0], st) != cudaSuccess) return -1;
+  g_ev_used = slot + 1;
+  return slot;
+}
+void launch_timer_end(int slot, cudaStream_t st) { cudaEventRecord(g_ev[slot][1], st); }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -24,10 +45,11 @@ void set_error(const char* fmt, ...) {
 // 16 weight gradients, 32 colour-net backward, 64 NeRF++ backward, 128 colour / NeRF++ forward).  Default (126): everything
 // except the forward value chains (gemm_engine.cuh explains why).
 static int g_tc_mask = -1;
+static const int kDefaultTcMask = 2 | 4 | 8 | 16 | 32 | 64;
 int tc_mask() {
   if (g_tc_mask < 0) {
     const char* e = getenv("NUDF_TC_MASK");
-    g_tc_mask = e ? atoi(e) : (2 | 4 | 8 | 16 | 32 | 64);
+    g_tc_mask = e ? atoi(e) : kDefaultTcMask;
   }
   return g_tc_mask;
 }
@@ -75,8 +97,28 @@ int nudf_set_engine(int engine) {
 int nudf_get_engine(void) { return nudf::get_engine(); }
 int nudf_set_tc_mask(int mask) { nudf::g_tc_mask = mask & 255; return 0; }
 int nudf_get_tc_mask(void) { return nudf::tc_mask(); }
+int nudf_default_tc_mask(void) { return nudf::kDefaultTcMask; }
 int nudf_set_chain_planes(int on) { nudf::g_chain_planes = on ? 1 : 0; return 0; }
 int nudf_get_chain_planes(void) { return nudf::chain_planes_flag(); }
 int64_t nudf_launch_count(void) { return (int64_t)__atomic_load_n(&nudf::g_launches, __ATOMIC_RELAXED); }
+
+int nudf_launch_family_count(void) { return nudf::FAM_COUNT; }
+int nudf_set_launch_timing(int on) {
+  nudf::g_timing = on != 0;
+  nudf::g_ev_used = 0;
+  return 0;
+}
+int nudf_read_launch_timing(float* ms_per_family, int32_t* launches_per_family) {
+  for (int f = 0; f < nudf::FAM_COUNT; ++f) { ms_per_family[f] = 0.f; launches_per_family[f] = 0; }
+  for (int i = 0; i < nudf::g_ev_used; ++i) {
+    if (cudaEventSynchronize(nudf::g_ev[i][1]) != cudaSuccess) { nudf::set_error("nudf_read_launch_timing: event sync failed"); return -2; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, nudf::g_ev[i][0], nudf::g_ev[i][1]) != cudaSuccess) { nudf::set_error("nudf_read_launch_timing: elapsed failed"); return -2; }
+    ms_per_family[nudf::g_ev_family[i]] += ms;
+    launches_per_family[nudf::g_ev_family[i]] += 1;
+  }
+  nudf::g_ev_used = 0;
+  return 0;
+}
 
 }  // extern "C"

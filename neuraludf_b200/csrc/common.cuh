@@ -53,6 +53,30 @@ namespace nudf {
 void set_error(const char* fmt, ...);
 void count_launch();
 
+// Per-kernel-family device timing for bench.py (nudf_set_launch_timing): while enabled, every launch wrapped in a
+// LaunchTimer is bracketed by a cudaEvent pair recorded on the launching stream; nudf_read_launch_timing() synchronises
+// and sums the pairs per family.  Off by default (zero overhead besides one branch).
+enum LaunchFamily {
+  FAM_UDF_FWD_CHAIN = 0,   // fused UDF value chain (udf_chain.cuh)
+  FAM_TC_REV = 1,          // one layer of the reverse sweep (grad_x udf) on tcgen05
+  FAM_TC_TAN = 2,          // one layer of the tangent chain
+  FAM_TC_BWD = 3,          // one layer of the backward chain
+  FAM_TC_OTHER = 4,        // other tcgen05 layer GEMMs (colour / NeRF++ backward, plain forward layers)
+  FAM_TC_WGRAD = 5,        // weight-gradient contractions on tcgen05
+  FAM_FFMA = 6,            // exact-fp32 FFMA GEMMs
+  FAM_RAY = 7,             // ray kernels: compositing forward / backward, sampling, blending
+  FAM_ELEMENTWISE = 8,     // element-wise kernels of the library (PE, fold / unfold, seeds, column sums)
+  FAM_COUNT = 9
+};
+bool launch_timing_on();
+int launch_timer_begin(int family, cudaStream_t st);
+void launch_timer_end(int slot, cudaStream_t st);
+struct LaunchTimer {
+  int slot; cudaStream_t st;
+  LaunchTimer(int family, cudaStream_t s) : slot(-1), st(s) { if (launch_timing_on()) slot = launch_timer_begin(family, s); }
+  ~LaunchTimer() { if (slot >= 0) launch_timer_end(slot, st); }
+};
+
 #define NUDF_CUDA_OK(expr)                                                              \
   do {                                                                                  \
     cudaError_t _e = (expr);                                                            \

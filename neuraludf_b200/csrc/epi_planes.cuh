@@ -63,4 +63,7 @@ struct EpiTanP {
   NUDF_EPI_CALL
 };
 
+template <> struct epi_family<EpiRevP> { static constexpr int value = FAM_TC_REV; };
+template <> struct epi_family<EpiTanP> { static constexpr int value = FAM_TC_TAN; };
+
 }  // namespace nudf

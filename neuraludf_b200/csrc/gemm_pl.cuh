@@ -339,6 +339,7 @@ static inline int gemm_wrp(const Planes& A, int64_t M, int N, int K, const uint1
   dim3 grid((unsigned)gx, (unsigned)nh);
   static int flip = 0;
   flip ^= 1;
+  LaunchTimer lt_(epi_family<Epi>::value, st);
   gemm_wrp_kernel<Epi><<<grid, PW_THREADS, smem, st>>>(A, M, N, K, img, epi, flip, tc_debug());
   NUDF_LAUNCH_OK();
   return 0;
@@ -376,6 +377,7 @@ static inline int gemm_tn_pl(const Planes& X, int M, const Planes& Y, int N, int
     attr_set = true;
   }
   dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 256), (unsigned)splits);
+  LaunchTimer lt_(FAM_TC_WGRAD, st);
   gemm_tn_pl_kernel<Epi><<<grid, TP_THREADS, smem, st>>>(X, M, Y, N, P, bps, epi, tc_debug());
   NUDF_LAUNCH_OK();
   return 0;

@@ -392,10 +392,19 @@ struct EpiReluBwd {
   NUDF_EPI_CALL
 };
 
+// launch family of a tensor-engine layer GEMM, by its epilogue (bench.py's per-family timing table)
+template <class Epi> struct epi_family { static constexpr int value = FAM_TC_OTHER; };
+template <> struct epi_family<EpiRev> { static constexpr int value = FAM_TC_REV; };
+template <> struct epi_family<EpiRevFinal> { static constexpr int value = FAM_TC_REV; };
+template <> struct epi_family<EpiTan> { static constexpr int value = FAM_TC_TAN; };
+template <> struct epi_family<EpiBwd> { static constexpr int value = FAM_TC_BWD; };
+template <> struct epi_family<EpiBwdR1> { static constexpr int value = FAM_TC_BWD; };
+
 template <bool A_KC, bool B_KC, class Epi>
 static inline int gemm_simt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int64_t K,
                             const Epi& epi, cudaStream_t st, int split_k = 1) {
   if (M <= 0 || N <= 0) return 0;
+  LaunchTimer lt_(FAM_FFMA, st);
   int64_t k_chunk = K;
   if (split_k > 1) {
     k_chunk = round_up(cdiv(K, split_k), GS_BK);

@@ -953,6 +953,7 @@ static inline int gemm_wp(const float* A, int64_t lda, int64_t M, int N, int K, 
   // the 126 MB L2 when the next kernel starts with them
   static int flip = 0;
   flip ^= 1;
+  LaunchTimer lt_(epi_family<Epi>::value, st);
   gemm_wp_kernel<Epi><<<grid, PTHREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip, tc_debug());
   NUDF_LAUNCH_OK();
   return 0;
@@ -976,6 +977,7 @@ static inline int gemm_wr(const float* A, int64_t lda, int64_t M, int N, int K, 
   dim3 grid((unsigned)gx, (unsigned)nh);
   static int flip = 0;
   flip ^= 1;
+  LaunchTimer lt_(epi_family<Epi>::value, st);
   gemm_wr_kernel<Epi><<<grid, RW_THREADS, smem, st>>>(A, lda, M, N, K, img, epi, flip);
   NUDF_LAUNCH_OK();
   return 0;
@@ -993,6 +995,7 @@ static inline int gemm_w(const float* A, int64_t lda, int64_t M, int N, int K, c
     attr_set = true;
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)n_tiles(N, NP));
+  LaunchTimer lt_(epi_family<Epi>::value, st);
   gemm_w_kernel<NP, Epi><<<grid, THREADS, smem, st>>>(A, lda, M, N, K, img, epi);
   NUDF_LAUNCH_OK();
   return 0;
@@ -1011,6 +1014,7 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     attr_set = true;
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, 256), (unsigned)splits);
+  LaunchTimer lt_(FAM_TC_WGRAD, st);
   gemm_tn_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi, colsum_a);
   NUDF_LAUNCH_OK();
   return 0;

@@ -265,6 +265,12 @@ composite_forward_kernel(nudf_render_cfg cfg, RayIn in, nudf_render_out out) {
       float* rs = out.ray_sums + (int64_t)r * 5;
       rs[0] = s_relax_ge; rs[1] = s_relax; rs[2] = s_near_ge; rs[3] = s_near; rs[4] = s_sparse;
     }
+    // the reference drops into pdb on a NaN eikonal term (udf_renderer_blending.py:543-544); here a device flag is raised
+    // and the Python wrapper turns it into a RuntimeError at its next host read
+    if (out.status != nullptr) {
+      const float chk = cc[0] + cc[1] + cc[2] + cb[0] + cb[1] + cb[2] + depth + ws_all + s_relax_ge + s_near_ge + s_sparse;
+      if (!isfinite(chk)) atomicOr(out.status, NUDF_STATUS_NONFINITE_RENDER);
+    }
   }
 }
 
@@ -484,6 +490,7 @@ int nudf_render_composite_forward(const nudf_render_cfg* cfg, const float* heads
   size_t smem = (size_t)RK_WARPS * RK_ARRAYS * (cfg->n_samples + cfg->n_outside) * sizeof(float);
   if (smem > 48 * 1024)
     NUDF_CUDA_OK(cudaFuncSetAttribute(composite_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchTimer lt_(FAM_RAY, (cudaStream_t)stream);
   composite_forward_kernel<<<(unsigned)cdiv(cfg->n_rays, RK_WARPS), RK_WARPS * 32, smem, (cudaStream_t)stream>>>(*cfg, in, *out);
   NUDF_LAUNCH_OK();
   return 0;
@@ -509,6 +516,7 @@ int nudf_render_composite_backward(const nudf_render_cfg* cfg, const float* head
   size_t smem = (size_t)RK_WARPS * RK_ARRAYS * (cfg->n_samples + cfg->n_outside) * sizeof(float);
   if (smem > 48 * 1024)
     NUDF_CUDA_OK(cudaFuncSetAttribute(composite_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchTimer lt_(FAM_RAY, (cudaStream_t)stream);
   composite_backward_kernel<<<(unsigned)cdiv(cfg->n_rays, RK_WARPS), RK_WARPS * 32, smem, (cudaStream_t)stream>>>(*cfg, in, rb, ob);
   NUDF_LAUNCH_OK();
   return 0;

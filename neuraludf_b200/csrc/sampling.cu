@@ -50,7 +50,7 @@ __device__ __forceinline__ void excl_cumprod_f64(const float* in, float* out, in
 // Inverse-CDF sampling with deterministic u (sample_pdf, det=True).  bins[n], w[n-1] (raw weights, +1e-5 added here),
 // cdf: scratch [n].  Writes samples[m] and optionally inds[m].
 __device__ __forceinline__ void sample_pdf_warp(const float* bins, const float* w, float* cdf, int n, const float* u, int m,
-                                                float* samples, int64_t* inds, int lane) {
+                                                float* samples, int64_t* inds, int lane, int32_t* status = nullptr) {
   const int nw = n - 1;
   double s = 0.0;
   for (int j = lane; j < nw; j += 32) s += (double)(w[j] + 1e-5f);
@@ -81,8 +81,11 @@ __device__ __forceinline__ void sample_pdf_warp(const float* bins, const float* 
     if (denom < 1e-5f) denom = 1.0f;
     float t = (uk - c0) / denom;
     float b0 = bins[below], b1 = bins[above];
-    samples[k] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+    const float smp = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+    samples[k] = smp;
     if (inds) inds[k] = lo;
+    // the reference traps non-finite samples with pdb (udf_renderer_blending.py:97-101, 265-269): raise the device flag
+    if (status != nullptr && !isfinite(smp)) atomicOr(status, NUDF_STATUS_NONFINITE_SAMPLES);
   }
 }
 
@@ -90,7 +93,8 @@ __device__ __forceinline__ void sample_pdf_warp(const float* bins, const float* 
 __global__ void __launch_bounds__(SP_WARPS * 32)
 up_sample_kernel(int mode, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z,
                  const float* __restrict__ udf, int n_rays, int n, int m, float sample_dist, float inv_s, float beta,
-                 float gamma, const float* __restrict__ u_lin, float* __restrict__ new_z, int64_t* __restrict__ inds) {
+                 float gamma, const float* __restrict__ u_lin, float* __restrict__ new_z, int64_t* __restrict__ inds,
+                 int32_t* __restrict__ status) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * SP_WARPS + warp;
@@ -157,12 +161,13 @@ up_sample_kernel(int mode, const float* __restrict__ rays_o, const float* __rest
     for (int j = lane; j < n - 1; j += 32) wts[j] = alp[j] * wts[j];
     __syncwarp();
   }
-  sample_pdf_warp(sz, wts, cdf, n, u_lin, m, new_z + (int64_t)r * m, inds ? inds + (int64_t)r * m : nullptr, lane);
+  sample_pdf_warp(sz, wts, cdf, n, u_lin, m, new_z + (int64_t)r * m, inds ? inds + (int64_t)r * m : nullptr, lane, status);
 }
 
 __global__ void __launch_bounds__(SP_WARPS * 32)
 sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, int n_rays, int n, int m,
-                  const float* __restrict__ u_lin, float* __restrict__ samples, int64_t* __restrict__ inds) {
+                  const float* __restrict__ u_lin, float* __restrict__ samples, int64_t* __restrict__ inds,
+                  int32_t* __restrict__ status) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * SP_WARPS + warp;
@@ -172,7 +177,7 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
   for (int i = lane; i < n; i += 32) sb[i] = bins[(int64_t)r * n + i];
   for (int i = lane; i < n - 1; i += 32) sw[i] = weights[(int64_t)r * (n - 1) + i];
   __syncwarp();
-  sample_pdf_warp(sb, sw, cdf, n, u_lin, m, samples + (int64_t)r * m, inds ? inds + (int64_t)r * m : nullptr, lane);
+  sample_pdf_warp(sb, sw, cdf, n, u_lin, m, samples + (int64_t)r * m, inds ? inds + (int64_t)r * m : nullptr, lane, status);
 }
 
 // Sorted merge of z[n] (sorted) and new_z[m] (sorted): rank by binary search; udf gathered alongside.
@@ -212,7 +217,7 @@ extern "C" {
 
 int nudf_up_sample(int32_t mode, const float* rays_o, const float* rays_d, const float* z, const float* udf, int32_t n_rays,
                    int32_t n, int32_t m, float sample_dist, float inv_s, float beta, float gamma, const float* u_lin,
-                   float* new_z, int64_t* inds, void* stream) {
+                   float* new_z, int64_t* inds, int32_t* status, void* stream) {
   NUDF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
   NUDF_REQUIRE(rays_o && rays_d && z && udf && new_z && u_lin, "null pointer");
   NUDF_REQUIRE(n >= 2 && m >= 1, "need n >= 2, m >= 1");
@@ -222,13 +227,13 @@ int nudf_up_sample(int32_t mode, const float* rays_o, const float* rays_d, const
   if (smem > 48 * 1024)
     NUDF_CUDA_OK(cudaFuncSetAttribute(up_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   up_sample_kernel<<<(unsigned)cdiv(n_rays, SP_WARPS), SP_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      mode, rays_o, rays_d, z, udf, n_rays, n, m, sample_dist, inv_s, beta, gamma, u_lin, new_z, inds);
+      mode, rays_o, rays_d, z, udf, n_rays, n, m, sample_dist, inv_s, beta, gamma, u_lin, new_z, inds, status);
   NUDF_LAUNCH_OK();
   return 0;
 }
 
 int nudf_sample_pdf(const float* bins, const float* weights, int32_t n_rays, int32_t n, int32_t m, const float* u_lin,
-                    float* samples, int64_t* inds, void* stream) {
+                    float* samples, int64_t* inds, int32_t* status, void* stream) {
   NUDF_REQUIRE(bins && weights && samples && u_lin, "null pointer");
   NUDF_REQUIRE(n >= 2 && m >= 1, "need n >= 2, m >= 1");
   if (n_rays <= 0) return 0;
@@ -237,7 +242,7 @@ int nudf_sample_pdf(const float* bins, const float* weights, int32_t n_rays, int
   if (smem > 48 * 1024)
     NUDF_CUDA_OK(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sample_pdf_kernel<<<(unsigned)cdiv(n_rays, SP_WARPS), SP_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      bins, weights, n_rays, n, m, u_lin, samples, inds);
+      bins, weights, n_rays, n, m, u_lin, samples, inds, status);
   NUDF_LAUNCH_OK();
   return 0;
 }

@@ -5,7 +5,9 @@ running on the libnudf CUDA kernels.
 Differences that are deliberate (DESIGN.md "boundary"):
   * one fused evaluation gives the UDF value, feature and exact input-gradient (the reference runs the MLP twice);
   * importance sampling, compositing and the regulariser sums never synchronise with the host (the reference has 13
-    blocking syncs per step); NaNs raise a RuntimeError at the end of render() instead of dropping into pdb;
+    blocking syncs per step).  Where the reference drops into pdb on a NaN (:97-101, 265-269, 543-544) the kernels raise a
+    device-side status flag; it is read together with render()'s one host read (`sample_dist`, :605) -- i.e. a non-finite
+    result of call k raises a RuntimeError at the start of call k+1 -- or on demand with `check_finite()`;
   * `render()` evaluates the NeRF++ background only on the n_outside samples render_core consumes (:493-501);
   * per-sample outputs (`gradients`, `alpha*`, ...) are returned detached -- the trainer only uses them after
     .detach() or for logging (exp_runner_blending.py:309-371, 641-668); `weights` is differentiable.
@@ -315,7 +317,8 @@ class UDFRendererBlending:
         if not isinstance(near, torch.Tensor):
             near = torch.Tensor([near]).view(1, 1).to(device)
             far = torch.Tensor([far]).view(1, 1).to(device)
-        sample_dist = ((far - near) / self.n_samples).mean().item()          # the one host sync of render()
+        # the one host sync of render() (:605); the same read carries the device status word of the previous kernels
+        sample_dist = ops.check_status(device, ((far - near) / self.n_samples).mean())
         z_vals = torch.linspace(0.0, 1.0, self.n_samples, device=device)
         z_vals = near + (far - near) * z_vals[None, :]
         z_vals_outside = None
@@ -340,15 +343,25 @@ class UDFRendererBlending:
             z_vals = z_vals.expand(batch_size, -1)
         z_vals = z_vals.contiguous()
 
-        background_alpha = None
-        background_sampled_color = None
         if self.n_importance > 0:
             if self.upsampling_type == 'classical':
                 z_vals = self.importance_sample(rays_o, rays_d, z_vals, sample_dist)
             else:
                 z_vals = self.importance_sample_mix(rays_o, rays_d, z_vals, sample_dist)
-            n_samples = z_vals.shape[1]
+        return self._render_from_z(rays_o, rays_d, z_vals, z_vals_outside, sample_dist, cos_anneal_ratio, background_rgb,
+                                   flip_saturation, color_maps, w2cs, intrinsics, query_c2w, img_index, rays_uv)
 
+    def _render_from_z(self, rays_o, rays_d, z_vals, z_vals_outside, sample_dist, cos_anneal_ratio=None,
+                       background_rgb=None, flip_saturation=0, color_maps=None, w2cs=None, intrinsics=None, query_c2w=None,
+                       img_index=None, rays_uv=None):
+        """Everything of render() after the (non-differentiable) sampling phase: NeRF++ background on the outside samples,
+        fine pass, sparse_random_error (reference :646-721).  Separate so that tests can feed the reference's own sample
+        positions and compare gradients tightly."""
+        device = rays_o.device
+        batch_size = len(rays_o)
+        n_samples = z_vals.shape[1]
+        background_alpha = None
+        background_sampled_color = None
         if self.n_outside > 0:
             z_out = z_vals_outside.expand(batch_size, -1) if z_vals_outside.shape[0] != batch_size else z_vals_outside
             z_vals_feed, _ = torch.sort(torch.cat([z_vals, z_out], dim=-1), dim=-1)
@@ -387,6 +400,13 @@ class UDFRendererBlending:
         out['z_vals'] = z_vals
         out['sparse_random_error'] = sparse_random_error
         return out
+
+    def check_finite(self, device=None):
+        """Synchronises and raises RuntimeError if any sampling / compositing kernel since the last check produced a
+        non-finite result (the reference's pdb traps, :97-101, 265-269, 543-544)."""
+        if device is None:
+            device = next(self.udf_network.parameters()).device
+        ops.check_status(torch.device(device))
 
     def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.01, device='cpu'):
         return extract_geometry(bound_min, bound_max, resolution, threshold,

@@ -26,6 +26,38 @@ def _f32c(t):
     return t.contiguous()
 
 
+_STATUS = {}
+
+
+def status_word(device):
+    """Per-device int32 status word the ray kernels OR their NUDF_STATUS_* bits into (device memory, never read here)."""
+    key = (device.type, device.index)
+    if key not in _STATUS:
+        _STATUS[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _STATUS[key]
+
+
+def check_status(device, extra=None):
+    """ONE host read of the status word (plus `extra`, a 0-d / 1-element tensor the caller wanted on the host anyway,
+    returned as a float).  Raises RuntimeError if a kernel flagged a non-finite result since the last check -- the
+    reference drops into pdb at these places (udf_renderer_blending.py:97-101, 265-269, 543-544)."""
+    st = status_word(device)
+    if extra is None:
+        bits, val = int(st.item()), None
+    else:
+        both = torch.cat([extra.reshape(1).double(), st.double()]).tolist()
+        val, bits = both[0], int(both[1])
+    if bits:
+        st.zero_()
+        what = []
+        if bits & L.STATUS_NONFINITE_SAMPLES:
+            what.append("importance sampling produced non-finite sample positions")
+        if bits & L.STATUS_NONFINITE_RENDER:
+            what.append("compositing produced non-finite colour / depth / regulariser values")
+        raise RuntimeError("neuraludf_b200: " + "; ".join(what) + " (status bits %d)" % bits)
+    return val
+
+
 def _ptr_array(tensors):
     arr = (ctypes.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
@@ -46,12 +78,18 @@ class UdfHandle:
         self._key = None
         self.desc = None
         self.wfold = None
+        self.grad_sink = None        # dp.GradBucket region: backward writes the parameter gradients in place there
 
     def params(self):
         ps = []
         for m in self.layers:
             ps += [m.weight_g, m.weight_v, m.bias]
         return ps
+
+    def sink_layout(self):
+        """parameter groups in the order a gradient bucket must lay them out: the biases first, contiguous and in layer
+        order (nudf_udf_backward writes dbias as ONE array), then g / v of every layer"""
+        return [[m.bias for m in self.layers], [p for m in self.layers for p in (m.weight_g, m.weight_v)]]
 
     def refresh(self):
         ps = self.params()
@@ -120,21 +158,32 @@ class _UdfFunction(torch.autograd.Function):
         nscr = lib.nudf_udf_scratch_floats(ctypes.byref(h.desc), P)
         scratch = torch.empty(max(nscr, 1), dtype=torch.float32, device=dev)
         dw = torch.empty_like(h.wfold)
-        nb = sum(int(m.bias.numel()) for m in h.layers)
-        db = torch.empty(nb, dtype=torch.float32, device=dev)
+        sink = h.grad_sink if (h.grad_sink is not None and h.grad_sink.begin()) else None
+        if sink is not None:                  # gradients land directly in the data-parallel bucket (dp.GradBucket)
+            db = sink.block([m.bias for m in h.layers])
+            dgs = [sink.view(m.weight_g) for m in h.layers]
+            dvs = [sink.view(m.weight_v) for m in h.layers]
+            dbs = [sink.view(m.bias) for m in h.layers]
+        else:
+            nb = sum(int(m.bias.numel()) for m in h.layers)
+            db = torch.empty(nb, dtype=torch.float32, device=dev)
+            dgs = [torch.empty_like(m.weight_g) for m in h.layers]
+            dvs = [torch.empty_like(m.weight_v) for m in h.layers]
+            dbs, off = [], 0
+            for m in h.layers:
+                n = m.bias.numel()
+                dbs.append(db[off:off + n])
+                off += n
         L.check(lib.nudf_udf_backward(ctypes.byref(h.desc), L.ptr(h.wfold), L.ptr(pts), P, L.ptr(out_bar),
                                       out_bar.shape[1] if out_bar is not None else 0, L.ptr(grad_bar), L.ptr(buf),
                                       L.ptr(scratch), L.ptr(dw), L.ptr(db), L.stream_ptr()), "nudf_udf_backward")
-        dgs = [torch.empty_like(m.weight_g) for m in h.layers]
-        dvs = [torch.empty_like(m.weight_v) for m in h.layers]
         L.check(lib.nudf_udf_unfold_grads(ctypes.byref(h.desc), L.ptr(dw), _ptr_array(dgs), _ptr_array(dvs),
                                           L.stream_ptr()), "nudf_udf_unfold_grads")
+        if sink is not None:
+            sink.ready()
         grads = []
-        off = 0
-        for l, m in enumerate(h.layers):
-            n = m.bias.numel()
-            grads += [dgs[l], dvs[l], db[off:off + n].clone()]
-            off += n
+        for l in range(len(h.layers)):
+            grads += [dgs[l], dvs[l], dbs[l]]
         return (None, None, None) + tuple(grads)
 
 
@@ -169,12 +218,18 @@ class ColorHandle:
         self._key = None
         self.desc = None
         self.wfold = None
+        self.grad_sink = None
 
     def params(self):
         ps = []
         for m in list(self.main) + list(self.base):
             ps += [m.weight_g, m.weight_v, m.bias]
         return ps
+
+    def sink_layout(self):
+        """biases first in the library's order (base layers, then main layers: nudf_color_backward's dbias), then g / v"""
+        mods = list(self.base) + list(self.main)
+        return [[m.bias for m in mods], [p for m in mods for p in (m.weight_g, m.weight_v)]]
 
     def refresh(self):
         ps = self.params()
@@ -240,24 +295,36 @@ class _ColorFunction(torch.autograd.Function):
         scratch = torch.empty(max(nscr, 1), dtype=torch.float32, device=dev)
         dfeat = torch.empty(P, d_feature, dtype=torch.float32, device=dev)
         dw = torch.empty_like(h.wfold)
-        nb = sum(int(m.bias.numel()) for m in list(h.base) + list(h.main))
-        db = torch.empty(nb, dtype=torch.float32, device=dev)
+        mods = list(h.base) + list(h.main)
+        sink = h.grad_sink if (h.grad_sink is not None and h.grad_sink.begin()) else None
+        if sink is not None:
+            db = sink.block([m.bias for m in mods])
+            new_g = lambda m: sink.view(m.weight_g)
+            new_v = lambda m: sink.view(m.weight_v)
+            bb = [sink.view(m.bias) for m in h.base]
+            bm = [sink.view(m.bias) for m in h.main]
+        else:
+            nb = sum(int(m.bias.numel()) for m in mods)
+            db = torch.empty(nb, dtype=torch.float32, device=dev)
+            new_g = lambda m: torch.empty_like(m.weight_g)
+            new_v = lambda m: torch.empty_like(m.weight_v)
+            off = 0            # bias layout in the library: base layers first, then main layers
+            bb, bm = [], []
+            for m in h.base:
+                n = m.bias.numel(); bb.append(db[off:off + n]); off += n
+            for m in h.main:
+                n = m.bias.numel(); bm.append(db[off:off + n]); off += n
         L.check(lib.nudf_color_backward(ctypes.byref(h.desc), L.ptr(h.wfold), P, L.ptr(cb_bar), L.ptr(c_bar),
                                         L.ptr(bl_bar), L.ptr(buf), L.ptr(scratch), L.ptr(dfeat), d_feature, L.ptr(dw),
                                         L.ptr(db), L.stream_ptr()), "nudf_color_backward")
-        dgb = [torch.empty_like(m.weight_g) for m in h.base]
-        dvb = [torch.empty_like(m.weight_v) for m in h.base]
-        dgm = [torch.empty_like(m.weight_g) for m in h.main]
-        dvm = [torch.empty_like(m.weight_v) for m in h.main]
+        dgb = [new_g(m) for m in h.base]
+        dvb = [new_v(m) for m in h.base]
+        dgm = [new_g(m) for m in h.main]
+        dvm = [new_v(m) for m in h.main]
         L.check(lib.nudf_color_unfold_grads(ctypes.byref(h.desc), L.ptr(dw), _ptr_array(dgb), _ptr_array(dvb),
                                             _ptr_array(dgm), _ptr_array(dvm), L.stream_ptr()), "nudf_color_unfold_grads")
-        # bias layout in the library: base layers first, then main layers
-        off = 0
-        bb, bm = [], []
-        for m in h.base:
-            n = m.bias.numel(); bb.append(db[off:off + n].clone()); off += n
-        for m in h.main:
-            n = m.bias.numel(); bm.append(db[off:off + n].clone()); off += n
+        if sink is not None:
+            sink.ready()
         grads = []
         for l in range(len(h.main)):
             grads += [dgm[l], dvm[l], bm[l]]
@@ -279,6 +346,10 @@ class NerfHandle:
         self.meta = (D, W, d_in, multires, multires_view, skip)
         self._key = None
         self.wimg = None
+        self.grad_sink = None
+
+    def sink_layout(self):
+        return [self.params()]
 
     def images(self):
         """bf16 hi/lo weight images for the tensor engine, rebuilt when a parameter changed (None on the fp32 engine)."""
@@ -338,7 +409,6 @@ class _NerfFunction(torch.autograd.Function):
         L.check(lib.nudf_nerf_forward(ctypes.byref(d), L.ptr(wimg), L.ptr(pts), L.ptr(dirs), int(samples_per_ray), P,
                                       L.ptr(sigma), L.ptr(rgb), L.ptr(buf), L.stream_ptr()), "nudf_nerf_forward")
         ctx.handle, ctx.P, ctx.wimg = handle, P, wimg
-        ctx.versions = tuple(p._version for p in params)
         ctx.save_for_backward(buf, *params)
         return sigma, rgb
 
@@ -353,9 +423,13 @@ class _NerfFunction(torch.autograd.Function):
         sigma_bar, rgb_bar = _f32c(sigma_bar), _f32c(rgb_bar)
         n = lib.nudf_nerf_scratch_floats(ctypes.byref(d), P)
         scratch = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
-        grads = [torch.empty_like(p) for p in params]
+        sink = ctx.handle.grad_sink if (ctx.handle.grad_sink is not None and ctx.handle.grad_sink.begin()) else None
+        live = ctx.handle.params()
+        grads = [sink.view(q) for q in live] if sink is not None else [torch.empty_like(p) for p in params]
         L.check(lib.nudf_nerf_backward(ctypes.byref(d), L.ptr(ctx.wimg), P, L.ptr(sigma_bar), L.ptr(rgb_bar), L.ptr(buf),
                                        L.ptr(scratch), _ptr_array(grads), L.stream_ptr()), "nudf_nerf_backward")
+        if sink is not None:
+            sink.ready()
         return (None, None, None, None) + tuple(grads)
 
 
@@ -429,6 +503,7 @@ class _CompositeFunction(torch.autograd.Function):
         ro = L.RenderOut()
         for k in L.RENDER_OUT_FIELDS:
             setattr(ro, k, outs[k].data_ptr() if k in outs else None)
+        ro.status = status_word(dev).data_ptr()
         L.check(lib.nudf_render_composite_forward(ctypes.byref(cfg), L.ptr(heads), L.ptr(rays_d), L.ptr(pts), L.ptr(mid),
                                                   L.ptr(dists), L.ptr(udf), ld_udf, L.ptr(grads), L.ptr(scb), L.ptr(sc),
                                                   L.ptr(bg_alpha), L.ptr(bg_color), ctypes.byref(ro), L.stream_ptr()),
@@ -560,7 +635,7 @@ def up_sample(mode, rays_o, rays_d, z, udf, sample_dist, m, inv_s, beta, gamma, 
     inds = torch.empty(N, m, dtype=torch.int64, device=z.device) if return_inds else None
     L.check(lib.nudf_up_sample(int(mode), L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(udf), N, n, m, float(sample_dist),
                                float(inv_s), float(beta), float(gamma), L.ptr(_u_lin(m, z.device)), L.ptr(new_z),
-                               L.ptr(inds), L.stream_ptr()), "nudf_up_sample")
+                               L.ptr(inds), L.ptr(status_word(z.device)), L.stream_ptr()), "nudf_up_sample")
     return (new_z, inds) if return_inds else new_z
 
 
@@ -572,7 +647,7 @@ def sample_pdf(bins, weights, m, return_inds=False):
     samples = torch.empty(N, m, dtype=torch.float32, device=bins.device)
     inds = torch.empty(N, m, dtype=torch.int64, device=bins.device) if return_inds else None
     L.check(lib.nudf_sample_pdf(L.ptr(bins), L.ptr(weights), N, n, m, L.ptr(_u_lin(m, bins.device)), L.ptr(samples),
-                                L.ptr(inds), L.stream_ptr()), "nudf_sample_pdf")
+                                L.ptr(inds), L.ptr(status_word(bins.device)), L.stream_ptr()), "nudf_sample_pdf")
     return (samples, inds) if return_inds else samples
 
 

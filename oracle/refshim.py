@@ -1,9 +1,10 @@
 """Import shim for the UNMODIFIED reference (xxlong0/NeuralUDF) -- test infrastructure only.
 
-The reference lives read-only at /root/reference and exists ONLY in the dev container (never on the
-GPU box).  This module is used by oracle/make_golden.py and by the `not gpu` tests that pin the
-oracle restatement (oracle/oracle_torch.py) against the real reference code.  Nothing on the product
-path imports it.
+The reference lives read-only at /root/reference in the dev container; on the GPU box only the
+byte-for-byte staged copy `oracle/_ref/` (oracle/make_ref.py; git-ignored, shipped with the snapshot)
+exists.  This module is used by oracle/make_golden.py, by the `not gpu` tests that pin the oracle
+restatement (oracle/oracle_torch.py) against the real reference code, and by bench.py's CPU-baseline /
+`--impl reference` arm.  Nothing on the product path imports it.
 
 The reference's `models/udf_renderer_blending.py:6-9` and `models/fields.py:6` import
 `mcubes, icecream, skimage.measure, termcolor`, none of which is used on the render path; they are
@@ -14,11 +15,26 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("NUDF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref")          # byte-for-byte copies made by oracle/make_ref.py (git-ignored; travel to the GPU box)
+
+
+def _pick_root():
+    r = os.environ.get("NUDF_REFERENCE_ROOT", "/root/reference")
+    if os.path.isfile(os.path.join(r, "models", "udf_renderer_blending.py")):
+        return r
+    return _STAGED
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "udf_renderer_blending.py"))
+
+
+def is_staged_copy() -> bool:
+    return os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_STAGED)
 
 
 def _stub(name, **attrs):

@@ -26,7 +26,7 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "ray-samples/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -85,7 +85,7 @@ def test_render_core_blending_vs_reference(golden, fx, engine):
                 worst = max(worst, e)
                 n += 1
                 report(tag + "dparam.%s.%s" % (mn, pn), rel=e)
-                assert e < (5e-3 if engine == 0 else 2e-2), (key, e)
+                assert e < 2e-3, (key, e)     # measured worst: 2.7e-4 (all engines); the reference's own fp32 noise is ~2e-3
         assert n >= 60
         report(tag + "dparam.worst_rel", rel=worst)
         # the blending logits (10 output rows of the colour head) must receive a gradient
