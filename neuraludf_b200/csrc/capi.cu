@@ -41,11 +41,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// NUDF_TC_MASK: which chains may run on the tensor engine (bits: 1 fwd value, 2 reverse sweep, 4 tangent, 8 backward,
-// 16 weight gradients, 32 colour-net backward, 64 NeRF++ backward, 128 colour / NeRF++ forward).  Default (126): everything
-// except the forward value chains (gemm_engine.cuh explains why).
+// NUDF_TC_MASK: which chains may run on the tensor engine (bits: 1 UDF value chain -- the fused exact fp16-slice kernel of
+// udf_chain.cuh --, 2 reverse sweep, 4 tangent, 8 backward, 16 weight gradients, 32 colour-net backward, 64 NeRF++ backward,
+// 128 colour / NeRF++ forward).  Default (127): everything except the forward passes of the ReLU networks (gemm_engine.cuh
+// explains why).
 static int g_tc_mask = -1;
-static const int kDefaultTcMask = 2 | 4 | 8 | 16 | 32 | 64;
+static const int kDefaultTcMask = 1 | 2 | 4 | 8 | 16 | 32 | 64;
 int tc_mask() {
   if (g_tc_mask < 0) {
     const char* e = getenv("NUDF_TC_MASK");

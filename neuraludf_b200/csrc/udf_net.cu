@@ -5,6 +5,7 @@
 #include "../../include/nudf.h"
 #include "common.cuh"
 #include "gemm_engine.cuh"
+#include "udf_chain.cuh"
 
 namespace nudf {
 
@@ -15,6 +16,9 @@ struct UdfPlan {
   int64_t w_off[NUDF_MAX_LAYERS], w_ld[NUDF_MAX_LAYERS], w_total;
   int64_t b_off[NUDF_MAX_LAYERS], b_total;
   int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_nt3[NUDF_MAX_LAYERS], img_nn1, img_total;   // uint16 offsets of the bf16 hi/lo weight images
+  int64_t img_chain[NUDF_MAX_LAYERS];   // uint16 offsets of the fused value chain's fp16 slice images (udf_chain.cuh)
+  int64_t sb_off[NUDF_MAX_LAYERS], sb_total;   // float offsets (after the images) of the chain's per-column (scale, bias) tables
+  int chain_ok;                         // the fused value chain supports this network shape
   int pe_ld, y_ld;
   int a_ld[NUDF_MAX_LAYERS];    // ld of A[l] (input of layer l), l >= 1
   int o_ld[NUDF_MAX_LAYERS];    // ld of D[l] / Q[l] (out_dim rounded)
@@ -54,7 +58,21 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
   // feature rows 1.. of the last layer as a (N = in, K = d_out - 1) operand: the udf-head row is applied as a rank-1 update
   p->img_nn1 = ioff;
   if (p->d_out > 1) ioff += tc::image_elems(p->in_dim[p->n_lin - 1], p->d_out - 1, 2);
+  ioff = round_up(ioff, 512);           // the chain image is fetched with cp.async.bulk: keep its slices 1024-byte aligned
+  for (int l = 0; l < p->n_lin; ++l) { p->img_chain[l] = ioff; ioff += chain::ch_layer_elems(p->out_dim[l], p->in_dim[l]); }
   p->img_total = round_up(ioff, 8);
+  int64_t soff = 0;
+  for (int l = 0; l < p->n_lin; ++l) { p->sb_off[l] = soff; soff += 2 * (int64_t)chain::CH_NT * chain::ch_n_tiles(p->out_dim[l]); }
+  p->sb_total = soff;
+  // shapes the fused chain handles: PE fits one K slice, every contraction K <= 256, hidden layers <= 2 output tiles
+  p->chain_ok = p->d_pe <= chain::CH_MAX_PE;
+  int n_st = 0;
+  for (int l = 0; l < p->n_lin; ++l) {
+    if (tc::pad64(p->in_dim[l]) > 64 * chain::CH_MAX_SLICES) p->chain_ok = 0;
+    if (l < p->n_lin - 1 && p->out_dim[l] + (l + 1 == p->skip ? p->d_pe : 0) > 2 * chain::CH_NT) p->chain_ok = 0;
+    n_st += chain::ch_n_tiles(p->out_dim[l]) * (tc::pad64(p->in_dim[l]) / 64);
+  }
+  if (n_st > chain::CH_MAX_STAGES) p->chain_ok = 0;
   NUDF_REQUIRE(p->in_dim[0] == p->d_pe, "in_dim[0] must equal the positional-encoding width");
   NUDF_REQUIRE(p->out_dim[p->n_lin - 1] == p->d_out, "last layer width must equal d_out");
   for (int l = 1; l < p->n_lin; ++l) {
@@ -366,15 +384,71 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
     if (p.d_out > 1)
       if (int rc = tc::prep_weights(wfold + p.w_off[last] + p.w_ld[last], p.w_ld[last], p.in_dim[last], p.d_out - 1, 1, 2, img + p.img_nn1, st))
         return rc;
+    if (p.chain_ok) {
+      // fused value chain: fp16 slice images + per-column (scale, bias) tables (udf_chain.cuh)
+      float2* sb = reinterpret_cast<float2*>(wfold + p.w_total + p.img_total / 2);
+      for (int l = 0; l < p.n_lin; ++l) {
+        chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.out_dim[l]), 64, 0, st>>>(
+            wfold + p.w_off[l], p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], img + p.img_chain[l], sb + p.sb_off[l] / 2);
+        NUDF_LAUNCH_OK();
+      }
+    }
   }
   return 0;
 }
+
 static inline const uint16_t* img_base(const UdfPlan& p, const float* wfold) {
   return reinterpret_cast<const uint16_t*>(wfold + p.w_total);
 }
 
+// Parameters of the fused value chain (udf_chain.cuh) for P points.  value_only: the last layer is restricted to its udf-head
+// row and only udf[P] is written; otherwise the context tensors E0, A[1..], Y are written as the per-layer path does.
+static void build_chain(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, float* ctx, const UdfCtx* c, float* udf,
+                        chain::ChainParams* cp) {
+  const bool value_only = udf != nullptr;
+  const float2* sb = reinterpret_cast<const float2*>(wfold + p.w_total + p.img_total / 2);
+  cp->n_layers = p.n_lin;
+  cp->img = img_base(p, wfold);
+  cp->pts = pts; cp->P = P; cp->scale = p.scale; cp->n_freq = p.L; cp->d_pe = p.d_pe;
+  cp->e0 = value_only ? nullptr : ctx + c->e0; cp->pe_ld = p.pe_ld;
+  cp->udf_out = udf; cp->inv_scale = 1.0f / p.scale;
+  cp->trace = nullptr;
+  int st = 0;
+  for (int l = 0; l < p.n_lin; ++l) {
+    chain::ChainLayer& L = cp->L[l];
+    const bool last = l == p.n_lin - 1;
+    L.K = p.in_dim[l];
+    L.N = (last && value_only) ? 1 : p.out_dim[l];
+    L.n_kslices = tc::pad64(L.K) / 64;
+    L.n_tiles = chain::ch_n_tiles(L.N);
+    L.stage0 = st;
+    L.last = last ? 1 : 0;
+    L.pe_next = (!last && l + 1 == p.skip) ? p.d_pe : 0;
+    L.post_scale = (!last && l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+    L.sb = sb + p.sb_off[l] / 2;
+    if (value_only) { L.out = nullptr; L.ld_out = 0; }
+    else if (last) { L.out = ctx + c->y; L.ld_out = p.y_ld; }
+    else { L.out = ctx + c->a[l + 1]; L.ld_out = p.a_ld[l + 1]; }
+    for (int t = 0; t < L.n_tiles; ++t) {
+      const int rows_full = chain::ch_tile_rows(p.out_dim[l], t);
+      for (int s = 0; s < L.n_kslices; ++s, ++st) {
+        chain::ChainStage& S = cp->S[st];
+        S.src = (uint32_t)(p.img_chain[l] + chain::ch_tile_off(p.out_dim[l], p.in_dim[l], t) + (int64_t)s * chain::CH_WPL * rows_full * 64);
+        S.rows = (uint16_t)((last && value_only) ? 16 : rows_full);
+        S.plane_rows = (uint16_t)rows_full;
+      }
+    }
+  }
+  cp->n_stages = st;
+}
+
 static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P,
                        float* ctx, const UdfCtx& c, cudaStream_t st) {
+  if (p.chain_ok && tc_on(TC_FWD)) {            // one fused tcgen05 kernel for all layers (activations stay on chip)
+    chain::ChainParams cp;
+    build_chain(p, wfold, pts, P, ctx, &c, nullptr, &cp);
+    return chain::launch_chain(cp, st);
+  }
   float* e0 = ctx + c.e0;
   float* askip = nullptr; int askip_ld = 0, askip_col = 0;
   if (p.skip >= 1) { askip = ctx + c.a[p.skip]; askip_ld = p.a_ld[p.skip]; askip_col = p.out_dim[p.skip - 1]; }
@@ -480,7 +554,7 @@ extern "C" {
 int64_t nudf_udf_folded_floats(const nudf_udf_desc* d) {
   UdfPlan p;
   if (make_plan(d, &p)) return -1;
-  return p.w_total + p.img_total / 2;   // fp32 folded weights, then the bf16 hi/lo images (2 per float)
+  return p.w_total + p.img_total / 2 + p.sb_total;   // fp32 folded weights, the 16-bit weight images (2 per float), the chain's (scale, bias) tables
 }
 
 int nudf_udf_fold_weights(const nudf_udf_desc* d, float* wfold, void* stream) {
@@ -530,8 +604,14 @@ int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts,
   UdfPlan p;
   if (int rc = make_plan(d, &p)) return rc;
   if (P <= 0) return 0;
-  NUDF_REQUIRE(wfold && pts && work && udf, "null pointer");
+  NUDF_REQUIRE(wfold && pts && udf, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (p.chain_ok && tc_on(TC_FWD)) {
+    chain::ChainParams cp;
+    build_chain(p, wfold, pts, P, nullptr, nullptr, udf, &cp);
+    return chain::launch_chain(cp, st);
+  }
+  NUDF_REQUIRE(work != nullptr, "null pointer (work)");
   UdfCtx c;
   ctx_layout(p, P, 0, &c);
   // value-only: the last layer needs only its row 0 (the udf head); the 256 feature rows are skipped.
