@@ -302,6 +302,22 @@ int nudf_blend_backward(const nudf_blend_cfg* cfg, const float* pts, const float
                         const float* imgs, const float* logits, int64_t ld_logits, const float* g_pix, const float* g_pat,
                         float* g_logits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * ray generation on the device (replaces the per-step tensor algebra of the reference's data loader)
+ * ------------------------------------------------------------------------------------------------------------ */
+/* gen_random_rays_patches_at (dataset/dataset.py:228-294) without the patch crop: for n pixels (px, py: DEVICE int64, drawn by
+ * the caller with torch.randint like the reference) of one image:
+ *   rays[n,10] = (origin, unit direction in world space, rgb gathered from image[H,W,3], mask[H,W,3] > 0)
+ *   ndc_uv[n,2] = 2 px/(W-1) - 1, 2 py/(H-1) - 1 (may be NULL);  near/far[n] = near_far_from_sphere (:329-335; may be NULL)
+ * intrinsics_inv: DEVICE row-major 3x3 (top-left block of intrinsics_all_inv[idx], compact), pose: DEVICE row-major 4x4 c2w. */
+int nudf_gen_rays(const float* intrinsics_inv, const float* pose, const int64_t* px, const int64_t* py, int32_t n,
+                  const float* image, const float* mask, int32_t H, int32_t W, float* rays, float* ndc_uv, float* near,
+                  float* far, void* stream);
+/* gen_rays_at (dataset/dataset.py:151-164): rays of the [Hl, Wl] = [H // level, W // level] grid of pixel centres
+ * linspace(0, W-1, Wl) x linspace(0, H-1, Hl); rays_o / rays_d [Hl, Wl, 3] (already transposed to image order). */
+int nudf_gen_rays_grid(const float* intrinsics_inv, const float* pose, int32_t W, int32_t H, int32_t Wl, int32_t Hl, float* rays_o,
+                       float* rays_d, float* near, float* far, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,6 +146,8 @@ _SIGNATURES = {
                                     ctypes.c_int32, c_void_p, c_void_p, c_void_p]),
     "nudf_points_on_rays": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32, c_void_p,
                                            c_void_p]),
+    "nudf_gen_rays": (ctypes.c_int, [c_void_p] * 4 + [ctypes.c_int32] + [c_void_p] * 2 + [ctypes.c_int32] * 2 + [c_void_p] * 5),
+    "nudf_gen_rays_grid": (ctypes.c_int, [c_void_p] * 2 + [ctypes.c_int32] * 4 + [c_void_p] * 5),
     "nudf_outside_points": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_float, c_void_p, c_void_p, c_void_p]),
 }

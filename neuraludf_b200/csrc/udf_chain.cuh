@@ -41,8 +41,10 @@ constexpr uint32_t CH_A_BYTES = CH_MAX_SLICES * 2u * CH_APLANE;     // 128 KB
 constexpr int CH_WPL = 3;                                   // weight planes
 constexpr uint32_t CH_WSLOT = CH_WPL * CH_NT * 128u;        // 48 KB: one K slice of one N tile, 3 planes
 constexpr int CH_NSLOT = 2;
-constexpr int CH_EPI_THREADS = 256;
-constexpr int CH_THREADS = 320;
+constexpr int CH_EPI_WARPS = 16;
+constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;           // 512
+constexpr int CH_MMA_WARP = 16, CH_LOAD_WARP = 17;
+constexpr int CH_THREADS = 576;
 constexpr int CH_MAX_STAGES = 112;
 constexpr int CH_MAX_PE = 64;                               // positional-encoding width (K of layer 0) <= one K slice
 
@@ -53,7 +55,8 @@ struct ChainLayer {
   int last;                  // 1: last layer (plain output, no activation)
   int pe_next;               // PE columns appended to the next layer's input (skip layer), else 0
   float post_scale;          // 1/sqrt(2) when the next layer is the skip layer
-  const float2* sb;          // [128 n_tiles] (2^(ew_n - 13), bias_n); zero for padded columns
+  const float* bias;         // [128 n_tiles], zero for padded columns
+  const float* wscale;       // DEVICE scalar 2^(E_l - 13): weights of this layer are 2^(E_l - 13) (w0 + w1 + w2)
   float* out;                // hidden: A[l+1] [P, ld_out] or null; last: Y [P, ld_out] or null
   int64_t ld_out;
 };
@@ -72,7 +75,7 @@ struct ChainParams {
   float* udf_out; float inv_scale;       // value-only mode: udf_out[P] = |y_0| / scale
   long long* trace;                      // profiling aid (NUDF_CHAIN_TRACE=1): clock64() stamps of CTA 0, first point tile
 };
-// trace layout: [role 0 = epilogue half 0, 1 = epilogue half 1, 2 = MMA issuer, 3 = loader][layer][8]
+// trace layout: [role 0 = epilogue warp 0, 1 = epilogue warp 12, 2 = MMA issuer][layer][8]
 constexpr int CH_TRACE_WORDS = 4 * NUDF_MAX_LAYERS * 8;
 #define CH_TR(role, l, k, v) do { if (tr_on) p.trace[((role) * NUDF_MAX_LAYERS + (l)) * 8 + (k)] = (v); } while (0)
 
@@ -91,32 +94,35 @@ __host__ __device__ inline int64_t ch_tile_off(int N, int K, int t) {
 }
 
 // ---- weight image ------------------------------------------------------------------------------------------------------
-// one block per padded output row; W row-major [N, ldw]
-static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int N, int K,
-                                         uint16_t* __restrict__ img, float2* __restrict__ sb) {
-  const int col = blockIdx.x;                    // padded output column: 128 t + local row
-  const int t = col / CH_NT, nl = col - t * CH_NT;
-  const int rows_t = ch_tile_rows(N, t);
-  if (nl >= rows_t) {                            // beyond the padded tile: only the (scale, bias) table entry exists
-    if (threadIdx.x == 0) sb[col] = make_float2(0.f, 0.f);
-    return;
-  }
-  const bool valid = col < N;
-  const int Kp = pad64(K);
+// meta[0] = 2^(3 - E), meta[1] = 2^(E - 13) with 2^E > max |W| over the whole layer (one power of two per LAYER: the integer
+// slice w0 then has up to 4 bits for the largest weights and fewer for small rows, whose precision lives in the floating
+// fp16 remainders w1, w2 -- 22 more bits relative to each element)
+static __global__ void chain_layer_scale_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, float* __restrict__ meta) {
   float mx = 0.f;
-  if (valid)
-    for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, fabsf(W[(int64_t)col * ldw + k]));
+  for (int64_t i = threadIdx.x; i < (int64_t)N * K; i += blockDim.x) mx = fmaxf(mx, fabsf(W[(i / K) * ldw + (i % K)]));
   __shared__ float red[32];
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
-  mx = 0.f;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
-  // 2^ew > max |w|  (exponent field + 1); scaled = w 2^(3 - ew) in (-8, 8)
-  int ew = 0;
-  if (mx > 1e-30f && mx < 1e30f) ew = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;
-  const float up = __uint_as_float((uint32_t)(3 - ew + 127) << 23);          // 2^(3 - ew)
-  if (threadIdx.x == 0) sb[col] = make_float2(valid ? __uint_as_float((uint32_t)(ew - 13 + 127) << 23) : 0.f, (valid && bias) ? bias[col] : 0.f);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+    int e = 0;
+    if (mx > 1e-30f && mx < 1e30f) e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;
+    meta[0] = __uint_as_float((uint32_t)(3 - e + 127) << 23);
+    meta[1] = __uint_as_float((uint32_t)(e - 13 + 127) << 23);
+  }
+}
+// one block per padded output row; W row-major [N, ldw]
+static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int N, int K,
+                                         const float* __restrict__ meta, uint16_t* __restrict__ img, float* __restrict__ bias_tab) {
+  const int col = blockIdx.x;                    // padded output column: 128 t + local row
+  const int t = col / CH_NT, nl = col - t * CH_NT;
+  const int rows_t = ch_tile_rows(N, t);
+  const bool valid = col < N;
+  if (threadIdx.x == 0) bias_tab[col] = (valid && bias) ? bias[col] : 0.f;
+  if (nl >= rows_t) return;                      // beyond the padded tile: only the bias table entry exists
+  const int Kp = pad64(K);
+  const float up = meta[0];                      // 2^(3 - E): scaled weights are in (-8, 8)
   uint16_t* base = img + ch_tile_off(N, K, t);
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
     float w = (valid && k < K) ? W[(int64_t)col * ldw + k] * up : 0.f;
@@ -138,25 +144,64 @@ static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ld
 __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) {     // kind::f16: D = F32, A = B = F16, K-major, M = 128
   return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float v[32]) {
+// TMEM -> registers, 16 consecutive columns of this thread's lane (row); load and wait::ld in ONE asm statement so that no
+// use of the destination registers can be scheduled between them
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// two loads (main and correction accumulator) in flight together, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float v[16], float w[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  uint32_t* q = reinterpret_cast<uint32_t*>(w);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]),
+        "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]),
+        "=r"(q[14]), "=r"(q[15])
+      : "r"(ta), "r"(tb)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
-      "r"(r[31])
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// per-row power-of-two scale: 2^e > m; returns sa = 2^(e - 11) and inv = 2^(11 - e)
-__device__ __forceinline__ void row_scale(float m, float& sa, float& inv) {
+// softplus(beta = 100) with the MUFU base-2 primitives: max(z, 0) + ln2/100 * log2(1 + 2^(-|100 z| log2 e)); identical to
+// common.cuh's softplus100 up to the rounding of the two constant folds (|diff| < 1e-9)
+__device__ __forceinline__ float softplus100_fast(float z) {
+  float t, l;
+  const float az = fabsf(z) * -144.26950408889634f;          // -100 log2(e) |z|
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(az));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
+  const float sp = fmaf(l, 0.0069314718055994531f, fmaxf(z, 0.0f));     // ln(2) / 100
+  return 100.0f * z > 20.0f ? z : sp;
+}
+// biased exponent field of a non-negative float: the per-row scale only needs max over the row of this
+__device__ __forceinline__ uint32_t expo_bits(float m) { return (__float_as_uint(m) >> 23) & 0xffu; }
+// per-row power-of-two scale from the exponent field E of the row maximum: 2^e > max with e = E - 126
+__device__ __forceinline__ void row_scale(uint32_t E, float& sa, float& inv) {
   int e = 0;
-  if (m > 1e-30f && m < 1e30f) e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;
+  if (E > 27u && E < 227u) e = (int)E - 126;
   sa = __uint_as_float((uint32_t)(e - 11 + 127) << 23);
   inv = __uint_as_float((uint32_t)(11 - e + 127) << 23);
 }
@@ -182,9 +227,9 @@ struct ChainCtl {
   uint64_t a_ready[CH_MAX_SLICES];
   uint32_t tmem_addr;
   uint32_t pad_;
-  float rowmax[2][2][128];      // [layer parity][column half][row]
+  uint8_t rowexp[2][4][128];    // [layer parity][column quarter][row]: exponent field of the partial row maximum
 };
-// 128 KB of A planes + 2 x 48 KB weight slots + control block = 226.1 KB of the 227 KB a CTA may have: no room for an alignment
+// 128 KB of A planes + 2 x 48 KB weight slots + control block = 225.1 KB of the 227 KB a CTA may have: no room for an alignment
 // slack, so the dynamic shared-memory window itself is declared 1024-byte aligned (SWIZZLE_128B operands need it) and the
 // kernel traps if the runtime did not honour that.
 constexpr size_t CH_SMEM_BYTES = (size_t)CH_A_BYTES + (size_t)CH_NSLOT * CH_WSLOT + sizeof(ChainCtl);
@@ -202,26 +247,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
 
   if (tid == 0) {
     for (int s = 0; s < CH_NSLOT; ++s) { mbar_init(&ctl->w_full[s], 1); mbar_init(&ctl->w_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_empty[s], 128); }
-    for (int s = 0; s < CH_MAX_SLICES; ++s) mbar_init(&ctl->a_ready[s], 128);
+    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_empty[s], CH_EPI_THREADS); }
+    for (int s = 0; s < CH_MAX_SLICES; ++s) mbar_init(&ctl->a_ready[s], CH_EPI_THREADS / 2);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&ctl->tmem_addr, 512);
+  if (warp == CH_MMA_WARP) tmem_alloc(&ctl->tmem_addr, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = ctl->tmem_addr;
 
-  if (warp < 8) {
+  if (warp < CH_EPI_WARPS) {
     // =========================================== epilogue warps ===========================================
-    const int quad = warp & 3, half = warp >> 2;
+    // warp w: TMEM lane quadrant w & 3 (tile rows 32 (w & 3) ..), column quarter cq = w >> 2: columns [32 cq, 32 cq + 32) of
+    // EVERY N tile, so all 16 warps work on tile 0 while the tensor core is still busy with tile 1.
+    const int quad = warp & 3, cq = warp >> 2;
     const int r_in = quad * 32 + lane;                       // row of the tile = TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t t_m = t_lane + (uint32_t)half * 256u;     // accumulator pair of N tile `half`: M at +0, C at +128
-    uint32_t af_cnt = 0;                                     // completed waits on acc_full[half]
-    uint32_t lp = 0;                                         // layer parity for the rowmax exchange buffers
+    uint32_t af_cnt[2] = {0u, 0u};                           // completed waits on acc_full[slot]
+    uint32_t lp = 0;                                         // layer parity of the row-exponent exchange buffers
     for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
-      const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && pt == blockIdx.x && (tid & 127) == 0;
+      const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && pt == blockIdx.x && lane == 0 && (warp == 0 || warp == 12);
+      const int tr_role = warp == 0 ? 0 : 1;
       const int64_t row = pt * 128 + r_in;
       const bool row_ok = row < p.P;
       float x[3] = {0.f, 0.f, 0.f};
@@ -245,24 +292,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
           f *= 2.0f;
         }
       }
-      // ---- layer-0 operand: PE(x) -> planes of K slice 0 (half 0 threads) ----
+      // ---- layer-0 operand: PE(x) -> planes of K slice 0 (column quarters 0 and 1 hold its 64 columns) ----
       float sa, inv;
       {
-        if (half == 0) {
-          float mx = 0.f;
+        float mx = 0.f;
+        if (cq < 2) {
 #pragma unroll 1
-          for (int j = 0; j < p.d_pe; ++j) mx = fmaxf(mx, fabsf(pe[j]));
-          ctl->rowmax[lp][0][r_in] = mx;
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(pe[32 * cq + j]));
         }
+        ctl->rowexp[lp][cq][r_in] = (uint8_t)expo_bits(mx);
         epi_bar_sync();
-        row_scale(ctl->rowmax[lp][0][r_in], sa, inv);
+        {
+          const uint32_t e01 = max((uint32_t)ctl->rowexp[lp][0][r_in], (uint32_t)ctl->rowexp[lp][1][r_in]);
+          const uint32_t e23 = max((uint32_t)ctl->rowexp[lp][2][r_in], (uint32_t)ctl->rowexp[lp][3][r_in]);
+          row_scale(max(e01, e23), sa, inv);
+        }
         lp ^= 1;
-        if (half == 0) {
+        if (cq < 2) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < 4; ++g) {
             uint4 p0, p1;
-            slice8(pe + 8 * g, inv, p0, p1);
-            const uint32_t off = sw128((uint32_t)r_in, (uint32_t)(8 * g));
+            slice8(pe + 32 * cq + 8 * g, inv, p0, p1);
+            const uint32_t off = sw128((uint32_t)r_in, (uint32_t)(32 * cq + 8 * g));
             *reinterpret_cast<uint4*>(a_smem + off) = p0;
             *reinterpret_cast<uint4*>(a_smem + CH_APLANE + off) = p1;
           }
@@ -270,155 +321,164 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
           mbar_arrive(&ctl->a_ready[0]);
           if (p.e0 != nullptr && row_ok) {
             float* e = p.e0 + row * p.pe_ld;
-#pragma unroll
-            for (int j = 0; j < CH_MAX_PE; ++j)
+#pragma unroll 1
+            for (int j = 32 * cq; j < 32 * cq + 32; ++j)
               if (j < p.pe_ld) e[j] = pe[j];
           }
         }
       }
       for (int l = 0; l < p.n_layers; ++l) {
         const ChainLayer& L = p.L[l];
-        CH_TR(half, l, 0, clock64());
+        CH_TR(tr_role, l, 0, clock64());
+        const float sl = sa * __ldg(L.wscale);              // z = sl (M + C) + b
         if (!L.last) {
           // ---------------- hidden layer: produce A_{l+1} ----------------
           const int n_next = L.N + L.pe_next;                          // width of the next layer's input
-          const bool active = CH_NT * half < n_next;                   // this half owns columns of the next input
-          const bool has_acc = half < L.n_tiles;
           float rmax = 0.f;
-          if (active) {
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t) {
+            if (CH_NT * t >= n_next) break;
+            const bool has_acc = t < L.n_tiles;
             int rows_t = 0, n_valid = 0;
+            float bl = 0.f;
             if (has_acc) {
-              rows_t = ch_tile_rows(L.N, half);
-              n_valid = L.N - CH_NT * half; n_valid = n_valid < CH_NT ? n_valid : CH_NT;
-              mbar_wait(&ctl->acc_full[half], af_cnt & 1u);
-              ++af_cnt;
+              rows_t = ch_tile_rows(L.N, t);
+              n_valid = L.N - CH_NT * t; n_valid = n_valid < CH_NT ? n_valid : CH_NT;
+              bl = __ldg(L.bias + CH_NT * t + 32 * cq + lane);      // lane j holds the bias of this warp's column j
+              mbar_wait(&ctl->acc_full[t], af_cnt[t] & 1u);
+              ++af_cnt[t];
               tcgen05_fence_after();
             }
-            CH_TR(half, l, 1, clock64());
-            const float srow = sa;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              float v[32];
-              const bool from_acc = 32 * c < rows_t;
-              if (from_acc) {
-                float cc[32];
-                tmem_ld32(t_m + (uint32_t)(32 * c), v);
-                tmem_ld32(t_m + 128u + (uint32_t)(32 * c), cc);
+            if (t == 0) CH_TR(tr_role, l, 1, clock64());
+            const uint32_t t_m = t_lane + (uint32_t)t * 256u;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += cc[j];
+            for (int sub = 0; sub < 2; ++sub) {
+              const int c0 = 32 * cq + 16 * sub;                     // column inside the tile
+              float v[16];
+              if (c0 < rows_t) {
+                float cc[16];
+                tmem_ld16x2(t_m + (uint32_t)c0, t_m + 128u + (uint32_t)c0, v, cc);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += cc[j];
               }
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int lc = 32 * c + j, col = CH_NT * half + lc;
+              for (int j = 0; j < 16; ++j) {
+                const int lc = c0 + j, col = CH_NT * t + lc;
+                const float b = __shfl_sync(0xffffffffu, bl, 16 * sub + j);
                 float a = 0.f;
-                if (lc < n_valid) {
-                  const float2 sb = __ldg(&L.sb[col]);
-                  a = softplus100(fmaf(v[j], srow * sb.x, sb.y)) * L.post_scale;
-                } else if (col >= L.N && col < n_next) {
-                  a = pe[col - L.N] * L.post_scale;
-                }
+                if (lc < n_valid) a = softplus100_fast(fmaf(v[j], sl, b)) * L.post_scale;
+                else if (col >= L.N && col < n_next) a = pe[col - L.N] * L.post_scale;
                 v[j] = a;
                 rmax = fmaxf(rmax, fabsf(a));
               }
-              tmem_st32(t_m + (uint32_t)(32 * c), v);
+              tmem_st16(t_m + (uint32_t)c0, v);
               if (L.out != nullptr && row_ok) {
-                float* o = L.out + row * L.ld_out + CH_NT * half + 32 * c;
-                const int nv = n_next - (CH_NT * half + 32 * c);
-                if (nv >= 32 && (L.ld_out & 3) == 0) {
+                float* o = L.out + row * L.ld_out + CH_NT * t + c0;
+                const int nv = n_next - (CH_NT * t + c0);
+                if (nv >= 16 && (L.ld_out & 3) == 0) {
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                  for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j)
+                  for (int j = 0; j < 16; ++j)
                     if (j < nv) o[j] = v[j];
                 }
               }
             }
-            tmem_wait_st();
           }
-          ctl->rowmax[lp][half][r_in] = rmax;
-          CH_TR(half, l, 2, clock64());
+          tmem_wait_st();
+          ctl->rowexp[lp][cq][r_in] = (uint8_t)expo_bits(rmax);
+          CH_TR(tr_role, l, 2, clock64());
           epi_bar_sync();                                    // all MMAs of this layer are complete, all row maxima are in
-          CH_TR(half, l, 3, clock64());
-          row_scale(fmaxf(ctl->rowmax[lp][0][r_in], ctl->rowmax[lp][1][r_in]), sa, inv);
+          CH_TR(tr_role, l, 3, clock64());
+          {
+            const uint32_t e01 = max((uint32_t)ctl->rowexp[lp][0][r_in], (uint32_t)ctl->rowexp[lp][1][r_in]);
+            const uint32_t e23 = max((uint32_t)ctl->rowexp[lp][2][r_in], (uint32_t)ctl->rowexp[lp][3][r_in]);
+            row_scale(max(e01, e23), sa, inv);
+          }
           lp ^= 1;
-          if (active) {
-            const int nks_next = pad64(n_next) / 64;
+          const int nks_next = pad64(n_next) / 64;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              const int s = 2 * half + (c >> 1);
-              if (s >= nks_next) break;
-              float v[32];
-              tmem_ld32(t_m + (uint32_t)(32 * c), v);
-              uint8_t* sl = a_smem + (size_t)s * 2 * CH_APLANE;
+          for (int t = 0; t < 2; ++t) {
+            if (CH_NT * t >= n_next) break;
+            const int s = 2 * t + (cq >> 1);                 // K slice of the next layer this warp's columns belong to
+            const uint32_t t_m = t_lane + (uint32_t)t * 256u;
+            if (s < nks_next) {
+              uint8_t* sl_base = a_smem + (size_t)s * 2 * CH_APLANE;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 p0, p1;
-                slice8(v + 8 * g, inv, p0, p1);
-                const uint32_t off = sw128((uint32_t)r_in, (uint32_t)((c & 1) * 32 + 8 * g));
-                *reinterpret_cast<uint4*>(sl + off) = p0;
-                *reinterpret_cast<uint4*>(sl + CH_APLANE + off) = p1;
+              for (int sub = 0; sub < 2; ++sub) {
+                float v[16];
+                tmem_ld16(t_m + (uint32_t)(32 * cq + 16 * sub), v);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                  uint4 p0, p1;
+                  slice8(v + 8 * g, inv, p0, p1);
+                  const uint32_t off = sw128((uint32_t)r_in, (uint32_t)((cq & 1) * 32 + 16 * sub + 8 * g));
+                  *reinterpret_cast<uint4*>(sl_base + off) = p0;
+                  *reinterpret_cast<uint4*>(sl_base + CH_APLANE + off) = p1;
+                }
               }
-              if ((c & 1) == 1) {
-                fence_proxy_async();
-                mbar_arrive(&ctl->a_ready[s]);
-              }
+              fence_proxy_async();
+              mbar_arrive(&ctl->a_ready[s]);
             }
-            if (has_acc) {
+            if (t < L.n_tiles) {
               tcgen05_fence_before();
-              mbar_arrive(&ctl->acc_empty[half]);
+              mbar_arrive(&ctl->acc_empty[t]);
             }
           }
-          CH_TR(half, l, 4, clock64());
+          CH_TR(tr_role, l, 4, clock64());
         } else {
-          // ---------------- last layer: plain output, tile t handled by half t & 1 ----------------
-          for (int t = half; t < L.n_tiles; t += 2) {
-            const int rows_t = ch_tile_rows(L.N, t);
-            mbar_wait(&ctl->acc_full[half], af_cnt & 1u);
-            ++af_cnt;
-            tcgen05_fence_after();
+          // ---------------- last layer: plain output ----------------
 #pragma unroll 1
-            for (int c = 0; 32 * c < rows_t; ++c) {
-              float v[32], cc[32];
-              tmem_ld32(t_m + (uint32_t)(32 * c), v);
-              tmem_ld32(t_m + 128u + (uint32_t)(32 * c), cc);
-              const int col0 = CH_NT * t + 32 * c;
+          for (int t = 0; t < L.n_tiles; ++t) {
+            const int slot = t & 1;
+            const int rows_t = ch_tile_rows(L.N, t);
+            const float bl = __ldg(L.bias + CH_NT * t + 32 * cq + lane);
+            mbar_wait(&ctl->acc_full[slot], af_cnt[slot] & 1u);
+            ++af_cnt[slot];
+            tcgen05_fence_after();
+            const uint32_t t_m = t_lane + (uint32_t)slot * 256u;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int col = col0 + j;
-                float z = 0.f;
-                if (col < L.N) {
-                  const float2 sb = __ldg(&L.sb[col]);
-                  z = fmaf(v[j] + cc[j], sa * sb.x, sb.y);
+            for (int sub = 0; sub < 2; ++sub) {
+              const int c0 = 32 * cq + 16 * sub;
+              if (c0 < rows_t) {
+                float v[16], cc[16];
+                tmem_ld16x2(t_m + (uint32_t)c0, t_m + 128u + (uint32_t)c0, v, cc);
+                const int col0 = CH_NT * t + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float b = __shfl_sync(0xffffffffu, bl, 16 * sub + j);
+                  v[j] = (col0 + j < L.N) ? fmaf(v[j] + cc[j], sl, b) : 0.f;
                 }
-                v[j] = z;
-              }
-              if (row_ok) {
-                if (L.out != nullptr) {
-                  float* o = L.out + row * L.ld_out + col0;
-                  const int nv = L.N - col0;
-                  if (nv >= 32 && (L.ld_out & 3) == 0) {
+                if (row_ok) {
+                  if (L.out != nullptr) {
+                    float* o = L.out + row * L.ld_out + col0;
+                    const int nv = L.N - col0;
+                    if (nv >= 16 && (L.ld_out & 3) == 0) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                  } else {
+                      for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                      if (j < nv) o[j] = v[j];
+                      for (int j = 0; j < 16; ++j)
+                        if (j < nv) o[j] = v[j];
+                    }
                   }
+                  if (p.udf_out != nullptr && col0 == 0) p.udf_out[row] = fabsf(v[0]) * p.inv_scale;
                 }
-                if (p.udf_out != nullptr && col0 == 0) p.udf_out[row] = fabsf(v[0]) * p.inv_scale;
+              } else {
+                // keep the warp-collective shuffles of the other branch matched: nothing to do
               }
             }
             tcgen05_fence_before();
-            mbar_arrive(&ctl->acc_empty[half]);
+            mbar_arrive(&ctl->acc_empty[slot]);
           }
-          CH_TR(half, l, 4, clock64());
+          CH_TR(tr_role, l, 4, clock64());
         }
       }
-      epi_bar_sync();     // every MMA of this point tile has completed (the owner of the last N tile waited for it): the A
-                          // planes may be overwritten by the next point tile's layer-0 operand
+      epi_bar_sync();     // every MMA of this point tile has completed (all warps waited for the last N tile): the A planes
+                          // may be overwritten by the next point tile's layer-0 operand
     }
-  } else if (warp == 8) {
+  } else if (warp == CH_MMA_WARP) {
     // =========================================== MMA issuer ===========================================
     if (lane == 0) {
       uint32_t wcnt = 0, ae_cnt[2] = {0u, 0u}, ar_cnt[CH_MAX_SLICES] = {0u, 0u, 0u, 0u};
@@ -495,7 +555,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == CH_MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

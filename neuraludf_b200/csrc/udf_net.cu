@@ -17,7 +17,7 @@ struct UdfPlan {
   int64_t b_off[NUDF_MAX_LAYERS], b_total;
   int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_nt3[NUDF_MAX_LAYERS], img_nn1, img_total;   // uint16 offsets of the bf16 hi/lo weight images
   int64_t img_chain[NUDF_MAX_LAYERS];   // uint16 offsets of the fused value chain's fp16 slice images (udf_chain.cuh)
-  int64_t sb_off[NUDF_MAX_LAYERS], sb_total;   // float offsets (after the images) of the chain's per-column (scale, bias) tables
+  int64_t sb_off[NUDF_MAX_LAYERS], sb_total;   // float offsets (after the images) of the chain's per-layer [scale meta (4) | bias table]
   int chain_ok;                         // the fused value chain supports this network shape
   int pe_ld, y_ld;
   int a_ld[NUDF_MAX_LAYERS];    // ld of A[l] (input of layer l), l >= 1
@@ -62,7 +62,7 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
   for (int l = 0; l < p->n_lin; ++l) { p->img_chain[l] = ioff; ioff += chain::ch_layer_elems(p->out_dim[l], p->in_dim[l]); }
   p->img_total = round_up(ioff, 8);
   int64_t soff = 0;
-  for (int l = 0; l < p->n_lin; ++l) { p->sb_off[l] = soff; soff += 2 * (int64_t)chain::CH_NT * chain::ch_n_tiles(p->out_dim[l]); }
+  for (int l = 0; l < p->n_lin; ++l) { p->sb_off[l] = soff; soff += 4 + (int64_t)chain::CH_NT * chain::ch_n_tiles(p->out_dim[l]); }
   p->sb_total = soff;
   // shapes the fused chain handles: PE fits one K slice, every contraction K <= 256, hidden layers <= 2 output tiles
   p->chain_ok = p->d_pe <= chain::CH_MAX_PE;
@@ -386,10 +386,13 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
         return rc;
     if (p.chain_ok) {
       // fused value chain: fp16 slice images + per-column (scale, bias) tables (udf_chain.cuh)
-      float2* sb = reinterpret_cast<float2*>(wfold + p.w_total + p.img_total / 2);
+      float* tab = wfold + p.w_total + p.img_total / 2;     // per layer: [2 floats of scale meta | bias table]
       for (int l = 0; l < p.n_lin; ++l) {
+        float* meta = tab + p.sb_off[l];
+        chain::chain_layer_scale_kernel<<<1, 256, 0, st>>>(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], meta);
+        NUDF_LAUNCH_OK();
         chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.out_dim[l]), 64, 0, st>>>(
-            wfold + p.w_off[l], p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], img + p.img_chain[l], sb + p.sb_off[l] / 2);
+            wfold + p.w_off[l], p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], meta, img + p.img_chain[l], meta + 4);
         NUDF_LAUNCH_OK();
       }
     }
@@ -406,7 +409,7 @@ static inline const uint16_t* img_base(const UdfPlan& p, const float* wfold) {
 static void build_chain(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, float* ctx, const UdfCtx* c, float* udf,
                         chain::ChainParams* cp) {
   const bool value_only = udf != nullptr;
-  const float2* sb = reinterpret_cast<const float2*>(wfold + p.w_total + p.img_total / 2);
+  const float* tab = wfold + p.w_total + p.img_total / 2;
   cp->n_layers = p.n_lin;
   cp->img = img_base(p, wfold);
   cp->pts = pts; cp->P = P; cp->scale = p.scale; cp->n_freq = p.L; cp->d_pe = p.d_pe;
@@ -425,7 +428,8 @@ static void build_chain(const UdfPlan& p, const float* wfold, const float* pts, 
     L.last = last ? 1 : 0;
     L.pe_next = (!last && l + 1 == p.skip) ? p.d_pe : 0;
     L.post_scale = (!last && l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
-    L.sb = sb + p.sb_off[l] / 2;
+    L.wscale = tab + p.sb_off[l] + 1;
+    L.bias = tab + p.sb_off[l] + 4;
     if (value_only) { L.out = nullptr; L.ld_out = 0; }
     else if (last) { L.out = ctx + c->y; L.ld_out = p.y_ld; }
     else { L.out = ctx + c->a[l + 1]; L.ld_out = p.a_ld[l + 1]; }

@@ -221,7 +221,15 @@ def install_stubs():
     tm.smoothing = _mod("trimesh.smoothing")
     _mod("h5py", File=_unavailable("h5py.File"))
     mpl = _mod("matplotlib")
+    mpl.__path__ = []
     mpl.pyplot = _mod("matplotlib.pyplot", figure=_unavailable("matplotlib"), subplots=_unavailable("matplotlib"))
+    def _get_cmap(name=None):
+        def cmapper(value, bytes=False):             # a two-colour ramp standing in for matplotlib's colormaps (validate()'s
+            v = np.clip(np.asarray(value, dtype=np.float64), 0.0, 1.0)     # depth visualisation, exp_runner_blending.py:847-866)
+            rgba = np.stack([v, 0.2 + 0.6 * v, 1.0 - v, np.ones_like(v)], axis=-1)
+            return (rgba * 255).astype(np.uint8) if bytes else rgba
+        return cmapper
+    mpl.cm = _mod("matplotlib.cm", get_cmap=_get_cmap)
     cm = _mod("custom_mc")
     cm.__path__ = []
     cm._marching_cubes_lewiner = _mod("custom_mc._marching_cubes_lewiner", udf_mc_lewiner=_unavailable("custom_mc"))
