@@ -49,8 +49,8 @@ _MAC_F = sum(_UDF_MAC)
 _MAC_R = sum(_UDF_MAC[:8])
 _MAC_B = sum(_UDF_MAC[1:])
 _MAC_COL = 153728
-FAMILY_MAC = {"udf_fwd_chain_fused": _MAC_F, "tc_layer_reverse_sweep": _MAC_R, "tc_layer_tangent": _MAC_R,
-              "tc_layer_backward": _MAC_B, "tc_weight_gradient": _MAC_R + _MAC_F + _MAC_COL}
+FAMILY_MAC = {"udf_fwd_chain_fused": _MAC_F + _MAC_R, "udf_bwd_chain_fused": _MAC_R + _MAC_B, "tc_layer_reverse_sweep": _MAC_R,
+              "tc_layer_tangent": _MAC_R, "tc_layer_backward": _MAC_B, "tc_weight_gradient": _MAC_R + _MAC_F + _MAC_COL}
 
 
 def peaks():
@@ -375,7 +375,7 @@ def run_ours(args):
         # roofline: the kernel family with the largest share of the step's device time
         tens = {k: v for k, v in fam.items() if "algorithmic_tflops" in v}
         dom = max(tens, key=lambda k: tens[k]["share"]) if tens else None
-        kernel_of = {"udf_fwd_chain_fused": "udf_chain_kernel", "tc_layer_reverse_sweep": "gemm_wr_kernel<nudf::EpiRev>",
+        kernel_of = {"udf_fwd_chain_fused": "udf_chain_kernel", "udf_bwd_chain_fused": "udf_chain_kernel", "tc_layer_reverse_sweep": "gemm_wr_kernel<nudf::EpiRev>",
                      "tc_layer_tangent": "gemm_wr_kernel<nudf::EpiTan>", "tc_layer_backward": "gemm_wr_kernel<nudf::EpiBwd>",
                      "tc_weight_gradient": "gemm_tn_kernel"}
         roof = None

@@ -78,7 +78,8 @@ int64_t nudf_launch_count(void);
 /* Per-kernel-family device times for the benchmark's roofline table: while enabled, the library brackets its launches with
  * cudaEvent pairs on the launching stream.  nudf_read_launch_timing synchronises, writes the summed milliseconds and the
  * launch counts per family (host arrays of nudf_launch_family_count() entries; order: fused UDF value chain, tcgen05
- * reverse-sweep / tangent / backward / other layers, tcgen05 weight gradients, fp32 FFMA GEMMs, ray kernels, element-wise)
+ * reverse-sweep / tangent / backward / other layers, tcgen05 weight gradients, fp32 FFMA GEMMs, ray kernels, element-wise,
+ * fused tangent + backward chains)
  * and clears the record. */
 int nudf_launch_family_count(void);
 int nudf_set_launch_timing(int on);

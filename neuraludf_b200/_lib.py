@@ -66,7 +66,7 @@ class RenderBar(ctypes.Structure):
 
 
 LAUNCH_FAMILIES = ["udf_fwd_chain_fused", "tc_layer_reverse_sweep", "tc_layer_tangent", "tc_layer_backward", "tc_layer_other",
-                   "tc_weight_gradient", "ffma_gemm", "ray_kernels", "elementwise"]
+                   "tc_weight_gradient", "ffma_gemm", "ray_kernels", "elementwise", "udf_bwd_chain_fused"]
 
 _lib = None
 

@@ -57,7 +57,7 @@ void count_launch();
 // LaunchTimer is bracketed by a cudaEvent pair recorded on the launching stream; nudf_read_launch_timing() synchronises
 // and sums the pairs per family.  Off by default (zero overhead besides one branch).
 enum LaunchFamily {
-  FAM_UDF_FWD_CHAIN = 0,   // fused UDF value chain (udf_chain.cuh)
+  FAM_UDF_FWD_CHAIN = 0,   // fused UDF value chain (+ reverse sweep when the gradient is requested) (udf_chain.cuh)
   FAM_TC_REV = 1,          // one layer of the reverse sweep (grad_x udf) on tcgen05
   FAM_TC_TAN = 2,          // one layer of the tangent chain
   FAM_TC_BWD = 3,          // one layer of the backward chain
@@ -66,7 +66,8 @@ enum LaunchFamily {
   FAM_FFMA = 6,            // exact-fp32 FFMA GEMMs
   FAM_RAY = 7,             // ray kernels: compositing forward / backward, sampling, blending
   FAM_ELEMENTWISE = 8,     // element-wise kernels of the library (PE, fold / unfold, seeds, column sums)
-  FAM_COUNT = 9
+  FAM_UDF_BWD_CHAIN = 9,   // fused tangent + backward chains (udf_chain.cuh)
+  FAM_COUNT = 10
 };
 bool launch_timing_on();
 int launch_timer_begin(int family, cudaStream_t st);

@@ -1,28 +1,38 @@
-// Fused UDF value chain for sm_100a: ONE persistent kernel walks every layer of UDFNetwork.forward (reference
-// models/fields.py:192-211) for a 128-point tile; the activations never leave the SM between layers.
+// Fused layer chains of UDFNetwork for sm_100a: ONE persistent kernel walks a whole sequence of dense layers for a 128-point
+// tile; the chain-carried activations never leave the SM between layers.  Four chains of the network run this way
+// (reference models/fields.py:192-231 and their autograd adjoints; maths: tests/proto/udf_pipeline.py):
 //
-//   pts --PE--> A_0 --[W_0]--> softplus --> A_1 --[W_1]--> ... --[W_last]--> y          (one CTA per SM, tiles of 128 points)
+//   F  value chain          pts --PE--> A_0 --[W_0]--> softplus --> A_1 ... --[W_last]--> y            (:192-211)
+//   R  reverse sweep        seed (sgn/scale) W_last[0,:] --> D_l = G_{l+1} s(100 z_l),  G_l = D_l W_l   (exact grad_x udf, :219-231)
+//   T  tangent chain        Adot_0 = J_e gbar,  Zdot_l = Adot_l W_l^T,  Q_l = Zdot D_l 100 (1 - S_l),  Adot_{l+1} = S_l Zdot_l
+//   B  backward chain       Zbar_{l-1} = (Zbar_l W_l) S_{l-1} + Q_{l-1}
+//
+// F and R are chained in one launch per forward call (the activations R needs were written a few microseconds earlier by
+// the same CTA and come back from L2), T and B in one launch per backward call.  Every chain-local tensor that another
+// kernel consumes later (saved activations, D, Q / Zbar, Adot for the weight-gradient contractions) is written once, in
+// fp32, by the thread that owns the row.
 //
 // * every layer is a tcgen05.mma contraction (M = 128 points, N <= 128 per output tile, K = 16 per instruction, fp32
-//   accumulators in TMEM); the epilogue warps read the accumulator with tcgen05.ld, apply bias + softplus(beta = 100), and
-//   write the NEXT layer's A operand straight into shared memory in the UMMA K-major SWIZZLE_128B layout -- no HBM round trip
-//   and no LSU operand path.  Weight slices stream from L2 through a cp.async.bulk (TMA engine) ring.
+//   accumulators in TMEM); the epilogue warps read the accumulator with tcgen05.ld, apply the element-wise part of the layer
+//   and write the NEXT layer's A operand straight into shared memory in the UMMA K-major SWIZZLE_128B layout -- no HBM round
+//   trip and no LSU operand path for the chain itself.  Weight slices stream from L2 through a cp.async.bulk (TMA) ring.
 // * fp32-grade accuracy on the tensor engine (the udf head feeds exp(-25000 u): SURVEY.md section 0, fact 3) comes from an
 //   EXACT-MAIN fp16 slice scheme instead of the truncating 3xBF16 split:
-//       activation row r :  a = 2^(ea_r - 11) (a0 + a1),  a0 = rint(a 2^(11 - ea_r)) in [-2048, 2048] (12-bit integer, exact in
-//                           fp16), a1 = fp16(remainder) in [-1/2, 1/2];   2^ea_r > max_k |a_rk|  (per-row power of two)
-//       weight row n     :  w = 2^(ew_n - 13) (w0 + w1 + w2),  w0 = 1024 rint(w 2^(3 - ew_n)) (4-bit integer x 2^10),
-//                           w1 = fp16(1024 remainder), w2 = fp16(second remainder)
+//       operand row r  :  a = 2^(ea_r - 11) (a0 + a1),  a0 = rint(a 2^(11 - ea_r)) in [-2048, 2048] (12-bit integer, exact in
+//                         fp16), a1 = fp16(remainder) in [-1/2, 1/2];   2^ea_r > max_k |a_rk|  (per-row power of two)
+//       weights, layer :  w = 2^(E - 13) (w0 + w1 + w2),  w0 = 1024 rint(w 2^(3 - E)) (<= 4-bit integer x 2^10),
+//                         w1 = fp16(1024 remainder), w2 = fp16(second remainder);  2^E > max |w| of the layer
 //   Main accumulator  M = sum_k a0 w0: every product is an integer multiple of 2^10 below 2^24 and the 256-term sum stays below
 //   2^22 units, so the tensor core's truncating fp32 accumulation is EXACT.  Correction accumulator
-//   C = sum_k a0 w1 + a0 w2 + a1 w0 + a1 w1 is ~2^-3 of M, so its truncation error is ~2^-27 of the result.  z = 2^(ea_r +
-//   ew_n - 24) (M + C) + b in fp32.  Dropped terms: a1 w2 (2^-24).  5 tensor products per K step; 2 fp16 planes of A (128 KB of
-//   shared memory for a [128 x 256] tile) + a 2-slot ring of 3-plane weight slices (2 x 48 KB).
-// * roles: warps 0-7 epilogue (warp w: TMEM lane quadrant w & 3 = tile rows 32 (w & 3).., output-column half w >> 2 = N tile
-//   w >> 2), warp 8 MMA issuer + TMEM owner, warp 9 weight-ring loader.  The two N tiles of a layer have their own
-//   accumulator pairs (M0 C0 M1 C1 = 512 TMEM columns), so the epilogue of tile 0 overlaps the MMAs of tile 1.
-//   Per-row scales need the row maximum over all 256 columns: pass 1 (activation, partial row max, value written back to
-//   TMEM over M), exchange through shared memory, pass 2 (slicing into the A planes).
+//   C = sum_k a0 w1 + a0 w2 + a1 w0 + a1 w1 is ~2^-3 of M, so its truncation error is ~2^-27 of the result.
+//   z = 2^(ea_r + E - 24) (M + C) (+ b) in fp32.  Dropped: a1 w2 (2^-24).  5 tensor products per K step; 2 fp16 planes of A
+//   (128 KB of shared memory for a [128 x 256] tile) + a 2-slot ring of 3-plane weight slices (2 x 48 KB).
+//   Measured: udf head error 3.7e-7 vs 1.2e-6 for the reference's own fp32 run (tests/test_gpu_chain.py).
+// * roles: warps 0-15 epilogue (warp w: TMEM lane quadrant w & 3 = tile rows 32 (w & 3).., column quarter w >> 2 = columns
+//   [32 cq, 32 cq + 32) of EVERY N tile), warp 16 MMA issuer + TMEM owner, warp 17 weight-ring loader.  The two N tiles of a
+//   layer have their own accumulator pairs (M0 C0 M1 C1 = 512 TMEM columns), so the epilogue of tile 0 overlaps the MMAs of
+//   tile 1.  Per-row scales need the row maximum over all columns: pass 1 (element-wise part, partial row max, value written
+//   back to TMEM over M), exchange of the exponent bytes through shared memory, pass 2 (slicing into the A planes).
 #pragma once
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -45,43 +55,57 @@ constexpr int CH_EPI_WARPS = 16;
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;           // 512
 constexpr int CH_MMA_WARP = 16, CH_LOAD_WARP = 17;
 constexpr int CH_THREADS = 576;
-constexpr int CH_MAX_STAGES = 112;
+constexpr int CH_MAX_STEPS = 24;
 constexpr int CH_MAX_PE = 64;                               // positional-encoding width (K of layer 0) <= one K slice
 
-struct ChainLayer {
-  int K, N;                  // logical contraction / output widths
-  int n_kslices, n_tiles;
-  int stage0;                // first weight stage of this layer in ChainParams::S
-  int last;                  // 1: last layer (plain output, no activation)
-  int pe_next;               // PE columns appended to the next layer's input (skip layer), else 0
-  float post_scale;          // 1/sqrt(2) when the next layer is the skip layer
-  const float* bias;         // [128 n_tiles], zero for padded columns
-  const float* wscale;       // DEVICE scalar 2^(E_l - 13): weights of this layer are 2^(E_l - 13) (w0 + w1 + w2)
-  float* out;                // hidden: A[l+1] [P, ld_out] or null; last: Y [P, ld_out] or null
-  int64_t ld_out;
+// what the epilogue does with the accumulator of a step (or, for steps without a GEMM, how the next operand is made)
+enum StepKind {
+  ST_PE = 0,         // no GEMM: next = PE(x)                          out0 = E0
+  ST_FWD = 1,        // a = softplus100(z + b) post                    out0 = A[l+1]        next = a (| PE columns at the skip layer)
+  ST_FWD_LAST = 2,   // y = z + b                                      out0 = Y, udf_out    (records sign(y_0) for a following R chain)
+  ST_REV_SEED = 3,   // no GEMM: g = (sgn/scale) W_last[0, c] post     as ST_REV
+  ST_REV = 4,        // g = z post; c < n_main: d = g s(in0)           out0 = D[l-1]        next = d;   c >= n_main: out1 (Gpe) = g
+  ST_REV_FINAL = 5,  // ge = z + in1 (Gpe)                             out0 = Ge
+  ST_EDOT = 6,       // no GEMM: next = scale J_e(x) gbar              out0 = Edot
+  ST_TAN = 7,        // q = z in1 (D) 100 (1 - S), n = S z post        out0 = Q[l], out1 = Adot[l+1]   next = n (| Edot columns at the skip layer)
+  ST_LOAD = 8,       // no GEMM: next = in0 (zf)
+  ST_BWD = 9,        // ab = z (+ rowv vec0[c]); c < n_main: zb = ab post s(in0) + in1 (Q)    out0 = Zbar[l-1]    next = zb
 };
-struct ChainStage {
-  uint32_t src;              // uint16-element offset of plane 0 of this (layer, N tile, K slice) in the chain image
-  uint16_t rows;             // rows to fetch / N of the MMA (multiple of 16)
-  uint16_t plane_rows;       // rows of the full tile in the image (plane stride = plane_rows * 64 elements)
+
+struct ChainStep {
+  int kind;
+  int K, N;                  // GEMM: logical contraction / output widths (N = 0: no GEMM in this step)
+  int n_kslices, n_tiles;    // of the GEMM
+  int rows_override;         // > 0: fetch / multiply only this many weight rows of tile 0 (value-only last layer)
+  int n_main;                // REV / BWD: output columns that continue the chain
+  int n_next;                // width of the operand this step produces for the next GEMM (0: none)
+  int sync_before;           // 1: the step starts with a barrier of the epilogue warps (reads state other threads wrote)
+  float post_scale, a_unscale;
+  uint32_t img_off;          // uint16-element offset of this GEMM's weight image in ChainParams::img
+  const float* bias;         // [128 n_tiles] or null
+  const float* wscale;       // DEVICE scalar 2^(E - 13) of the weight image
+  const float* in0; const float* in1;          // auxiliary inputs  [P, ld]
+  float* out0; float* out1;                    // outputs           [P, ld]
+  const float* vec0;         // per-column vector (REV_SEED: W_last[0,:], BWD first step: W_last[0,:])
+  const float* rowv;         // per-row vector (BWD first step: z0 [P]) or null
+  int ld_in0, ld_in1, ld_out0, ld_out1;
 };
 struct ChainParams {
-  int n_layers, n_stages;
-  ChainLayer L[NUDF_MAX_LAYERS];
-  ChainStage S[CH_MAX_STAGES];
+  int n_steps;
+  ChainStep S[CH_MAX_STEPS];
   const uint16_t* img;
   const float* pts; int64_t P; float scale; int n_freq, d_pe;
-  float* e0; int pe_ld;                  // PE(x) [P, pe_ld] or null
+  const float* gbar;                     // T chain: upstream gradient of grad_x udf [P,3]
   float* udf_out; float inv_scale;       // value-only mode: udf_out[P] = |y_0| / scale
-  long long* trace;                      // profiling aid (NUDF_CHAIN_TRACE=1): clock64() stamps of CTA 0, first point tile
+  long long* trace;                      // profiling aid (NUDF_CHAIN_TRACE=n): clock64() stamps of CTA 0, first point tile
 };
-// trace layout: [role 0 = epilogue warp 0, 1 = epilogue warp 12, 2 = MMA issuer][layer][8]
-constexpr int CH_TRACE_WORDS = 4 * NUDF_MAX_LAYERS * 8;
-#define CH_TR(role, l, k, v) do { if (tr_on) p.trace[((role) * NUDF_MAX_LAYERS + (l)) * 8 + (k)] = (v); } while (0)
+// trace layout: [role 0 = epilogue warp 0, 1 = epilogue warp 12, 2 = MMA issuer][step][8]
+constexpr int CH_TRACE_WORDS = 3 * CH_MAX_STEPS * 8;
+#define CH_TR(role, l, k, v) do { if (tr_on) p.trace[((role) * CH_MAX_STEPS + (l)) * 8 + (k)] = (v); } while (0)
 
 __host__ __device__ inline int ch_tile_rows(int N, int t) { int r = N - CH_NT * t; return pad16(r < CH_NT ? r : CH_NT); }
 __host__ __device__ inline int ch_n_tiles(int N) { return (N + CH_NT - 1) / CH_NT; }
-// uint16 elements of the chain image of one layer: [tile][k slice][plane][rows_t x 64]
+// uint16 elements of the chain image of one GEMM: [tile][k slice][plane][rows_t x 64]
 __host__ __device__ inline int64_t ch_layer_elems(int N, int K) {
   int64_t e = 0;
   for (int t = 0; t < ch_n_tiles(N); ++t) e += (int64_t)ch_tile_rows(N, t) * pad64(K) * CH_WPL;
@@ -97,9 +121,9 @@ __host__ __device__ inline int64_t ch_tile_off(int N, int K, int t) {
 // meta[0] = 2^(3 - E), meta[1] = 2^(E - 13) with 2^E > max |W| over the whole layer (one power of two per LAYER: the integer
 // slice w0 then has up to 4 bits for the largest weights and fewer for small rows, whose precision lives in the floating
 // fp16 remainders w1, w2 -- 22 more bits relative to each element)
-static __global__ void chain_layer_scale_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, float* __restrict__ meta) {
+static __global__ void chain_layer_scale_kernel(const float* __restrict__ W, int64_t ldw, int rows, int cols, float* __restrict__ meta) {
   float mx = 0.f;
-  for (int64_t i = threadIdx.x; i < (int64_t)N * K; i += blockDim.x) mx = fmaxf(mx, fabsf(W[(i / K) * ldw + (i % K)]));
+  for (int64_t i = threadIdx.x; i < (int64_t)rows * cols; i += blockDim.x) mx = fmaxf(mx, fabsf(W[(i / cols) * ldw + (i % cols)]));
   __shared__ float red[32];
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -112,20 +136,23 @@ static __global__ void chain_layer_scale_kernel(const float* __restrict__ W, int
     meta[1] = __uint_as_float((uint32_t)(e - 13 + 127) << 23);
   }
 }
-// one block per padded output row; W row-major [N, ldw]
+// one block per padded operand row n of B(n, k), n < N, k < K.  transposed == 0: B(n,k) = W[n*ldw + k] (X W^T);
+// transposed == 1: B(n,k) = W[k*ldw + n] (dY W).  bias_tab (optional): [128 n_tiles] copy of bias, zero padded.
 static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int N, int K,
-                                         const float* __restrict__ meta, uint16_t* __restrict__ img, float* __restrict__ bias_tab) {
+                                         int transposed, const float* __restrict__ meta, uint16_t* __restrict__ img,
+                                         float* __restrict__ bias_tab) {
   const int col = blockIdx.x;                    // padded output column: 128 t + local row
   const int t = col / CH_NT, nl = col - t * CH_NT;
   const int rows_t = ch_tile_rows(N, t);
   const bool valid = col < N;
-  if (threadIdx.x == 0) bias_tab[col] = (valid && bias) ? bias[col] : 0.f;
+  if (threadIdx.x == 0 && bias_tab != nullptr) bias_tab[col] = (valid && bias) ? bias[col] : 0.f;
   if (nl >= rows_t) return;                      // beyond the padded tile: only the bias table entry exists
   const int Kp = pad64(K);
   const float up = meta[0];                      // 2^(3 - E): scaled weights are in (-8, 8)
   uint16_t* base = img + ch_tile_off(N, K, t);
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-    float w = (valid && k < K) ? W[(int64_t)col * ldw + k] * up : 0.f;
+    float w = 0.f;
+    if (valid && k < K) w = (transposed ? W[(int64_t)k * ldw + col] : W[(int64_t)col * ldw + k]) * up;
     const float w0 = rintf(w);
     const float r1 = (w - w0) * 1024.0f;
     const __half h1 = __float2half_rn(r1);
@@ -183,6 +210,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// elect.sync: one lane of a converged warp.  The MMA warp runs its issue loop with warp-uniform control flow and issues inside
+// `if (elect_one())`: ptxas then keeps the descriptor arithmetic on the uniform datapath (UIADD3 / UMOV between consecutive
+// UTCHMMAs) instead of the R2UR round trips a `lane == 0` loop needs (~90 cycles per 64-cycle MMA in the first version).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -205,7 +247,7 @@ __device__ __forceinline__ void row_scale(uint32_t E, float& sa, float& inv) {
   sa = __uint_as_float((uint32_t)(e - 11 + 127) << 23);
   inv = __uint_as_float((uint32_t)(11 - e + 127) << 23);
 }
-// 8 consecutive activations -> 16 bytes of plane 0 (integer part) and plane 1 (remainder), fp16
+// 8 consecutive values -> 16 bytes of plane 0 (integer part) and plane 1 (remainder), fp16
 __device__ __forceinline__ void slice8(const float* a, float inv, uint4& p0, uint4& p1) {
   uint32_t o0[4], o1[4];
 #pragma unroll
@@ -220,6 +262,32 @@ __device__ __forceinline__ void slice8(const float* a, float inv, uint4& p0, uin
   p0 = make_uint4(o0[0], o0[1], o0[2], o0[3]);
   p1 = make_uint4(o1[0], o1[1], o1[2], o1[3]);
 }
+// 16 consecutive floats of one row of a [P, ld] tensor (columns c .. c+15, `nv` of them valid); 16-byte accesses when aligned.
+// Plain (coherent) loads: tensors written earlier by this very kernel are read here (F -> R, T -> B hand-offs).
+__device__ __forceinline__ void ld_row16(const float* base, int64_t ld, int64_t row, int c, int nv, float v[16]) {
+  const float* q = base + row * ld + c;
+  if (nv >= 16 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = reinterpret_cast<const float4*>(q)[i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = j < nv ? q[j] : 0.f;
+  }
+}
+__device__ __forceinline__ void st_row16(float* base, int64_t ld, int64_t row, int c, int nv, const float v[16]) {
+  float* q = base + row * ld + c;
+  if (nv >= 16 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nv) q[j] = v[j];
+  }
+}
 
 struct ChainCtl {
   uint64_t w_full[CH_NSLOT], w_empty[CH_NSLOT];
@@ -227,13 +295,146 @@ struct ChainCtl {
   uint64_t a_ready[CH_MAX_SLICES];
   uint32_t tmem_addr;
   uint32_t pad_;
-  uint8_t rowexp[2][4][128];    // [layer parity][column quarter][row]: exponent field of the partial row maximum
+  uint8_t rowexp[2][4][128];    // [step parity][column quarter][row]: exponent field of the partial row maximum
+  float rowsgn[128];            // sign(y_0) / scale of the last F layer, for the seed of a following R chain
 };
-// 128 KB of A planes + 2 x 48 KB weight slots + control block = 225.1 KB of the 227 KB a CTA may have: no room for an alignment
+// 128 KB of A planes + 2 x 48 KB weight slots + control block = 225.6 KB of the 227 KB a CTA may have: no room for an alignment
 // slack, so the dynamic shared-memory window itself is declared 1024-byte aligned (SWIZZLE_128B operands need it) and the
 // kernel traps if the runtime did not honour that.
 constexpr size_t CH_SMEM_BYTES = (size_t)CH_A_BYTES + (size_t)CH_NSLOT * CH_WSLOT + sizeof(ChainCtl);
 static_assert(CH_SMEM_BYTES <= 227 * 1024, "fused chain: shared-memory budget exceeded");
+
+// One 16-column group of one row: element-wise part of a step.  `z` = accumulator values already scaled (sl (M + C)), zeros for
+// steps without a GEMM.  Writes the value that continues the chain into nx[] (0 where nothing continues) and performs the
+// step's global stores when `do_store`.  col0 = first logical output column of the group.
+__device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams& p, int64_t row, bool row_ok, int col0,
+                                           const float* z, const float* bv, const float* pe, float sgn_scaled, bool do_store,
+                                           float nx[16]) {
+  const int kind = S.kind;
+  if (kind == ST_PE || kind == ST_EDOT) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.n_next) ? pe[col0 + j] : 0.f;
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.ld_out0) st_row16(S.out0, S.ld_out0, row, col0, S.ld_out0 - col0, nx);
+    return;
+  }
+  if (kind == ST_LOAD) {
+    if (row_ok && col0 < S.n_next) ld_row16(S.in0, S.ld_in0, row, col0, S.n_next - col0, nx);
+    else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) nx[j] = 0.f;
+    }
+    return;
+  }
+  if (kind == ST_FWD) {
+    const int n_valid = S.N;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      float a = 0.f;
+      if (col < n_valid) a = softplus100_fast(z[j] + bv[j]) * S.post_scale;
+      else if (col < S.n_next) a = pe[col - n_valid] * S.post_scale;
+      nx[j] = a;
+    }
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_next) st_row16(S.out0, S.ld_out0, row, col0, S.n_next - col0, nx);
+    return;
+  }
+  if (kind == ST_FWD_LAST) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.N) ? z[j] + bv[j] : 0.f;
+    if (do_store && row_ok) {
+      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, nx);
+      if (p.udf_out != nullptr && col0 == 0) p.udf_out[row] = fabsf(nx[0]) * p.inv_scale;
+    }
+    return;
+  }
+  if (kind == ST_REV_FINAL) {
+    float g[16];
+    if (S.in1 != nullptr && row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, g);
+    else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) g[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.N) ? z[j] + g[j] : 0.f;
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, nx);
+    return;
+  }
+  // the remaining kinds recover S = sigma(100 z_prev) from the stored softplus output in0 (= A of the right layer)
+  float a[16];
+  const int n_act = (kind == ST_TAN) ? S.N : S.n_main;           // columns that have an activation behind them
+  if (row_ok && col0 < n_act) ld_row16(S.in0, S.ld_in0, row, col0, n_act - col0, a);
+  else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = 0.f;
+  }
+  if (kind == ST_REV || kind == ST_REV_SEED) {
+    float gp[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      float raw = z[j];
+      if (kind == ST_REV_SEED) raw = (col < S.n_main) ? sgn_scaled * __ldg(S.vec0 + col) : 0.f;
+      gp[j] = raw * S.post_scale;
+      nx[j] = (col < S.n_main) ? gp[j] * sig_from_softplus(a[j] * S.a_unscale) : 0.f;
+    }
+    if (do_store && row_ok) {
+      if (S.out0 != nullptr && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, nx);
+      if (S.out1 != nullptr && kind == ST_REV && col0 + 16 > S.n_main && col0 < S.N) {       // skip layer: columns >= n_main go to Gpe
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          if (col >= S.n_main && col < S.N) S.out1[row * S.ld_out1 + (col - S.n_main)] = gp[j];
+        }
+      }
+    }
+    return;
+  }
+  if (kind == ST_TAN) {
+    float d[16], q[16];
+    if (row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, d);
+    else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) d[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      float n = 0.f;
+      q[j] = 0.f;
+      if (col < S.N) {
+        const float s = sig_from_softplus(a[j] * S.a_unscale);
+        q[j] = z[j] * d[j] * (100.0f * (1.0f - s));
+        n = s * z[j] * S.post_scale;
+      } else if (col < S.n_main) {                   // n_main = width of Adot[l+1] (Edot columns appended at the skip layer)
+        n = pe[col - S.N] * S.post_scale;
+      }
+      nx[j] = n;
+    }
+    if (do_store && row_ok) {
+      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, q);
+      if (S.out1 != nullptr && col0 < S.n_main) st_row16(S.out1, S.ld_out1, row, col0, S.n_main - col0, nx);
+    }
+    return;
+  }
+  // ST_BWD
+  {
+    float q[16];
+    if (row_ok && col0 < S.n_main) ld_row16(S.in1, S.ld_in1, row, col0, S.n_main - col0, q);
+    else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) q[j] = 0.f;
+    }
+    const float rz = (S.rowv != nullptr && row_ok) ? S.rowv[row] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      float ab = z[j];
+      if (S.rowv != nullptr && col < S.n_main) ab = fmaf(rz, __ldg(S.vec0 + col), ab);
+      nx[j] = (col < S.n_main) ? ab * S.post_scale * sig_from_softplus(a[j] * S.a_unscale) + q[j] : 0.f;
+    }
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, nx);
+  }
+}
 
 __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -259,13 +460,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
 
   if (warp < CH_EPI_WARPS) {
     // =========================================== epilogue warps ===========================================
-    // warp w: TMEM lane quadrant w & 3 (tile rows 32 (w & 3) ..), column quarter cq = w >> 2: columns [32 cq, 32 cq + 32) of
-    // EVERY N tile, so all 16 warps work on tile 0 while the tensor core is still busy with tile 1.
     const int quad = warp & 3, cq = warp >> 2;
     const int r_in = quad * 32 + lane;                       // row of the tile = TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t af_cnt[2] = {0u, 0u};                           // completed waits on acc_full[slot]
-    uint32_t lp = 0;                                         // layer parity of the row-exponent exchange buffers
+    uint32_t lp = 0;                                         // parity of the row-exponent exchange buffers
     for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
       const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && pt == blockIdx.x && lane == 0 && (warp == 0 || warp == 12);
       const int tr_role = warp == 0 ? 0 : 1;
@@ -273,12 +472,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
       const bool row_ok = row < p.P;
       float x[3] = {0.f, 0.f, 0.f};
       if (row_ok) { x[0] = p.pts[row * 3 + 0] * p.scale; x[1] = p.pts[row * 3 + 1] * p.scale; x[2] = p.pts[row * 3 + 2] * p.scale; }
-      // PE(x) of this thread's row (models/embedder.py:22-36): [x | sin(2^q x) | cos(2^q x)]_q; kept for the skip layer
+      // per-row local vector: PE(x) (models/embedder.py:22-36) for the F chain, Edot = scale J_e(x) gbar for the T chain
       float pe[CH_MAX_PE];
 #pragma unroll
       for (int j = 0; j < CH_MAX_PE; ++j) pe[j] = 0.f;
-      pe[0] = x[0]; pe[1] = x[1]; pe[2] = x[2];
-      {
+      if (p.S[0].kind == ST_PE || p.S[0].kind == ST_EDOT) {
+        const bool jvp = p.S[0].kind == ST_EDOT;
+        float v[3] = {1.f, 1.f, 1.f};
+        if (jvp) {
+          v[0] = v[1] = v[2] = 0.f;
+          if (row_ok) { v[0] = p.gbar[row * 3 + 0] * p.scale; v[1] = p.gbar[row * 3 + 1] * p.scale; v[2] = p.gbar[row * 3 + 2] * p.scale; }
+        }
+        pe[0] = jvp ? v[0] : x[0]; pe[1] = jvp ? v[1] : x[1]; pe[2] = jvp ? v[2] : x[2];
         float f = 1.0f;
 #pragma unroll 1
         for (int q = 0; q < p.n_freq; ++q) {
@@ -286,110 +491,78 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
           for (int c = 0; c < 3; ++c) {
             float sn, cs;
             sincosf(x[c] * f, &sn, &cs);
-            pe[3 + 6 * q + c] = sn;
-            pe[3 + 6 * q + 3 + c] = cs;
+            pe[3 + 6 * q + c] = jvp ? f * cs * v[c] : sn;
+            pe[3 + 6 * q + 3 + c] = jvp ? -f * sn * v[c] : cs;
           }
           f *= 2.0f;
         }
       }
-      // ---- layer-0 operand: PE(x) -> planes of K slice 0 (column quarters 0 and 1 hold its 64 columns) ----
-      float sa, inv;
-      {
-        float mx = 0.f;
-        if (cq < 2) {
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(pe[32 * cq + j]));
-        }
-        ctl->rowexp[lp][cq][r_in] = (uint8_t)expo_bits(mx);
-        epi_bar_sync();
-        {
-          const uint32_t e01 = max((uint32_t)ctl->rowexp[lp][0][r_in], (uint32_t)ctl->rowexp[lp][1][r_in]);
-          const uint32_t e23 = max((uint32_t)ctl->rowexp[lp][2][r_in], (uint32_t)ctl->rowexp[lp][3][r_in]);
-          row_scale(max(e01, e23), sa, inv);
-        }
-        lp ^= 1;
-        if (cq < 2) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 p0, p1;
-            slice8(pe + 32 * cq + 8 * g, inv, p0, p1);
-            const uint32_t off = sw128((uint32_t)r_in, (uint32_t)(32 * cq + 8 * g));
-            *reinterpret_cast<uint4*>(a_smem + off) = p0;
-            *reinterpret_cast<uint4*>(a_smem + CH_APLANE + off) = p1;
-          }
-          fence_proxy_async();
-          mbar_arrive(&ctl->a_ready[0]);
-          if (p.e0 != nullptr && row_ok) {
-            float* e = p.e0 + row * p.pe_ld;
-#pragma unroll 1
-            for (int j = 32 * cq; j < 32 * cq + 32; ++j)
-              if (j < p.pe_ld) e[j] = pe[j];
-          }
-        }
-      }
-      for (int l = 0; l < p.n_layers; ++l) {
-        const ChainLayer& L = p.L[l];
+      float sa = 1.0f, inv = 1.0f;                           // scale of the operand currently in shared memory
+      for (int l = 0; l < p.n_steps; ++l) {
+        const ChainStep& S = p.S[l];
         CH_TR(tr_role, l, 0, clock64());
-        const float sl = sa * __ldg(L.wscale);              // z = sl (M + C) + b
-        if (!L.last) {
-          // ---------------- hidden layer: produce A_{l+1} ----------------
-          const int n_next = L.N + L.pe_next;                          // width of the next layer's input
-          float rmax = 0.f;
+        if (S.sync_before) epi_bar_sync();
+        const bool has_gemm = S.n_tiles > 0;
+        const float sl = has_gemm ? sa * __ldg(S.wscale) : 0.f;          // z = sl (M + C)
+        const float sgn_scaled = (S.kind == ST_REV_SEED) ? ctl->rowsgn[r_in] : 0.f;
+        int n_cols = S.n_next > S.N ? S.n_next : S.N;                   // logical columns this step's epilogue walks
+        if (S.kind == ST_TAN && S.n_main > n_cols) n_cols = S.n_main;
+        const int n_out_tiles = (n_cols + CH_NT - 1) / CH_NT;
+        float rmax = 0.f;
+        // ---------------- pass 1: element-wise part, stores, partial row maximum ----------------
 #pragma unroll 1
-          for (int t = 0; t < 2; ++t) {
-            if (CH_NT * t >= n_next) break;
-            const bool has_acc = t < L.n_tiles;
-            int rows_t = 0, n_valid = 0;
-            float bl = 0.f;
-            if (has_acc) {
-              rows_t = ch_tile_rows(L.N, t);
-              n_valid = L.N - CH_NT * t; n_valid = n_valid < CH_NT ? n_valid : CH_NT;
-              bl = __ldg(L.bias + CH_NT * t + 32 * cq + lane);      // lane j holds the bias of this warp's column j
-              mbar_wait(&ctl->acc_full[t], af_cnt[t] & 1u);
-              ++af_cnt[t];
-              tcgen05_fence_after();
+        for (int t = 0; t < n_out_tiles; ++t) {
+          const bool has_acc = t < S.n_tiles;
+          const int slot = t & 1;
+          int rows_t = 0;
+          float bl = 0.f;
+          if (has_acc) {
+            rows_t = S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t);
+            if (S.bias != nullptr) bl = __ldg(S.bias + CH_NT * t + 32 * cq + lane);    // lane j: bias of this warp's column j
+            mbar_wait(&ctl->acc_full[slot], af_cnt[slot] & 1u);
+            ++af_cnt[slot];
+            tcgen05_fence_after();
+          }
+          if (t == 0) CH_TR(tr_role, l, 1, clock64());
+          const uint32_t t_m = t_lane + (uint32_t)slot * 256u;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int c0 = 32 * cq + 16 * sub;                       // column inside the tile
+            const int col0 = CH_NT * t + c0;
+            float z[16], bv[16];
+            if (has_acc && c0 < rows_t) {
+              float cc[16];
+              tmem_ld16x2(t_m + (uint32_t)c0, t_m + 128u + (uint32_t)c0, z, cc);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) z[j] = (z[j] + cc[j]) * sl;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) z[j] = 0.f;
             }
-            if (t == 0) CH_TR(tr_role, l, 1, clock64());
-            const uint32_t t_m = t_lane + (uint32_t)t * 256u;
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              const int c0 = 32 * cq + 16 * sub;                     // column inside the tile
-              float v[16];
-              if (c0 < rows_t) {
-                float cc[16];
-                tmem_ld16x2(t_m + (uint32_t)c0, t_m + 128u + (uint32_t)c0, v, cc);
+            for (int j = 0; j < 16; ++j) bv[j] = __shfl_sync(0xffffffffu, bl, 16 * sub + j);
+            float nx[16];
+            step_group(S, p, row, row_ok, col0, z, bv, pe, sgn_scaled, true, nx);
+            if (S.kind == ST_FWD_LAST && col0 == 0) {
+              const float y0 = nx[0];
+              ctl->rowsgn[r_in] = (y0 > 0.f ? 1.f : (y0 < 0.f ? -1.f : 0.f)) * p.inv_scale;
+            }
+            if (S.n_next > 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += cc[j];
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int lc = c0 + j, col = CH_NT * t + lc;
-                const float b = __shfl_sync(0xffffffffu, bl, 16 * sub + j);
-                float a = 0.f;
-                if (lc < n_valid) a = softplus100_fast(fmaf(v[j], sl, b)) * L.post_scale;
-                else if (col >= L.N && col < n_next) a = pe[col - L.N] * L.post_scale;
-                v[j] = a;
-                rmax = fmaxf(rmax, fabsf(a));
-              }
-              tmem_st16(t_m + (uint32_t)c0, v);
-              if (L.out != nullptr && row_ok) {
-                float* o = L.out + row * L.ld_out + CH_NT * t + c0;
-                const int nv = n_next - (CH_NT * t + c0);
-                if (nv >= 16 && (L.ld_out & 3) == 0) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (j < nv) o[j] = v[j];
-                }
-              }
+              for (int j = 0; j < 16; ++j) rmax = fmaxf(rmax, fabsf(nx[j]));
+              if (has_gemm) tmem_st16(t_m + (uint32_t)c0, nx);       // parked in TMEM (over M) until the row scale is known
             }
           }
-          tmem_wait_st();
+          if (has_acc && S.n_next == 0) {                            // nothing continues: the accumulator pair is free again
+            tcgen05_fence_before();
+            mbar_arrive(&ctl->acc_empty[slot]);
+          }
+        }
+        CH_TR(tr_role, l, 2, clock64());
+        if (S.n_next > 0) {
+          if (has_gemm) tmem_wait_st();
           ctl->rowexp[lp][cq][r_in] = (uint8_t)expo_bits(rmax);
-          CH_TR(tr_role, l, 2, clock64());
-          epi_bar_sync();                                    // all MMAs of this layer are complete, all row maxima are in
+          epi_bar_sync();            // all MMAs of this step are complete (every warp waited for every tile), all maxima are in
           CH_TR(tr_role, l, 3, clock64());
           {
             const uint32_t e01 = max((uint32_t)ctl->rowexp[lp][0][r_in], (uint32_t)ctl->rowexp[lp][1][r_in]);
@@ -397,18 +570,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
             row_scale(max(e01, e23), sa, inv);
           }
           lp ^= 1;
-          const int nks_next = pad64(n_next) / 64;
+          // ---------------- pass 2: slice the new operand into the A planes ----------------
+          const int nks_next = pad64(S.n_next) / 64;
+          const int n_nx_tiles = (S.n_next + CH_NT - 1) / CH_NT;
 #pragma unroll 1
-          for (int t = 0; t < 2; ++t) {
-            if (CH_NT * t >= n_next) break;
-            const int s = 2 * t + (cq >> 1);                 // K slice of the next layer this warp's columns belong to
-            const uint32_t t_m = t_lane + (uint32_t)t * 256u;
-            if (s < nks_next) {
+          for (int t = 0; t < n_out_tiles; ++t) {
+            const int slot = t & 1;
+            const int s = 2 * t + (cq >> 1);                 // K slice of the next GEMM this warp's columns belong to
+            const uint32_t t_m = t_lane + (uint32_t)slot * 256u;
+            if (t < n_nx_tiles && s < nks_next) {
               uint8_t* sl_base = a_smem + (size_t)s * 2 * CH_APLANE;
 #pragma unroll
               for (int sub = 0; sub < 2; ++sub) {
+                const int c0 = 32 * cq + 16 * sub;
                 float v[16];
-                tmem_ld16(t_m + (uint32_t)(32 * cq + 16 * sub), v);
+                if (has_gemm) {
+                  tmem_ld16(t_m + (uint32_t)c0, v);
+                } else {
+                  float z[16], bv[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { z[j] = 0.f; bv[j] = 0.f; }
+                  step_group(S, p, row, row_ok, CH_NT * t + c0, z, bv, pe, sgn_scaled, false, v);   // cheap to recompute
+                }
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                   uint4 p0, p1;
@@ -421,76 +604,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
               fence_proxy_async();
               mbar_arrive(&ctl->a_ready[s]);
             }
-            if (t < L.n_tiles) {
+            if (t < S.n_tiles) {
               tcgen05_fence_before();
-              mbar_arrive(&ctl->acc_empty[t]);
+              mbar_arrive(&ctl->acc_empty[slot]);
             }
           }
-          CH_TR(tr_role, l, 4, clock64());
-        } else {
-          // ---------------- last layer: plain output ----------------
-#pragma unroll 1
-          for (int t = 0; t < L.n_tiles; ++t) {
-            const int slot = t & 1;
-            const int rows_t = ch_tile_rows(L.N, t);
-            const float bl = __ldg(L.bias + CH_NT * t + 32 * cq + lane);
-            mbar_wait(&ctl->acc_full[slot], af_cnt[slot] & 1u);
-            ++af_cnt[slot];
-            tcgen05_fence_after();
-            const uint32_t t_m = t_lane + (uint32_t)slot * 256u;
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              const int c0 = 32 * cq + 16 * sub;
-              if (c0 < rows_t) {
-                float v[16], cc[16];
-                tmem_ld16x2(t_m + (uint32_t)c0, t_m + 128u + (uint32_t)c0, v, cc);
-                const int col0 = CH_NT * t + c0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float b = __shfl_sync(0xffffffffu, bl, 16 * sub + j);
-                  v[j] = (col0 + j < L.N) ? fmaf(v[j] + cc[j], sl, b) : 0.f;
-                }
-                if (row_ok) {
-                  if (L.out != nullptr) {
-                    float* o = L.out + row * L.ld_out + col0;
-                    const int nv = L.N - col0;
-                    if (nv >= 16 && (L.ld_out & 3) == 0) {
-#pragma unroll
-                      for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    } else {
-#pragma unroll
-                      for (int j = 0; j < 16; ++j)
-                        if (j < nv) o[j] = v[j];
-                    }
-                  }
-                  if (p.udf_out != nullptr && col0 == 0) p.udf_out[row] = fabsf(v[0]) * p.inv_scale;
-                }
-              } else {
-                // keep the warp-collective shuffles of the other branch matched: nothing to do
-              }
-            }
-            tcgen05_fence_before();
-            mbar_arrive(&ctl->acc_empty[slot]);
-          }
-          CH_TR(tr_role, l, 4, clock64());
         }
+        CH_TR(tr_role, l, 4, clock64());
       }
       epi_bar_sync();     // every MMA of this point tile has completed (all warps waited for the last N tile): the A planes
-                          // may be overwritten by the next point tile's layer-0 operand
+                          // may be overwritten by the next point tile's first operand
     }
   } else if (warp == CH_MMA_WARP) {
     // =========================================== MMA issuer ===========================================
-    if (lane == 0) {
+    {
+      // the whole warp walks the loop; one elected lane issues (see elect_one)
       uint32_t wcnt = 0, ae_cnt[2] = {0u, 0u}, ar_cnt[CH_MAX_SLICES] = {0u, 0u, 0u, 0u};
       const uint32_t a_addr = smem_u32(a_smem), w_addr = smem_u32(w_smem);
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
-        const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && pt == blockIdx.x;
-        for (int l = 0; l < p.n_layers; ++l) {
-          const ChainLayer& L = p.L[l];
-          int st = L.stage0;
+        const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && pt == blockIdx.x && lane == 0;
+        for (int l = 0; l < p.n_steps; ++l) {
+          const ChainStep& S = p.S[l];
           long long w_acc = 0, w_a = 0, w_w = 0, t0;
           CH_TR(2, l, 0, clock64());
-          for (int t = 0; t < L.n_tiles; ++t) {
+          for (int t = 0; t < S.n_tiles; ++t) {
             const uint32_t slot = (uint32_t)(t & 1);
             t0 = clock64();
             mbar_wait(&ctl->acc_empty[slot], (ae_cnt[slot] & 1u) ^ 1u);       // the epilogue has drained this accumulator pair
@@ -498,7 +635,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
             ++ae_cnt[slot];
             tcgen05_fence_after();
             const uint32_t acc_m = tmem_base + slot * 256u, acc_c = acc_m + 128u;
-            for (int s = 0; s < L.n_kslices; ++s, ++st, ++wcnt) {
+            const uint32_t rows = (uint32_t)(S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t));
+            const uint32_t idesc = make_idesc_f16(rows);
+            for (int s = 0; s < S.n_kslices; ++s, ++wcnt) {
               t0 = clock64();
               if (t == 0) { mbar_wait(&ctl->a_ready[s], ar_cnt[s] & 1u); ++ar_cnt[s]; }
               w_a += clock64() - t0;
@@ -507,24 +646,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
               mbar_wait(&ctl->w_full[ws], wu & 1u);
               w_w += clock64() - t0;
               tcgen05_fence_after();
-              const uint32_t rows = p.S[st].rows;
-              const uint32_t idesc = make_idesc_f16(rows);
-              const uint32_t a0 = a_addr + (uint32_t)s * 2u * CH_APLANE, a1 = a0 + CH_APLANE;
-              const uint32_t w0 = w_addr + ws * CH_WSLOT, w1 = w0 + rows * 128u, w2 = w1 + rows * 128u;
+              // descriptors of the K step j = 0; step j adds 32 bytes = 2 units of the 16-byte address field
+              const uint64_t da0 = make_desc(a_addr + (uint32_t)s * 2u * CH_APLANE), da1 = make_desc(a_addr + (uint32_t)s * 2u * CH_APLANE + CH_APLANE);
+              const uint32_t wb = w_addr + ws * CH_WSLOT;
+              const uint64_t db0 = make_desc(wb), db1 = make_desc(wb + rows * 128u), db2 = make_desc(wb + 2u * rows * 128u);
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t first = (s == 0 && j == 0) ? 0u : 1u;
-                const uint64_t da0 = make_desc(a0 + j * 32), da1 = make_desc(a1 + j * 32);
-                const uint64_t db0 = make_desc(w0 + j * 32), db1 = make_desc(w1 + j * 32), db2 = make_desc(w2 + j * 32);
-                mma_bf16(acc_m, da0, db0, idesc, first);            // exact main term
-                mma_bf16(acc_c, da1, db1, idesc, first);            // corrections, smallest first
-                mma_bf16(acc_c, da0, db2, idesc, 1u);
-                mma_bf16(acc_c, da1, db0, idesc, 1u);
-                mma_bf16(acc_c, da0, db1, idesc, 1u);
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t first = (s == 0 && j == 0) ? 0u : 1u;
+                  const uint64_t o = (uint64_t)(2 * j);
+                  mma_bf16(acc_m, da0 + o, db0 + o, idesc, first);            // exact main term
+                  mma_bf16(acc_c, da1 + o, db1 + o, idesc, first);            // corrections, smallest first
+                  mma_bf16(acc_c, da0 + o, db2 + o, idesc, 1u);
+                  mma_bf16(acc_c, da1 + o, db0 + o, idesc, 1u);
+                  mma_bf16(acc_c, da0 + o, db1 + o, idesc, 1u);
+                }
+                mma_commit(&ctl->w_empty[ws]);
               }
-              mma_commit(&ctl->w_empty[ws]);
+              __syncwarp();
             }
-            mma_commit(&ctl->acc_full[slot]);
+            if (elect_one()) mma_commit(&ctl->acc_full[slot]);
+            __syncwarp();
           }
           CH_TR(2, l, 1, clock64());
           CH_TR(2, l, 2, w_acc);
@@ -539,16 +681,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
     if (lane == 0) {
       uint32_t wcnt = 0;
       for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
-        for (int st = 0; st < p.n_stages; ++st, ++wcnt) {
-          const uint32_t ws = wcnt % CH_NSLOT, wu = wcnt / CH_NSLOT;
-          mbar_wait(&ctl->w_empty[ws], (wu & 1u) ^ 1u);
-          const ChainStage S = p.S[st];
-          const uint32_t bytes = (uint32_t)S.rows * 128u;
-          mbar_arrive_expect_tx(&ctl->w_full[ws], CH_WPL * bytes);
-          uint8_t* dst = w_smem + ws * CH_WSLOT;
+        for (int l = 0; l < p.n_steps; ++l) {
+          const ChainStep& S = p.S[l];
+          for (int t = 0; t < S.n_tiles; ++t) {
+            const int rows_full = ch_tile_rows(S.N, t);
+            const uint32_t rows = (uint32_t)(S.rows_override > 0 ? S.rows_override : rows_full);
+            const uint32_t bytes = rows * 128u;
+            const uint16_t* tile = p.img + S.img_off + ch_tile_off(S.N, S.K, t);
+            for (int s = 0; s < S.n_kslices; ++s, ++wcnt) {
+              const uint32_t ws = wcnt % CH_NSLOT, wu = wcnt / CH_NSLOT;
+              mbar_wait(&ctl->w_empty[ws], (wu & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&ctl->w_full[ws], CH_WPL * bytes);
+              uint8_t* dst = w_smem + ws * CH_WSLOT;
+              const uint16_t* src = tile + (int64_t)s * CH_WPL * rows_full * 64;
 #pragma unroll
-          for (int pl = 0; pl < CH_WPL; ++pl)
-            bulk_g2s(dst + pl * bytes, p.img + S.src + (int64_t)pl * S.plane_rows * 64, bytes, &ctl->w_full[ws]);
+              for (int pl = 0; pl < CH_WPL; ++pl) bulk_g2s(dst + pl * bytes, src + (int64_t)pl * rows_full * 64, bytes, &ctl->w_full[ws]);
+            }
+          }
         }
       }
     }
@@ -562,7 +711,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
 }
 
 // host: launch on `st`
-static inline int launch_chain(const ChainParams& p, cudaStream_t st) {
+static inline int launch_chain(const ChainParams& p, int family, cudaStream_t st) {
   if (p.P <= 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -572,8 +721,8 @@ static inline int launch_chain(const ChainParams& p, cudaStream_t st) {
   int64_t grid = (p.P + 127) / 128;
   if (grid > sm_count()) grid = sm_count();
   static int trace_mode = -1;
-  if (trace_mode < 0) { const char* e = getenv("NUDF_CHAIN_TRACE"); trace_mode = (e && atoi(e) != 0) ? 1 : 0; }
-  if (trace_mode == 1 && p.P >= 128 * 148) {              // profiling aid: synchronous, prints CTA 0's pipeline stamps
+  if (trace_mode < 0) { const char* e = getenv("NUDF_CHAIN_TRACE"); trace_mode = (e && atoi(e) > 0) ? atoi(e) : 0; }
+  if (trace_mode > 0 && p.P >= 128 * 148) {              // profiling aid: synchronous, prints CTA 0's pipeline stamps
     static long long* dbuf = nullptr;
     if (!dbuf) NUDF_CUDA_OK(cudaMalloc(&dbuf, sizeof(long long) * CH_TRACE_WORDS));
     NUDF_CUDA_OK(cudaMemsetAsync(dbuf, 0, sizeof(long long) * CH_TRACE_WORDS, st));
@@ -584,21 +733,21 @@ static inline int launch_chain(const ChainParams& p, cudaStream_t st) {
     static long long h[CH_TRACE_WORDS];
     NUDF_CUDA_OK(cudaMemcpyAsync(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost, st));
     NUDF_CUDA_OK(cudaStreamSynchronize(st));
-    const long long z = h[(0 * NUDF_MAX_LAYERS + 0) * 8 + 0];
-    fprintf(stderr, "[chain trace] P=%lld layers=%d (cycles rel. to epilogue layer-0 start)\n", (long long)p.P, p.n_layers);
-    for (int l = 0; l < p.n_layers; ++l) {
-      const long long* e0 = h + (0 * NUDF_MAX_LAYERS + l) * 8;
-      const long long* e1 = h + (1 * NUDF_MAX_LAYERS + l) * 8;
-      const long long* m = h + (2 * NUDF_MAX_LAYERS + l) * 8;
-      fprintf(stderr, "  L%d epi0: start %7lld acc %7lld p1 %7lld bar %7lld p2 %7lld | epi1: acc %7lld p1 %7lld p2 %7lld | mma: start %7lld end %7lld "
+    const long long z = h[0];
+    fprintf(stderr, "[chain trace] P=%lld steps=%d (cycles rel. to the first step's start; epi0 = warp 0, epi1 = warp 12)\n", (long long)p.P, p.n_steps);
+    for (int l = 0; l < p.n_steps; ++l) {
+      const long long* e0 = h + (0 * CH_MAX_STEPS + l) * 8;
+      const long long* e1 = h + (1 * CH_MAX_STEPS + l) * 8;
+      const long long* m = h + (2 * CH_MAX_STEPS + l) * 8;
+      fprintf(stderr, "  S%02d kind %d epi0: start %7lld acc %7lld p1 %7lld bar %7lld p2 %7lld | epi1: acc %7lld p1 %7lld p2 %7lld | mma: start %7lld end %7lld "
                       "wait acc_empty %6lld a_ready %6lld w_full %6lld\n",
-              l, e0[0] - z, e0[1] - z, e0[2] - z, e0[3] - z, e0[4] - z, e1[1] ? e1[1] - z : 0, e1[2] ? e1[2] - z : 0, e1[4] ? e1[4] - z : 0,
-              m[0] - z, m[1] - z, m[2], m[3], m[4]);
+              l, p.S[l].kind, e0[0] - z, e0[1] ? e0[1] - z : 0, e0[2] - z, e0[3] ? e0[3] - z : 0, e0[4] - z, e1[1] ? e1[1] - z : 0,
+              e1[2] ? e1[2] - z : 0, e1[4] ? e1[4] - z : 0, m[0] ? m[0] - z : 0, m[1] ? m[1] - z : 0, m[2], m[3], m[4]);
     }
-    trace_mode = 2;                                         // once per process
+    --trace_mode;                                           // NUDF_CHAIN_TRACE = number of launches to trace
     return 0;
   }
-  LaunchTimer lt_(FAM_UDF_FWD_CHAIN, st);
+  LaunchTimer lt_(family, st);
   udf_chain_kernel<<<(unsigned)grid, CH_THREADS, CH_SMEM_BYTES, st>>>(p);
   NUDF_LAUNCH_OK();
   return 0;

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "gemm_engine.cuh"
 #include "udf_chain.cuh"
+#include <string.h>
 
 namespace nudf {
 
@@ -16,7 +17,9 @@ struct UdfPlan {
   int64_t w_off[NUDF_MAX_LAYERS], w_ld[NUDF_MAX_LAYERS], w_total;
   int64_t b_off[NUDF_MAX_LAYERS], b_total;
   int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_nt3[NUDF_MAX_LAYERS], img_nn1, img_total;   // uint16 offsets of the bf16 hi/lo weight images
-  int64_t img_chain[NUDF_MAX_LAYERS];   // uint16 offsets of the fused value chain's fp16 slice images (udf_chain.cuh)
+  int64_t img_chain[NUDF_MAX_LAYERS];   // uint16 offsets of the fused chains' fp16 slice images (udf_chain.cuh): X W_l^T operands
+  int64_t img_chain_nn[NUDF_MAX_LAYERS], img_chain_nn1;   // dY W_l operands (R / B chains); nn1: feature rows 1.. of the last layer
+  int chain_tb_ok;                      // the fused T + B chains support this network shape as well
   int64_t sb_off[NUDF_MAX_LAYERS], sb_total;   // float offsets (after the images) of the chain's per-layer [scale meta (4) | bias table]
   int chain_ok;                         // the fused value chain supports this network shape
   int pe_ld, y_ld;
@@ -60,19 +63,23 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
   if (p->d_out > 1) ioff += tc::image_elems(p->in_dim[p->n_lin - 1], p->d_out - 1, 2);
   ioff = round_up(ioff, 512);           // the chain image is fetched with cp.async.bulk: keep its slices 1024-byte aligned
   for (int l = 0; l < p->n_lin; ++l) { p->img_chain[l] = ioff; ioff += chain::ch_layer_elems(p->out_dim[l], p->in_dim[l]); }
+  for (int l = 0; l < p->n_lin - 1; ++l) { p->img_chain_nn[l] = ioff; ioff += chain::ch_layer_elems(p->in_dim[l], p->out_dim[l]); }
+  p->img_chain_nn1 = ioff;
+  if (p->d_out > 1) ioff += chain::ch_layer_elems(p->in_dim[p->n_lin - 1], p->d_out - 1);
   p->img_total = round_up(ioff, 8);
   int64_t soff = 0;
   for (int l = 0; l < p->n_lin; ++l) { p->sb_off[l] = soff; soff += 4 + (int64_t)chain::CH_NT * chain::ch_n_tiles(p->out_dim[l]); }
   p->sb_total = soff;
   // shapes the fused chain handles: PE fits one K slice, every contraction K <= 256, hidden layers <= 2 output tiles
   p->chain_ok = p->d_pe <= chain::CH_MAX_PE;
-  int n_st = 0;
   for (int l = 0; l < p->n_lin; ++l) {
     if (tc::pad64(p->in_dim[l]) > 64 * chain::CH_MAX_SLICES) p->chain_ok = 0;
     if (l < p->n_lin - 1 && p->out_dim[l] + (l + 1 == p->skip ? p->d_pe : 0) > 2 * chain::CH_NT) p->chain_ok = 0;
-    n_st += chain::ch_n_tiles(p->out_dim[l]) * (tc::pad64(p->in_dim[l]) / 64);
   }
-  if (n_st > chain::CH_MAX_STAGES) p->chain_ok = 0;
+  if (2 * p->n_lin + 2 > chain::CH_MAX_STEPS) p->chain_ok = 0;
+  // T + B: the last layer is split into its feature rows (a K = d_out - 1 contraction) and the udf-head row (rank-1 term)
+  const int F_ = p->d_out - 1;
+  p->chain_tb_ok = p->chain_ok && F_ >= 16 && F_ <= 64 * chain::CH_MAX_SLICES && (F_ % 4) == 0 && p->n_lin >= 3;
   NUDF_REQUIRE(p->in_dim[0] == p->d_pe, "in_dim[0] must equal the positional-encoding width");
   NUDF_REQUIRE(p->out_dim[p->n_lin - 1] == p->d_out, "last layer width must equal d_out");
   for (int l = 1; l < p->n_lin; ++l) {
@@ -83,6 +90,11 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
   p->y_ld = (int)round_up(p->d_out, 4);
   return 0;
 }
+
+// Which chains run as fused kernels (udf_chain.cuh).  Like the engine and the chain mask these must not change between a
+// forward call and its backward (context / scratch layouts and the folded images depend on them).
+static inline bool fused_fr_on(const UdfPlan& p) { return p.chain_ok && tc_on(TC_FWD) && tc_on(TC_REV) && !chain_planes_on(); }
+static inline bool fused_tb_on(const UdfPlan& p) { return p.chain_tb_ok && tc_on(TC_TAN) && tc_on(TC_BWD) && !chain_planes_on(); }
 
 // ---- context / scratch layout (all offsets in floats; every block starts 16B-aligned) -------------------------
 struct UdfCtx {
@@ -118,14 +130,20 @@ static void ctx_layout(const UdfPlan& p, int64_t P, int with_grad, UdfCtx* c) {
 }
 struct UdfScratch {
   int64_t edot, adot[2], q[NUDF_MAX_LAYERS], zlast, total;
+  int64_t adot_l[NUDF_MAX_LAYERS];           // fused T chain: Adot[l], l = 1..last, all kept for the weight gradients
   int64_t pl_off, adpl[NUDF_MAX_LAYERS];     // plane mode: Adot[l] (input of layer l of the tangent chain)
 };
 static void scratch_layout(const UdfPlan& p, int64_t P, UdfScratch* s) {
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
   s->edot = take(P * p.pe_ld);
-  s->adot[0] = take(P * p.max_ld);
-  s->adot[1] = take(P * p.max_ld);
+  if (fused_tb_on(p)) {
+    s->adot[0] = s->adot[1] = 0;
+    for (int l = 1; l < p.n_lin; ++l) s->adot_l[l] = take(P * p.a_ld[l]);
+  } else {
+    s->adot[0] = take(P * p.max_ld);
+    s->adot[1] = take(P * p.max_ld);
+  }
   for (int l = 0; l < p.n_lin - 1; ++l) s->q[l] = take(P * p.o_ld[l]);
   s->zlast = take(P * p.y_ld);
   s->pl_off = 0;
@@ -375,25 +393,38 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
   }
   if (get_engine() == 1) {
     uint16_t* img = reinterpret_cast<uint16_t*>(wfold + p.w_total);
-    for (int l = 0; l < p.n_lin; ++l) {
-      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, 2, img + p.img_nt[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.in_dim[l], p.out_dim[l], 1, 2, img + p.img_nn[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, 3, img + p.img_nt3[l], st)) return rc;
-    }
     const int last = p.n_lin - 1;
-    if (p.d_out > 1)
-      if (int rc = tc::prep_weights(wfold + p.w_off[last] + p.w_ld[last], p.w_ld[last], p.in_dim[last], p.d_out - 1, 1, 2, img + p.img_nn1, st))
-        return rc;
+    if (!(fused_fr_on(p) && fused_tb_on(p))) {      // split-bf16 images of the layer-by-layer tensor kernels (gemm_tc.cuh)
+      for (int l = 0; l < p.n_lin; ++l) {
+        if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, 2, img + p.img_nt[l], st)) return rc;
+        if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.in_dim[l], p.out_dim[l], 1, 2, img + p.img_nn[l], st)) return rc;
+        if (int rc = tc::prep_weights(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], 0, 3, img + p.img_nt3[l], st)) return rc;
+      }
+      if (p.d_out > 1)
+        if (int rc = tc::prep_weights(wfold + p.w_off[last] + p.w_ld[last], p.w_ld[last], p.in_dim[last], p.d_out - 1, 1, 2, img + p.img_nn1, st))
+          return rc;
+    }
     if (p.chain_ok) {
-      // fused value chain: fp16 slice images + per-column (scale, bias) tables (udf_chain.cuh)
-      float* tab = wfold + p.w_total + p.img_total / 2;     // per layer: [2 floats of scale meta | bias table]
+      // fused chains (udf_chain.cuh): fp16 slice images of W_l as the X W^T operand (F, T) and as the dY W operand (R, B),
+      // one power-of-two scale per layer, bias tables
+      float* tab = wfold + p.w_total + p.img_total / 2;     // per layer: [4 floats of scale meta | bias table]
       for (int l = 0; l < p.n_lin; ++l) {
         float* meta = tab + p.sb_off[l];
-        chain::chain_layer_scale_kernel<<<1, 256, 0, st>>>(wfold + p.w_off[l], p.w_ld[l], p.out_dim[l], p.in_dim[l], meta);
+        const float* W = wfold + p.w_off[l];
+        chain::chain_layer_scale_kernel<<<1, 256, 0, st>>>(W, p.w_ld[l], p.out_dim[l], p.in_dim[l], meta);
         NUDF_LAUNCH_OK();
         chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.out_dim[l]), 64, 0, st>>>(
-            wfold + p.w_off[l], p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], meta, img + p.img_chain[l], meta + 4);
+            W, p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], 0, meta, img + p.img_chain[l], meta + 4);
         NUDF_LAUNCH_OK();
+        if (l < last) {
+          chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.in_dim[l]), 64, 0, st>>>(
+              W, p.w_ld[l], nullptr, p.in_dim[l], p.out_dim[l], 1, meta, img + p.img_chain_nn[l], nullptr);
+          NUDF_LAUNCH_OK();
+        } else if (p.d_out > 1) {
+          chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.in_dim[l]), 64, 0, st>>>(
+              W + p.w_ld[l], p.w_ld[l], nullptr, p.in_dim[l], p.d_out - 1, 1, meta, img + p.img_chain_nn1, nullptr);
+          NUDF_LAUNCH_OK();
+        }
       }
     }
   }
@@ -404,54 +435,142 @@ static inline const uint16_t* img_base(const UdfPlan& p, const float* wfold) {
   return reinterpret_cast<const uint16_t*>(wfold + p.w_total);
 }
 
-// Parameters of the fused value chain (udf_chain.cuh) for P points.  value_only: the last layer is restricted to its udf-head
-// row and only udf[P] is written; otherwise the context tensors E0, A[1..], Y are written as the per-layer path does.
-static void build_chain(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, float* ctx, const UdfCtx* c, float* udf,
-                        chain::ChainParams* cp) {
-  const bool value_only = udf != nullptr;
+// ---- fused chains (udf_chain.cuh): step lists -------------------------------------------------------------------------
+static chain::ChainStep* add_step(chain::ChainParams* cp, int kind) {
+  chain::ChainStep* S = &cp->S[cp->n_steps++];
+  memset(S, 0, sizeof(*S));
+  S->kind = kind;
+  S->post_scale = 1.0f;
+  S->a_unscale = 1.0f;
+  return S;
+}
+static void set_gemm(chain::ChainStep* S, const UdfPlan& p, const float* wfold, int layer, int K, int N, int64_t img_off) {
   const float* tab = wfold + p.w_total + p.img_total / 2;
-  cp->n_layers = p.n_lin;
+  S->K = K; S->N = N;
+  S->n_kslices = tc::pad64(K) / 64;
+  S->n_tiles = chain::ch_n_tiles(N);
+  S->img_off = (uint32_t)img_off;
+  S->wscale = tab + p.sb_off[layer] + 1;
+}
+static void chain_common(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, chain::ChainParams* cp) {
+  cp->n_steps = 0;
   cp->img = img_base(p, wfold);
   cp->pts = pts; cp->P = P; cp->scale = p.scale; cp->n_freq = p.L; cp->d_pe = p.d_pe;
-  cp->e0 = value_only ? nullptr : ctx + c->e0; cp->pe_ld = p.pe_ld;
-  cp->udf_out = udf; cp->inv_scale = 1.0f / p.scale;
+  cp->gbar = nullptr;
+  cp->udf_out = nullptr; cp->inv_scale = 1.0f / p.scale;
   cp->trace = nullptr;
-  int st = 0;
-  for (int l = 0; l < p.n_lin; ++l) {
-    chain::ChainLayer& L = cp->L[l];
-    const bool last = l == p.n_lin - 1;
-    L.K = p.in_dim[l];
-    L.N = (last && value_only) ? 1 : p.out_dim[l];
-    L.n_kslices = tc::pad64(L.K) / 64;
-    L.n_tiles = chain::ch_n_tiles(L.N);
-    L.stage0 = st;
-    L.last = last ? 1 : 0;
-    L.pe_next = (!last && l + 1 == p.skip) ? p.d_pe : 0;
-    L.post_scale = (!last && l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
-    L.wscale = tab + p.sb_off[l] + 1;
-    L.bias = tab + p.sb_off[l] + 4;
-    if (value_only) { L.out = nullptr; L.ld_out = 0; }
-    else if (last) { L.out = ctx + c->y; L.ld_out = p.y_ld; }
-    else { L.out = ctx + c->a[l + 1]; L.ld_out = p.a_ld[l + 1]; }
-    for (int t = 0; t < L.n_tiles; ++t) {
-      const int rows_full = chain::ch_tile_rows(p.out_dim[l], t);
-      for (int s = 0; s < L.n_kslices; ++s, ++st) {
-        chain::ChainStage& S = cp->S[st];
-        S.src = (uint32_t)(p.img_chain[l] + chain::ch_tile_off(p.out_dim[l], p.in_dim[l], t) + (int64_t)s * chain::CH_WPL * rows_full * 64);
-        S.rows = (uint16_t)((last && value_only) ? 16 : rows_full);
-        S.plane_rows = (uint16_t)rows_full;
-      }
+}
+// F chain for P points; value_only (udf != null): the last layer is restricted to its udf-head row and only udf[P] is
+// written; otherwise the context tensors E0, A[1..], Y are written.  with_rev: the R chain (exact grad_x udf) follows in the
+// same launch and writes D[0..last-1], Gpe, Ge.
+static void build_forward(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, float* ctx, const UdfCtx* c, float* udf,
+                          bool with_rev, chain::ChainParams* cp) {
+  const bool value_only = udf != nullptr;
+  const float* tab = wfold + p.w_total + p.img_total / 2;
+  const int last = p.n_lin - 1;
+  chain_common(p, wfold, pts, P, cp);
+  cp->udf_out = udf;
+  chain::ChainStep* S = add_step(cp, chain::ST_PE);
+  S->n_next = p.d_pe;
+  if (!value_only) { S->out0 = ctx + c->e0; S->ld_out0 = p.pe_ld; }
+  for (int l = 0; l < last; ++l) {
+    S = add_step(cp, chain::ST_FWD);
+    set_gemm(S, p, wfold, l, p.in_dim[l], p.out_dim[l], p.img_chain[l]);
+    S->bias = tab + p.sb_off[l] + 4;
+    S->n_next = p.in_dim[l + 1];
+    S->post_scale = (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+    if (!value_only) { S->out0 = ctx + c->a[l + 1]; S->ld_out0 = p.a_ld[l + 1]; }
+  }
+  S = add_step(cp, chain::ST_FWD_LAST);
+  set_gemm(S, p, wfold, last, p.in_dim[last], value_only ? 1 : p.out_dim[last], p.img_chain[last]);
+  S->bias = tab + p.sb_off[last] + 4;
+  if (value_only) S->rows_override = 16;
+  else { S->out0 = ctx + c->y; S->ld_out0 = p.y_ld; }
+  if (!with_rev) return;
+  auto rev_common = [&](chain::ChainStep* R, int l) {       // epilogue that turns G (w.r.t. A[l]) into D[l-1]
+    R->n_main = p.out_dim[l - 1];
+    R->n_next = R->n_main;
+    R->post_scale = (l == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+    R->a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
+    R->in0 = ctx + c->a[l]; R->ld_in0 = p.a_ld[l];
+    R->out0 = ctx + c->d[l - 1]; R->ld_out0 = p.o_ld[l - 1];
+    if (l == p.skip) { R->out1 = ctx + c->gpe; R->ld_out1 = p.pe_ld; }
+  };
+  S = add_step(cp, chain::ST_REV_SEED);                     // G_last = (sgn / scale) W_last[0, :]
+  S->N = p.in_dim[last];
+  S->vec0 = wfold + p.w_off[last];
+  S->sync_before = 1;
+  rev_common(S, last);
+  for (int l = last - 1; l >= 1; --l) {
+    S = add_step(cp, chain::ST_REV);
+    set_gemm(S, p, wfold, l, p.out_dim[l], p.in_dim[l], p.img_chain_nn[l]);
+    rev_common(S, l);
+  }
+  S = add_step(cp, chain::ST_REV_FINAL);
+  set_gemm(S, p, wfold, 0, p.out_dim[0], p.in_dim[0], p.img_chain_nn[0]);
+  if (p.skip >= 1) { S->in1 = ctx + c->gpe; S->ld_in1 = p.pe_ld; }
+  S->out0 = ctx + c->ge; S->ld_out0 = p.pe_ld;
+}
+
+// T chain (tangent, needs grad_bar) followed by the B chain (backward) in one launch.  Tensors: ctx (read): E0, A[l], D[l];
+// scratch: Edot, Adot[l] (written by T, read later by the weight gradients), Q[l] (written by T, turned into Zbar[l] in place by
+// B), zf / z0 (the split upstream gradient of the last layer, zlast_split_kernel).  with_t = false: Q was zero-filled.
+static void build_backward(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, const float* grad_bar, float* ctx,
+                           const UdfCtx& c, float* scr, const UdfScratch& s, const float* zf, const float* z0, bool with_t,
+                           chain::ChainParams* cp) {
+  const int last = p.n_lin - 1;
+  const int F = p.d_out - 1;
+  chain_common(p, wfold, pts, P, cp);
+  cp->gbar = grad_bar;
+  chain::ChainStep* S;
+  if (with_t) {
+    S = add_step(cp, chain::ST_EDOT);
+    S->n_next = p.d_pe;
+    S->out0 = scr + s.edot; S->ld_out0 = p.pe_ld;
+    for (int l = 0; l < last; ++l) {
+      S = add_step(cp, chain::ST_TAN);
+      set_gemm(S, p, wfold, l, p.in_dim[l], p.out_dim[l], p.img_chain[l]);
+      S->n_main = p.in_dim[l + 1];                          // width of Adot[l+1] (incl. the Edot columns at the skip layer)
+      S->n_next = (l + 1 < last) ? p.in_dim[l + 1] : 0;     // Adot[last] feeds no GEMM (only a weighted column sum)
+      S->post_scale = (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+      S->a_unscale = (l + 1 == p.skip) ? 1.41421356237309504880f : 1.0f;
+      S->in0 = ctx + c.a[l + 1]; S->ld_in0 = p.a_ld[l + 1];
+      S->in1 = ctx + c.d[l]; S->ld_in1 = p.o_ld[l];
+      S->out0 = scr + s.q[l]; S->ld_out0 = p.o_ld[l];
+      S->out1 = scr + s.adot_l[l + 1]; S->ld_out1 = p.a_ld[l + 1];
     }
   }
-  cp->n_stages = st;
+  S = add_step(cp, chain::ST_LOAD);                         // operand of the first B GEMM: the feature part of out_bar
+  S->n_next = F;
+  S->in0 = zf; S->ld_in0 = F;
+  S->sync_before = 1;
+  auto bwd_common = [&](chain::ChainStep* B, int l) {       // Abar (w.r.t. A[l]) -> Zbar[l-1] = Abar S_{l-1} + Q[l-1], in place over Q
+    B->n_main = p.out_dim[l - 1];
+    B->n_next = (l - 1 >= 1) ? B->n_main : 0;               // Zbar[0] feeds no further GEMM
+    B->post_scale = (l == p.skip) ? NUDF_SQRT1_2 : 1.0f;
+    B->a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
+    B->in0 = ctx + c.a[l]; B->ld_in0 = p.a_ld[l];
+    B->in1 = scr + s.q[l - 1]; B->ld_in1 = p.o_ld[l - 1];
+    B->out0 = scr + s.q[l - 1]; B->ld_out0 = p.o_ld[l - 1];
+  };
+  S = add_step(cp, chain::ST_BWD);                          // last layer: feature rows as a K = F contraction + rank-1 udf-head term
+  set_gemm(S, p, wfold, last, F, p.in_dim[last], p.img_chain_nn1);
+  S->rowv = z0;
+  S->vec0 = wfold + p.w_off[last];
+  bwd_common(S, last);
+  for (int l = last - 1; l >= 1; --l) {
+    S = add_step(cp, chain::ST_BWD);
+    set_gemm(S, p, wfold, l, p.out_dim[l], p.in_dim[l], p.img_chain_nn[l]);
+    bwd_common(S, l);
+  }
 }
 
 static int value_chain(const UdfPlan& p, const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P,
                        float* ctx, const UdfCtx& c, cudaStream_t st) {
   if (p.chain_ok && tc_on(TC_FWD)) {            // one fused tcgen05 kernel for all layers (activations stay on chip)
     chain::ChainParams cp;
-    build_chain(p, wfold, pts, P, ctx, &c, nullptr, &cp);
-    return chain::launch_chain(cp, st);
+    build_forward(p, wfold, pts, P, ctx, &c, nullptr, false, &cp);
+    return chain::launch_chain(cp, FAM_UDF_FWD_CHAIN, st);
   }
   float* e0 = ctx + c.e0;
   float* askip = nullptr; int askip_ld = 0, askip_col = 0;
@@ -595,6 +714,18 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
   cudaStream_t st = (cudaStream_t)stream;
   UdfCtx c;
   ctx_layout(p, P, grad != nullptr, &c);
+  if (grad != nullptr && fused_fr_on(p)) {
+    // value chain + reverse sweep of every 128-point tile in ONE launch (udf_chain.cuh): writes E0, A[l], Y, D[l], Gpe, Ge
+    chain::ChainParams cp;
+    build_forward(p, wfold, pts, P, ctx, &c, nullptr, true, &cp);
+    if (int rc = chain::launch_chain(cp, FAM_UDF_FWD_CHAIN, st)) return rc;
+    udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
+                                                                ctx + c.sgn);
+    NUDF_LAUNCH_OK();
+    pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad);
+    NUDF_LAUNCH_OK();
+    return 0;
+  }
   if (int rc = value_chain(p, d, wfold, pts, P, ctx, c, st)) return rc;
   udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
                                                               ctx + c.sgn);
@@ -612,8 +743,8 @@ int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts,
   cudaStream_t st = (cudaStream_t)stream;
   if (p.chain_ok && tc_on(TC_FWD)) {
     chain::ChainParams cp;
-    build_chain(p, wfold, pts, P, nullptr, nullptr, udf, &cp);
-    return chain::launch_chain(cp, st);
+    build_forward(p, wfold, pts, P, nullptr, nullptr, udf, false, &cp);
+    return chain::launch_chain(cp, FAM_UDF_FWD_CHAIN, st);
   }
   NUDF_REQUIRE(work != nullptr, "null pointer (work)");
   UdfCtx c;
@@ -646,6 +777,53 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
   scratch_layout(p, P, &s);
   const int last = p.n_lin - 1;
   const int split = (int)cdiv(P, 2048);
+
+  if (fused_tb_on(p)) {
+    // ---- tangent + backward chains of every 128-point tile in ONE launch (udf_chain.cuh), then the weight gradients ----
+    const int F = p.d_out - 1;
+    float* zf = scratch + s.zlast;                  // [P, F] feature part of the upstream gradient of the last layer
+    float* z0 = zf + P * F;                         // [P]    udf-head part, times sgn / scale
+    if (out_bar) {
+      zlast_split_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
+      NUDF_LAUNCH_OK();
+    } else {
+      NUDF_CUDA_OK(cudaMemsetAsync(zf, 0, sizeof(float) * P * (F + 1), st));
+    }
+    const bool with_t = grad_bar != nullptr;
+    if (!with_t)
+      for (int l = 0; l < last; ++l) NUDF_CUDA_OK(cudaMemsetAsync(scratch + s.q[l], 0, sizeof(float) * P * p.o_ld[l], st));
+    {
+      chain::ChainParams cp;
+      build_backward(p, wfold, pts, P, grad_bar, ctx, c, scratch, s, zf, z0, with_t, &cp);
+      if (int rc = chain::launch_chain(cp, FAM_UDF_BWD_CHAIN, st)) return rc;
+    }
+    if (with_t) {
+      for (int l = 0; l < last; ++l) {              // dW_l += D_l^T Adot_l   (Adot_0 = Edot)
+        const float* adot = l == 0 ? scratch + s.edot : scratch + s.adot_l[l];
+        const int64_t ld_adot = l == 0 ? p.pe_ld : p.a_ld[l];
+        EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
+        if (int rc = gemm_tn(ctx + c.d[l], p.o_ld[l], adot, ld_adot, p.out_dim[l], p.in_dim[l], P, ew, st, split)) return rc;
+      }
+      // g_last = W_last^T d_last with d_last = (sgn/scale) e_0  =>  dW_last[0,:] += sum_p (sgn/scale) Adot_last
+      if (int rc = colsum(scratch + s.adot_l[last], p.a_ld[last], ctx + c.sgn, 1.0f / p.scale, P, p.in_dim[last], dwfold + p.w_off[last], st))
+        return rc;
+    }
+    if (out_bar) {
+      float* dWl = dwfold + p.w_off[last];
+      EpiAtomicAdd ew{dWl + p.w_ld[last], p.w_ld[last]};
+      if (int rc = gemm_tn(zf, F, ctx + c.a[last], p.a_ld[last], F, p.in_dim[last], P, ew, st, split, TC_WGRAD, dbias + p.b_off[last] + 1))
+        return rc;
+      if (int rc = colsum(ctx + c.a[last], p.a_ld[last], z0, 1.0f, P, p.in_dim[last], dWl, st)) return rc;
+      if (int rc = colsum(z0, 1, nullptr, 1.0f, P, 1, dbias + p.b_off[last], st)) return rc;
+    }
+    for (int l = last - 1; l >= 0; --l) {           // dW_l += Zbar_l^T A_l, db_l = column sums of Zbar_l
+      const float* A = l == 0 ? ctx + c.e0 : ctx + c.a[l];
+      const int64_t lda = l == 0 ? p.pe_ld : p.a_ld[l];
+      EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
+      if (int rc = gemm_tn(scratch + s.q[l], p.o_ld[l], A, lda, p.out_dim[l], p.in_dim[l], P, ew, st, split, TC_WGRAD, dbias + p.b_off[l])) return rc;
+    }
+    return 0;
+  }
 
   // ---- tangent chain (second-order terms) ----
   if (grad_bar && chain_planes_on()) {

@@ -94,7 +94,9 @@ class UdfHandle:
     def refresh(self):
         ps = self.params()
         _require_cuda(*ps)
-        key = tuple((p.data_ptr(), p._version) for p in ps) + (L.lib().nudf_get_engine(),)
+        lib_ = L.lib()
+        # the folded images depend on the engine and on which chains run fused (chain mask, plane mode)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (lib_.nudf_get_engine(), lib_.nudf_get_tc_mask(), lib_.nudf_get_chain_planes())
         if key == self._key:
             return
         d = L.UdfDesc()

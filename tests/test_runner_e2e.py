@@ -25,7 +25,17 @@ sys.path.insert(0, {root!r})
 from tests import runner_env
 runner_env.install_stubs()
 from neuraludf_b200 import launch
-sys.exit(launch.main({argv!r}))
+try:
+    rc = launch.main({argv!r})
+except NotImplementedError as e:
+    # `--mode train` ends with runner.extract_udf_mesh(resolution=512) (exp_runner_blending.py:900-902): the dense 512^3 UDF +
+    # gradient grid query runs on the nudf kernels, then the Cython MeshUDF marching cubes (custom_mc, SURVEY.md 2 row 10, out
+    # of scope, absent from this image) is called -- the stub raises there, after the training loop has finished
+    if "custom_mc" not in str(e):
+        raise
+    print("REACHED_CUSTOM_MC_STUB_AFTER_TRAINING")
+    rc = 0
+sys.exit(rc)
 """
 
 
@@ -70,6 +80,7 @@ def test_unmodified_runner_trains_checkpoints_and_validates(tmp_path):
     imgs = glob.glob(os.path.join(exp_dir, "**", "*.png"), recursive=True)
     assert len(imgs) >= 1, tail
     assert "iter:" in r.stdout and "psnr" in r.stdout
+    assert "REACHED_CUSTOM_MC_STUB_AFTER_TRAINING" in r.stdout       # the post-training 512^3 grid query ran on our kernels
     # resume: --is_continue loads the last checkpoint (exp_runner_blending.py:150-162, 467-482) and trains on to iteration 6
     conf2 = runner_env.write_conf(ref, os.path.join(tmp, "synth2.conf"), os.path.join(tmp, "data", "CASE_NAME") + "/", exp,
                                   end_iter=6, batch_size=256, save_freq=2, val_freq=100)
