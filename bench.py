@@ -119,7 +119,7 @@ def make_optimizer(udf, others, fused=True):
     groups = [{"params": [p for p in udf.parameters() if p.requires_grad], "lr": 1e-4},
               {"params": [p for m in others for p in m.parameters() if p.requires_grad], "lr": 5e-4}]
     try:
-        return torch.optim.Adam(groups, fused=fused)
+        return torch.optim.Adam(groups, fused=fused, capturable=fused)      # capturable: the step can live in a CUDA graph
     except Exception:
         return torch.optim.Adam(groups)
 
@@ -292,25 +292,58 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(o, d, z)
     barrier()
+    # ---- eager loop: every kernel launched from Python (ctypes / torch) each step ----
     l0 = lib.nudf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if clocks:
-        clocks.begin()
     barrier()
     e0.record()
     for _ in range(args.steps):
         step(o, d, z)
     e1.record()
     barrier()
+    ms_eager = e0.elapsed_time(e1)
+    launches = lib.nudf_launch_count() - l0
+    # ---- the same step captured ONCE into a CUDA graph and replayed (no host work per step; the step has no host read) ----
+    graph, g_in, g_loss, graph_err = None, None, None, None
+    if not args.no_graph:
+        try:
+            g_in = [t.clone() for t in (o, d, z)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(*g_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_loss = step(*g_in)
+            for _ in range(3):
+                graph.replay()
+            barrier()
+        except Exception as e:                         # capture not possible here: the eager number stands
+            graph, graph_err = None, "%s: %s" % (type(e).__name__, str(e)[:200])
+            torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if clocks:
+        clocks.begin()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        if graph is not None:
+            graph.replay()
+        else:
+            step(o, d, z)
+    e1.record()
+    barrier()
     if clocks:
         clocks.end()
     ms = e0.elapsed_time(e1)
-    launches = lib.nudf_launch_count() - l0
     clk = clocks.stop() if clocks else None
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+            print(json.dumps({"quick": True, "ms_per_step": ms / args.steps, "ms_per_step_eager": ms_eager / args.steps,
+                              "cuda_graph": graph is not None, "gpu_launches": int(launches),
                               "value": world * N_RAYS * N_SAMPLES * args.steps / (ms * 1e-3)}), flush=True)
         if world > 1:
             dist.barrier()
@@ -332,14 +365,21 @@ def run_ours(args):
     # ---- end-to-end: host (pinned) inputs, H2D + D2H inside the timed region, through the public module API ----
     ho, hd, hz, _ = rays(seed=rank)
     ho, hd, hz = ho.pin_memory(), hd.pin_memory(), hz.contiguous().pin_memory()
+    def e2e_step():
+        if graph is not None:                          # H2D into the graph's static inputs, replay, D2H of the loss
+            g_in[0].copy_(ho, non_blocking=True); g_in[1].copy_(hd, non_blocking=True); g_in[2].copy_(hz, non_blocking=True)
+            graph.replay()
+            return g_loss
+        return step(ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True), hz.to(dev, non_blocking=True))
+
     for _ in range(2):
-        l = step(ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True), hz.to(dev, non_blocking=True))
+        l = e2e_step()
     barrier()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        l = step(ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True), hz.to(dev, non_blocking=True))
+        l = e2e_step()
         float(l.item())                                # D2H read of the step's result (loss)
     f1.record()
     barrier()
@@ -352,10 +392,11 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(times[0]), float(times[1])
 
+    graph_flag = graph is not None
     # ---- the other BASELINE.json configs (short runs) ----
     extra = {}
     if not args.no_extra:
-        del ren, bucket, opt
+        del ren, bucket, opt, graph, g_in, g_loss
         torch.cuda.empty_cache()
         sub = argparse.Namespace(steps=5, warmup=3)
         for name, fn in (("c1", run_c1), ("c3", run_c3), ("c4", run_c4), ("c5", run_c5)):
@@ -371,6 +412,7 @@ def run_ours(args):
         samples = world * N_RAYS * N_SAMPLES * args.steps
         value = samples / (ms * 1e-3)
         engine = lib.nudf_get_engine()
+        graph_used = graph_flag
         step_tflops = value * FLOP_FWD_BWD / 1e12 / world
         # roofline: the kernel family with the largest share of the step's device time
         tens = {k: v for k, v in fam.items() if "algorithmic_tflops" in v}
@@ -397,6 +439,7 @@ def run_ours(args):
         out = {
             "metric": "ray-samples/sec (render_core fwd+bwd)", "value": value, "unit": "ray-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "ms_per_step_eager": ms_eager / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded geometric-init sphere scene, random-perturbed weights)",
             "config": {"workload": "C2: 512 rays x 128 uniform samples per GPU, UDF 8x256 + colour 2x(4x128), "
@@ -404,6 +447,8 @@ def run_ours(args):
                        "rays_per_gpu": N_RAYS, "samples_per_ray": N_SAMPLES,
                        "parallelism": "dp%d (rays sharded, NCCL all-reduce of the flat gradient bucket)" % world,
                        "l2": "per-step working set (> 1 GB of saved activations) exceeds the 126 MB L2",
+                       "launch": ("whole step captured once in a CUDA graph and replayed" if graph_used else
+                                  "eager (every kernel launched from Python each step)" + (": graph capture failed -- " + graph_err if graph_err else "")),
                        "engine": ("tcgen05 (fused exact fp16-split value chain + 3xBF16 gradient chains), chain mask %d" % lib.nudf_get_tc_mask())
                        if engine == 1 else "fp32 FFMA",
                        "algorithmic_flop_per_sample": FLOP_FWD_BWD,
@@ -544,39 +589,23 @@ def run_c3(args, dev, lib, rank, world):
 def run_c5(args, dev, lib, rank, world):
     """BASELINE configs[4]: 256^3 lattice on [-1,1]^3 -- UDF value at every point, then the normalised gradient where
     udf < 2 voxels (the reference's get_udf_normals_grid_slow, extract_mesh.py:18-105) and, as an upper bound, at every
-    point.  With N ranks the lattice is slab-partitioned along x (replicas only, no exchange)."""
+    point.  Lattice generated, compacted and handed over on the device (neuraludf_b200/grid.py).  With N ranks the lattice is
+    slab-partitioned along x (replicas only, no exchange)."""
     import torch.distributed as dist
+    from neuraludf_b200 import grid
     udf, _, _, _ = scene(dev)
     R = 256
-    lo, hi = rank * R // world, (rank + 1) * R // world
-    ax = torch.linspace(-1.0, 1.0, R, device=dev)
-    voxel = 2.0 / (R - 1)
-    chunk = 1 << 21
+    n_pts = R ** 3
+    lo, hi = rank * n_pts // world, (rank + 1) * n_pts // world
 
-    def slab_points():
-        for i0 in range(lo, hi, 8):
-            i1 = min(i0 + 8, hi)
-            yield torch.cartesian_prod(ax[i0:i1], ax, ax)
-
-    def sweep_values():
-        out = []
-        for pts in slab_points():
-            for c in range(0, pts.shape[0], chunk):
-                out.append(udf.udf_values(pts[c:c + chunk]))
-        return torch.cat(out)
-
-    def sweep_grads(mask=None):
+    def sweep_all_grads():
         n = 0
-        off = 0
-        for pts in slab_points():
-            if mask is not None:
-                pts = pts[mask[off:off + pts.shape[0]]]
-            off += (8 * R * R)
-            for c in range(0, pts.shape[0], chunk):
-                with torch.no_grad():
-                    g = udf.gradient(pts[c:c + chunk]).squeeze(1)
-                    g = g / (g.norm(dim=-1, keepdim=True) + 1e-12)
-                n += g.shape[0]
+        for head in range(lo, hi, 1 << 20):
+            m = min(1 << 20, hi - head)
+            with torch.no_grad():
+                g = udf.gradient(grid.lattice_points(head, m, R, dev)).squeeze(1)
+                g = g / (g.norm(dim=-1, keepdim=True) + 1e-12)
+            n += m
         return n
 
     def timed(fn):
@@ -592,20 +621,18 @@ def run_c5(args, dev, lib, rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), r
 
-    t_val, u = timed(sweep_values)
-    near = u < 2 * voxel
-    t_gn, n_near = timed(lambda: sweep_grads(near))
-    t_ga, n_all = timed(lambda: sweep_grads(None))
+    t_val, u = timed(lambda: grid.udf_grid(udf, R, lo=lo, hi=hi))
+    t_gn, cells = timed(lambda: grid.near_surface_cells(udf, R, u, lo=lo))
+    t_ga, _ = timed(sweep_all_grads)
     pk = peaks()
-    n_pts = R ** 3
-    return {"workload": "c5: 256^3 grid query (value everywhere; normalised gradient near the surface / everywhere)",
-            "n_gpus": world, "value_sweep_s": t_val, "value_Mpts_per_s": n_pts / t_val / 1e6,
-            "value_algorithmic_tflops": n_pts * 918016 / t_val / 1e12,
-            "value_hbm_gbs": n_pts * 16 / t_val / 1e9, "value_hbm_frac": n_pts * 16 / t_val / 1e9 / pk["hbm"],
-            "near_surface_points_this_rank": int(n_near), "near_surface_gradient_sweep_s": t_gn,
+    return {"workload": "c5: 256^3 grid query (value everywhere; normalised gradient near the surface / everywhere), lattice "
+                        "generated and compacted on the device", "n_gpus": world, "value_sweep_s": t_val,
+            "value_Mpts_per_s": n_pts / t_val / 1e6, "value_algorithmic_tflops": n_pts * 918016 / t_val / 1e12,
+            "value_hbm_gbs": n_pts * 4 / t_val / 1e9, "value_hbm_frac": n_pts * 4 / t_val / 1e9 / pk["hbm"],
+            "near_surface_cells_this_rank": int(cells[0].numel()), "near_surface_gradient_sweep_s": t_gn,
             "all_points_gradient_sweep_s": t_ga, "all_points_value_and_gradient_Mpts_per_s": n_pts / t_ga / 1e6,
-            "note": "compute-bound by construction (0.9-1.8 MFLOP per point vs 16 B of HBM traffic per point): the HBM "
-                    "fraction is small and is not the bound (SURVEY 8(d))"}
+            "note": "compute-bound by construction (0.9-1.8 MFLOP per point vs 4 B of HBM traffic per point -- the lattice is "
+                    "generated in place --): the HBM fraction is small and is not the bound (SURVEY 8(d))"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -734,6 +761,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="main timed loop only (for profiler runs): no e2e leg, no "
                     "family table, no CPU baseline, no secondary workloads; prints a reduced JSON line")
     ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="time the eager loop only (no CUDA-graph capture)")
     args = ap.parse_args()
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:

@@ -40,6 +40,19 @@ NUDF_HD float sig_from_softplus(float a) {
 #endif
 }
 NUDF_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// "T128" layout of a [rows, ld] fp32 tensor (ld % 4 == 0, storage for round_up(rows, 128) rows): 128-row tiles, inside a tile
+// the 4-column groups are outermost and the rows innermost,
+//     offset(row, col) = (((row / 128) * (ld / 4) + col / 4) * 128 + row % 128) * 4 + col % 4.
+// The fused chain kernels give every thread one ROW of a 128-row tile (that is how tcgen05.ld hands out the accumulator): in
+// this layout the 32 lanes of a warp (32 consecutive rows, same column group) touch 512 contiguous bytes per 16-byte access
+// -- fully coalesced -- where row-major would touch 32 different lines (1/8 of the L1 wavefront efficiency; measured: the
+// epilogues were bound by exactly that).  The weight-gradient kernels, which contract over rows, read 4 consecutive columns of
+// consecutive rows: contiguous here as well.
+NUDF_HD int64_t t128_off(int64_t row, int64_t col, int64_t ld) {
+  return ((((row >> 7) * (ld >> 2) + (col >> 2)) << 7) + (row & 127)) * 4 + (col & 3);
+}
+NUDF_HD int64_t mat_off(bool t128, int64_t row, int64_t col, int64_t ld) { return t128 ? t128_off(row, col, ld) : row * ld + col; }
 NUDF_HD float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 }  // namespace nudf

@@ -37,7 +37,7 @@ static inline int gemm_nn(const float* A, int64_t lda, const float* W, int64_t l
   return gemm_simt<true, false, Epi>(A, lda, W, ldw, M, N, K, epi, st, 1);
 }
 // C[M x N] += A[K x M]^T B[K x N]   (contraction over points)
-int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st);
+int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st, bool t128 = false);
 
 // ---- plane-fed chains (gemm_pl.cuh) -------------------------------------------------------------------------------
 // Optional mode (nudf_set_chain_planes(1) / NUDF_PLANES=1): the reverse-sweep and tangent chains of the UDF network carry
@@ -67,17 +67,19 @@ static __global__ void copy_cols_planes_kernel(const float* __restrict__ src, in
 
 // colsum_a (optional): colsum_a[m] += sum_k A[k, m] -- the bias gradient that goes with a weight gradient; fused into the
 // tensor-engine kernel's operand staging, a separate reduction kernel on the FFMA path.
+// t128: both operands are stored in the T128 layout (common.cuh) -- tensor-engine kernel only.
 template <class Epi>
 static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K,
-                          const Epi& epi, cudaStream_t st, int split_k, int chain = TC_WGRAD, float* colsum_a = nullptr) {
-  if (tc_on(chain) && M >= 32 && N >= 32 && K >= 128) {
+                          const Epi& epi, cudaStream_t st, int split_k, int chain = TC_WGRAD, float* colsum_a = nullptr,
+                          bool t128 = false) {
+  if (t128 || (tc_on(chain) && M >= 32 && N >= 32 && K >= 128)) {
     // split the points so that (M tiles x N tiles x splits) fills the SMs once, with at least 8 slices of 64 points per CTA
     const int tiles = (int)(cdiv(M, 128) * cdiv(N, 256));
     int splits = tc::sm_count() / tiles;
     const int max_splits = (int)cdiv(K, 512);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    return tc::gemm_tn(A, lda, B, ldb, M, N, K, epi, st, splits, colsum_a);
+    return tc::gemm_tn(A, lda, B, ldb, M, N, K, epi, st, splits, colsum_a, t128);
   }
   if (int rc = gemm_simt<false, false, Epi>(A, lda, B, ldb, M, N, K, epi, st, split_k)) return rc;
   if (colsum_a != nullptr) return colsum(A, lda, nullptr, 1.f, K, M, colsum_a, st);

@@ -217,7 +217,7 @@ __device__ __forceinline__ void stage_a_direct(const float* __restrict__ A, int6
 template <bool CSUM = false>
 __device__ __forceinline__ void stage_block_t(const float* __restrict__ X, int64_t ld, int m0, int m_total, int r0, int rows,
                                               int64_t k0, int64_t k_end, uint8_t* s_hi, uint8_t* s_lo, int lane, bool vec_ok,
-                                              float* csum = nullptr) {
+                                              float* csum = nullptr, bool t128 = false) {
   const int mq = lane & 7, kq = lane >> 3;
   if (r0 + 4 * mq >= rows) return;      // tile rows are padded to 16, blocks cover 32: skip quads beyond the tile
   const int m = m0 + r0 + 4 * mq;
@@ -229,7 +229,7 @@ __device__ __forceinline__ void stage_block_t(const float* __restrict__ X, int64
       const int64_t k = k0 + 2 * (4 * q + kq) + kk;
       v[q][kk] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < k_end) {
-        const float* p = X + k * ld + m;
+        const float* p = X + (t128 ? t128_off(k, m, ld) : k * ld + m);       // T128 (common.cuh): 4 features of a point stay contiguous
         if (vec_ok && m + 3 < m_total) {
           v[q][kk] = *reinterpret_cast<const float4*>(p);
         } else {
@@ -830,7 +830,7 @@ constexpr int TN_THREADS = 416;   // + warp 12: MMA issuer and TMEM owner
 template <class Epi>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int M, int N, int64_t K,
-               int64_t k_chunk, Epi epi, float* __restrict__ colsum_a) {
+               int64_t k_chunk, Epi epi, float* __restrict__ colsum_a, int t128) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -868,10 +868,11 @@ gemm_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict
       uint8_t* st = smem + s * stage_bytes;
       const int64_t k0 = kb + (int64_t)ks * BK;
       if (warp < 4) {
-        if (do_csum) stage_block_t<true>(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec, csum);
-        else stage_block_t(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec);
+        if (do_csum) stage_block_t<true>(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec, csum, t128 != 0);
+        else stage_block_t(A, lda, m0, M, 32 * warp, BM, k0, ke, st, st + A_HALF_BYTES, lane, a_vec, nullptr, t128 != 0);
       } else if (32 * (warp - 4) < rows_b) {
-        stage_block_t(B, ldb, n0, N, 32 * (warp - 4), rows_b, k0, ke, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, lane, b_vec);
+        stage_block_t(B, ldb, n0, N, 32 * (warp - 4), rows_b, k0, ke, st + 2 * A_HALF_BYTES, st + 2 * A_HALF_BYTES + b_half_bytes, lane, b_vec,
+                      nullptr, t128 != 0);
       }
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
@@ -1003,7 +1004,7 @@ static inline int gemm_w(const float* A, int64_t lda, int64_t M, int N, int K, c
 
 template <class Epi>
 static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K, const Epi& epi,
-                          cudaStream_t st, int split_k, float* colsum_a = nullptr) {
+                          cudaStream_t st, int split_k, float* colsum_a = nullptr, bool t128 = false) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   int64_t k_chunk = round_up(cdiv(K, split_k < 1 ? 1 : split_k), BK);
   int splits = (int)cdiv(K, k_chunk);
@@ -1015,7 +1016,7 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, 256), (unsigned)splits);
   LaunchTimer lt_(FAM_TC_WGRAD, st);
-  gemm_tn_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi, colsum_a);
+  gemm_tn_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(A, lda, B, ldb, M, N, K, k_chunk, epi, colsum_a, t128 ? 1 : 0);
   NUDF_LAUNCH_OK();
   return 0;
 }

@@ -77,6 +77,7 @@ struct ChainStep {
   int K, N;                  // GEMM: logical contraction / output widths (N = 0: no GEMM in this step)
   int n_kslices, n_tiles;    // of the GEMM
   int rows_override;         // > 0: fetch / multiply only this many weight rows of tile 0 (value-only last layer)
+  int img_N;                 // N the weight image was laid out for (differs from N only in the value-only last layer)
   int n_main;                // REV / BWD: output columns that continue the chain
   int n_next;                // width of the operand this step produces for the next GEMM (0: none)
   int sync_before;           // 1: the step starts with a barrier of the epilogue warps (reads state other threads wrote)
@@ -96,6 +97,7 @@ struct ChainParams {
   const uint16_t* img;
   const float* pts; int64_t P; float scale; int n_freq, d_pe;
   const float* gbar;                     // T chain: upstream gradient of grad_x udf [P,3]
+  int t128;                              // 1: every [P, ld] tensor of the steps is stored in the T128 layout (common.cuh)
   float* udf_out; float inv_scale;       // value-only mode: udf_out[P] = |y_0| / scale
   long long* trace;                      // profiling aid (NUDF_CHAIN_TRACE=n): clock64() stamps of CTA 0, first point tile
 };
@@ -262,9 +264,25 @@ __device__ __forceinline__ void slice8(const float* a, float inv, uint4& p0, uin
   p0 = make_uint4(o0[0], o0[1], o0[2], o0[3]);
   p1 = make_uint4(o1[0], o1[1], o1[2], o1[3]);
 }
-// 16 consecutive floats of one row of a [P, ld] tensor (columns c .. c+15, `nv` of them valid); 16-byte accesses when aligned.
+// 16 consecutive floats of one row of a [P, ld] tensor (columns c .. c+15, c % 16 == 0, `nv` of them valid); 16-byte accesses.
 // Plain (coherent) loads: tensors written earlier by this very kernel are read here (F -> R, T -> B hand-offs).
-__device__ __forceinline__ void ld_row16(const float* base, int64_t ld, int64_t row, int c, int nv, float v[16]) {
+// t128: T128 layout (common.cuh) -- lanes = consecutive rows => every access instruction of a warp is contiguous.
+__device__ __forceinline__ void ld_row16(const float* base, int64_t ld, int64_t row, int c, int nv, bool t128, float v[16]) {
+  if (t128) {
+    const float* q = base + t128_off(row, c, ld);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * i < nv) t = *reinterpret_cast<const float4*>(q + (int64_t)i * 512);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+    if (nv < 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j >= nv) v[j] = 0.f;
+    }
+    return;
+  }
   const float* q = base + row * ld + c;
   if (nv >= 16 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0) {
 #pragma unroll
@@ -277,7 +295,16 @@ __device__ __forceinline__ void ld_row16(const float* base, int64_t ld, int64_t 
     for (int j = 0; j < 16; ++j) v[j] = j < nv ? q[j] : 0.f;
   }
 }
-__device__ __forceinline__ void st_row16(float* base, int64_t ld, int64_t row, int c, int nv, const float v[16]) {
+// store; in the T128 layout whole 4-column groups are written (values beyond nv must already be zero: they land in the
+// tensor's own padding columns, nv <= ld - c)
+__device__ __forceinline__ void st_row16(float* base, int64_t ld, int64_t row, int c, int nv, bool t128, const float v[16]) {
+  if (t128) {
+    float* q = base + t128_off(row, c, ld);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (4 * i < nv) *reinterpret_cast<float4*>(q + (int64_t)i * 512) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return;
+  }
   float* q = base + row * ld + c;
   if (nv >= 16 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15u) == 0) {
 #pragma unroll
@@ -311,14 +338,15 @@ __device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams
                                            const float* z, const float* bv, const float* pe, float sgn_scaled, bool do_store,
                                            float nx[16]) {
   const int kind = S.kind;
+  const bool T = p.t128 != 0;
   if (kind == ST_PE || kind == ST_EDOT) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.n_next) ? pe[col0 + j] : 0.f;
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.ld_out0) st_row16(S.out0, S.ld_out0, row, col0, S.ld_out0 - col0, nx);
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.ld_out0) st_row16(S.out0, S.ld_out0, row, col0, S.ld_out0 - col0, T, nx);
     return;
   }
   if (kind == ST_LOAD) {
-    if (row_ok && col0 < S.n_next) ld_row16(S.in0, S.ld_in0, row, col0, S.n_next - col0, nx);
+    if (row_ok && col0 < S.n_next) ld_row16(S.in0, S.ld_in0, row, col0, S.n_next - col0, T, nx);
     else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) nx[j] = 0.f;
@@ -335,34 +363,34 @@ __device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams
       else if (col < S.n_next) a = pe[col - n_valid] * S.post_scale;
       nx[j] = a;
     }
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_next) st_row16(S.out0, S.ld_out0, row, col0, S.n_next - col0, nx);
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_next) st_row16(S.out0, S.ld_out0, row, col0, S.n_next - col0, T, nx);
     return;
   }
   if (kind == ST_FWD_LAST) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.N) ? z[j] + bv[j] : 0.f;
     if (do_store && row_ok) {
-      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, nx);
+      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, T, nx);
       if (p.udf_out != nullptr && col0 == 0) p.udf_out[row] = fabsf(nx[0]) * p.inv_scale;
     }
     return;
   }
   if (kind == ST_REV_FINAL) {
     float g[16];
-    if (S.in1 != nullptr && row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, g);
+    if (S.in1 != nullptr && row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, T, g);
     else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) g[j] = 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.N) ? z[j] + g[j] : 0.f;
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, nx);
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, T, nx);
     return;
   }
   // the remaining kinds recover S = sigma(100 z_prev) from the stored softplus output in0 (= A of the right layer)
   float a[16];
   const int n_act = (kind == ST_TAN) ? S.N : S.n_main;           // columns that have an activation behind them
-  if (row_ok && col0 < n_act) ld_row16(S.in0, S.ld_in0, row, col0, n_act - col0, a);
+  if (row_ok && col0 < n_act) ld_row16(S.in0, S.ld_in0, row, col0, n_act - col0, T, a);
   else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[j] = 0.f;
@@ -378,12 +406,12 @@ __device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams
       nx[j] = (col < S.n_main) ? gp[j] * sig_from_softplus(a[j] * S.a_unscale) : 0.f;
     }
     if (do_store && row_ok) {
-      if (S.out0 != nullptr && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, nx);
+      if (S.out0 != nullptr && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, T, nx);
       if (S.out1 != nullptr && kind == ST_REV && col0 + 16 > S.n_main && col0 < S.N) {       // skip layer: columns >= n_main go to Gpe
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = col0 + j;
-          if (col >= S.n_main && col < S.N) S.out1[row * S.ld_out1 + (col - S.n_main)] = gp[j];
+          if (col >= S.n_main && col < S.N) S.out1[mat_off(T, row, col - S.n_main, S.ld_out1)] = gp[j];
         }
       }
     }
@@ -391,7 +419,7 @@ __device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams
   }
   if (kind == ST_TAN) {
     float d[16], q[16];
-    if (row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, d);
+    if (row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, T, d);
     else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) d[j] = 0.f;
@@ -411,15 +439,15 @@ __device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams
       nx[j] = n;
     }
     if (do_store && row_ok) {
-      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, q);
-      if (S.out1 != nullptr && col0 < S.n_main) st_row16(S.out1, S.ld_out1, row, col0, S.n_main - col0, nx);
+      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, T, q);
+      if (S.out1 != nullptr && col0 < S.n_main) st_row16(S.out1, S.ld_out1, row, col0, S.n_main - col0, T, nx);
     }
     return;
   }
   // ST_BWD
   {
     float q[16];
-    if (row_ok && col0 < S.n_main) ld_row16(S.in1, S.ld_in1, row, col0, S.n_main - col0, q);
+    if (row_ok && col0 < S.n_main) ld_row16(S.in1, S.ld_in1, row, col0, S.n_main - col0, T, q);
     else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) q[j] = 0.f;
@@ -432,7 +460,7 @@ __device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams
       if (S.rowv != nullptr && col < S.n_main) ab = fmaf(rz, __ldg(S.vec0 + col), ab);
       nx[j] = (col < S.n_main) ? ab * S.post_scale * sig_from_softplus(a[j] * S.a_unscale) + q[j] : 0.f;
     }
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, nx);
+    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, T, nx);
   }
 }
 
@@ -684,10 +712,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
         for (int l = 0; l < p.n_steps; ++l) {
           const ChainStep& S = p.S[l];
           for (int t = 0; t < S.n_tiles; ++t) {
-            const int rows_full = ch_tile_rows(S.N, t);
+            const int rows_full = ch_tile_rows(S.img_N, t);
             const uint32_t rows = (uint32_t)(S.rows_override > 0 ? S.rows_override : rows_full);
             const uint32_t bytes = rows * 128u;
-            const uint16_t* tile = p.img + S.img_off + ch_tile_off(S.N, S.K, t);
+            const uint16_t* tile = p.img + S.img_off + ch_tile_off(S.img_N, S.K, t);
             for (int s = 0; s < S.n_kslices; ++s, ++wcnt) {
               const uint32_t ws = wcnt % CH_NSLOT, wu = wcnt / CH_NSLOT;
               mbar_wait(&ctl->w_empty[ws], (wu & 1u) ^ 1u);

@@ -93,8 +93,14 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
 
 // Which chains run as fused kernels (udf_chain.cuh).  Like the engine and the chain mask these must not change between a
 // forward call and its backward (context / scratch layouts and the folded images depend on them).
-static inline bool fused_fr_on(const UdfPlan& p) { return p.chain_ok && tc_on(TC_FWD) && tc_on(TC_REV) && !chain_planes_on(); }
-static inline bool fused_tb_on(const UdfPlan& p) { return p.chain_tb_ok && tc_on(TC_TAN) && tc_on(TC_BWD) && !chain_planes_on(); }
+// fused_on: F + R and T + B run as fused kernels and every context / scratch tensor they exchange (and the weight-gradient
+// kernels read) is stored in the T128 layout (common.cuh).
+static inline bool fused_on(const UdfPlan& p) {
+  return p.chain_tb_ok && tc_on(TC_FWD) && tc_on(TC_REV) && tc_on(TC_TAN) && tc_on(TC_BWD) && tc_on(TC_WGRAD) && !chain_planes_on();
+}
+static inline bool fused_fr_on(const UdfPlan& p) { return fused_on(p); }
+static inline bool fused_tb_on(const UdfPlan& p) { return fused_on(p); }
+static inline int64_t ctx_rows(const UdfPlan& p, int64_t P) { return fused_on(p) ? round_up(P, 128) : P; }
 
 // ---- context / scratch layout (all offsets in floats; every block starts 16B-aligned) -------------------------
 struct UdfCtx {
@@ -107,7 +113,8 @@ static inline uint16_t* plane_area(float* base, int64_t off) {
   return reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(base + off) + 1023) & ~(uintptr_t)1023);
 }
 static inline int cb_of(int cols) { return (cols + 63) / 64; }
-static void ctx_layout(const UdfPlan& p, int64_t P, int with_grad, UdfCtx* c) {
+static void ctx_layout(const UdfPlan& p, int64_t P_, int with_grad, UdfCtx* c) {
+  const int64_t P = ctx_rows(p, P_);            // T128 tensors are stored in whole 128-row tiles
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
   c->e0 = take(P * p.pe_ld);
@@ -133,7 +140,8 @@ struct UdfScratch {
   int64_t adot_l[NUDF_MAX_LAYERS];           // fused T chain: Adot[l], l = 1..last, all kept for the weight gradients
   int64_t pl_off, adpl[NUDF_MAX_LAYERS];     // plane mode: Adot[l] (input of layer l of the tangent chain)
 };
-static void scratch_layout(const UdfPlan& p, int64_t P, UdfScratch* s) {
+static void scratch_layout(const UdfPlan& p, int64_t P_, UdfScratch* s) {
+  const int64_t P = ctx_rows(p, P_);
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
   s->edot = take(P * p.pe_ld);
@@ -233,12 +241,12 @@ __global__ void pe_forward_kernel(const float* __restrict__ pts, int64_t P, int 
 
 // out = cat(|y0|/scale, y[1:]); sgn = sign(y0)
 __global__ void udf_finalize_kernel(const float* __restrict__ y, int y_ld, int d_out, int64_t P, float inv_scale,
-                                    float* __restrict__ out, int64_t ld_out, float* __restrict__ sgn) {
+                                    float* __restrict__ out, int64_t ld_out, float* __restrict__ sgn, int t128) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t row = idx / d_out;
   int c = (int)(idx - row * d_out);
   if (row >= P) return;
-  float v = y[row * y_ld + c];
+  float v = y[mat_off(t128 != 0, row, c, y_ld)];
   if (c == 0) {
     if (sgn) sgn[row] = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
     v = fabsf(v) * inv_scale;
@@ -269,10 +277,12 @@ __global__ void rev_init_kernel(const float* __restrict__ sgn, const float* __re
 
 // grad_x = scale * J_e(x)^T Ge
 __global__ void pe_vjp_kernel(const float* __restrict__ pts, const float* __restrict__ ge, int pe_ld, int64_t P, int L,
-                              float scale, float* __restrict__ grad) {
+                              float scale, float* __restrict__ grad, int t128 = 0) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  const float* g = ge + i * pe_ld;
+  float g[3 * (1 + 2 * 16)];
+  const int d_pe_ = 3 * (1 + 2 * L);
+  for (int c = 0; c < d_pe_; ++c) g[c] = ge[mat_off(t128 != 0, i, c, pe_ld)];
   float f = 1.0f;
   float acc[3] = {g[0], g[1], g[2]};
   float x[3] = {pts[i * 3 + 0] * scale, pts[i * 3 + 1] * scale, pts[i * 3 + 2] * scale};
@@ -326,14 +336,14 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int64_t lds, flo
 
 // out[c] (+)= sum_rows w[row] * X[row, c]   (w may be null = 1).  grid: (col tiles of 32, row chunks)
 __global__ void weighted_colsum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, float wscale,
-                                       int64_t P, int N, int64_t rows_per_block, float* __restrict__ out) {
+                                       int64_t P, int N, int64_t rows_per_block, float* __restrict__ out, int t128) {
   int c = blockIdx.x * 32 + (threadIdx.x & 31);
   int ry = threadIdx.x >> 5;  // 0..7
   int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   int64_t r1 = r0 + rows_per_block < P ? r0 + rows_per_block : P;
   float acc = 0.f;
   if (c < N)
-    for (int64_t r = r0 + ry; r < r1; r += 8) acc += (w ? w[r] * wscale : 1.f) * X[r * ldx + c];
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += (w ? w[r] * wscale : 1.f) * X[mat_off(t128 != 0, r, c, ldx)];
   __shared__ float red[8][33];
   red[ry][threadIdx.x & 31] = acc;
   __syncthreads();
@@ -345,11 +355,11 @@ __global__ void weighted_colsum_kernel(const float* __restrict__ X, int64_t ldx,
   }
 }
 
-int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st) {
+int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P, int N, float* out, cudaStream_t st, bool t128) {
   if (P <= 0 || N <= 0) return 0;
   int64_t rpb = 512;
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(P, rpb));
-  weighted_colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, w, wscale, P, N, rpb, out);
+  weighted_colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, w, wscale, P, N, rpb, out, t128 ? 1 : 0);
   NUDF_LAUNCH_OK();
   return 0;
 }
@@ -371,14 +381,14 @@ __global__ void zlast_kernel(const float* __restrict__ ob, int64_t ld_ob, const 
 
 // Same, split: zf[:, j] = ob[:, 1 + j] (features, ld = F) and z0 = sgn * ob[:, 0] / scale (udf head)
 __global__ void zlast_split_kernel(const float* __restrict__ ob, int64_t ld_ob, const float* __restrict__ sgn, float inv_scale,
-                                   int F, int64_t P, float* __restrict__ zf, float* __restrict__ z0) {
+                                   int F, int64_t P, float* __restrict__ zf, float* __restrict__ z0, int t128 = 0) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t row = idx / (F + 1);
   int c = (int)(idx - row * (F + 1));
   if (row >= P) return;
   float v = ob[row * ld_ob + c];
   if (c == 0) z0[row] = v * sgn[row] * inv_scale;
-  else zf[row * F + (c - 1)] = v;
+  else zf[mat_off(t128 != 0, row, c - 1, F)] = v;
 }
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)cdiv(n, t); }
@@ -446,7 +456,7 @@ static chain::ChainStep* add_step(chain::ChainParams* cp, int kind) {
 }
 static void set_gemm(chain::ChainStep* S, const UdfPlan& p, const float* wfold, int layer, int K, int N, int64_t img_off) {
   const float* tab = wfold + p.w_total + p.img_total / 2;
-  S->K = K; S->N = N;
+  S->K = K; S->N = N; S->img_N = N;
   S->n_kslices = tc::pad64(K) / 64;
   S->n_tiles = chain::ch_n_tiles(N);
   S->img_off = (uint32_t)img_off;
@@ -457,6 +467,7 @@ static void chain_common(const UdfPlan& p, const float* wfold, const float* pts,
   cp->img = img_base(p, wfold);
   cp->pts = pts; cp->P = P; cp->scale = p.scale; cp->n_freq = p.L; cp->d_pe = p.d_pe;
   cp->gbar = nullptr;
+  cp->t128 = fused_on(p) ? 1 : 0;
   cp->udf_out = nullptr; cp->inv_scale = 1.0f / p.scale;
   cp->trace = nullptr;
 }
@@ -484,7 +495,7 @@ static void build_forward(const UdfPlan& p, const float* wfold, const float* pts
   S = add_step(cp, chain::ST_FWD_LAST);
   set_gemm(S, p, wfold, last, p.in_dim[last], value_only ? 1 : p.out_dim[last], p.img_chain[last]);
   S->bias = tab + p.sb_off[last] + 4;
-  if (value_only) S->rows_override = 16;
+  if (value_only) { S->rows_override = 16; S->img_N = p.out_dim[last]; }
   else { S->out0 = ctx + c->y; S->ld_out0 = p.y_ld; }
   if (!with_rev) return;
   auto rev_common = [&](chain::ChainStep* R, int l) {       // epilogue that turns G (w.r.t. A[l]) into D[l-1]
@@ -720,15 +731,15 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
     build_forward(p, wfold, pts, P, ctx, &c, nullptr, true, &cp);
     if (int rc = chain::launch_chain(cp, FAM_UDF_FWD_CHAIN, st)) return rc;
     udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
-                                                                ctx + c.sgn);
+                                                                ctx + c.sgn, 1);
     NUDF_LAUNCH_OK();
-    pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad);
+    pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad, 1);
     NUDF_LAUNCH_OK();
     return 0;
   }
   if (int rc = value_chain(p, d, wfold, pts, P, ctx, c, st)) return rc;
   udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
-                                                              ctx + c.sgn);
+                                                              ctx + c.sgn, fused_on(p) ? 1 : 0);
   NUDF_LAUNCH_OK();
   if (grad) return reverse_chain(p, wfold, pts, P, ctx, c, grad, st);
   return 0;
@@ -782,16 +793,16 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
     // ---- tangent + backward chains of every 128-point tile in ONE launch (udf_chain.cuh), then the weight gradients ----
     const int F = p.d_out - 1;
     float* zf = scratch + s.zlast;                  // [P, F] feature part of the upstream gradient of the last layer
-    float* z0 = zf + P * F;                         // [P]    udf-head part, times sgn / scale
+    float* z0 = zf + ctx_rows(p, P) * F;            // [P]    udf-head part, times sgn / scale
     if (out_bar) {
-      zlast_split_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
+      zlast_split_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0, 1);
       NUDF_LAUNCH_OK();
     } else {
-      NUDF_CUDA_OK(cudaMemsetAsync(zf, 0, sizeof(float) * P * (F + 1), st));
+      NUDF_CUDA_OK(cudaMemsetAsync(zf, 0, sizeof(float) * (ctx_rows(p, P) * F + P), st));
     }
     const bool with_t = grad_bar != nullptr;
     if (!with_t)
-      for (int l = 0; l < last; ++l) NUDF_CUDA_OK(cudaMemsetAsync(scratch + s.q[l], 0, sizeof(float) * P * p.o_ld[l], st));
+      for (int l = 0; l < last; ++l) NUDF_CUDA_OK(cudaMemsetAsync(scratch + s.q[l], 0, sizeof(float) * ctx_rows(p, P) * p.o_ld[l], st));
     {
       chain::ChainParams cp;
       build_backward(p, wfold, pts, P, grad_bar, ctx, c, scratch, s, zf, z0, with_t, &cp);
@@ -802,25 +813,25 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
         const float* adot = l == 0 ? scratch + s.edot : scratch + s.adot_l[l];
         const int64_t ld_adot = l == 0 ? p.pe_ld : p.a_ld[l];
         EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
-        if (int rc = gemm_tn(ctx + c.d[l], p.o_ld[l], adot, ld_adot, p.out_dim[l], p.in_dim[l], P, ew, st, split)) return rc;
+        if (int rc = gemm_tn(ctx + c.d[l], p.o_ld[l], adot, ld_adot, p.out_dim[l], p.in_dim[l], P, ew, st, split, TC_WGRAD, nullptr, true)) return rc;
       }
       // g_last = W_last^T d_last with d_last = (sgn/scale) e_0  =>  dW_last[0,:] += sum_p (sgn/scale) Adot_last
-      if (int rc = colsum(scratch + s.adot_l[last], p.a_ld[last], ctx + c.sgn, 1.0f / p.scale, P, p.in_dim[last], dwfold + p.w_off[last], st))
+      if (int rc = colsum(scratch + s.adot_l[last], p.a_ld[last], ctx + c.sgn, 1.0f / p.scale, P, p.in_dim[last], dwfold + p.w_off[last], st, true))
         return rc;
     }
     if (out_bar) {
       float* dWl = dwfold + p.w_off[last];
       EpiAtomicAdd ew{dWl + p.w_ld[last], p.w_ld[last]};
-      if (int rc = gemm_tn(zf, F, ctx + c.a[last], p.a_ld[last], F, p.in_dim[last], P, ew, st, split, TC_WGRAD, dbias + p.b_off[last] + 1))
+      if (int rc = gemm_tn(zf, F, ctx + c.a[last], p.a_ld[last], F, p.in_dim[last], P, ew, st, split, TC_WGRAD, dbias + p.b_off[last] + 1, true))
         return rc;
-      if (int rc = colsum(ctx + c.a[last], p.a_ld[last], z0, 1.0f, P, p.in_dim[last], dWl, st)) return rc;
+      if (int rc = colsum(ctx + c.a[last], p.a_ld[last], z0, 1.0f, P, p.in_dim[last], dWl, st, true)) return rc;
       if (int rc = colsum(z0, 1, nullptr, 1.0f, P, 1, dbias + p.b_off[last], st)) return rc;
     }
     for (int l = last - 1; l >= 0; --l) {           // dW_l += Zbar_l^T A_l, db_l = column sums of Zbar_l
       const float* A = l == 0 ? ctx + c.e0 : ctx + c.a[l];
       const int64_t lda = l == 0 ? p.pe_ld : p.a_ld[l];
       EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
-      if (int rc = gemm_tn(scratch + s.q[l], p.o_ld[l], A, lda, p.out_dim[l], p.in_dim[l], P, ew, st, split, TC_WGRAD, dbias + p.b_off[l])) return rc;
+      if (int rc = gemm_tn(scratch + s.q[l], p.o_ld[l], A, lda, p.out_dim[l], p.in_dim[l], P, ew, st, split, TC_WGRAD, dbias + p.b_off[l], true)) return rc;
     }
     return 0;
   }

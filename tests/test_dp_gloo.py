@@ -56,3 +56,74 @@ def test_ray_sharding_and_gradient_allreduce_world2():
     for r in range(world):
         assert torch.allclose(out[r][1], expect_w)
         assert torch.allclose(out[r][2], torch.full((3,), 1.5))
+
+
+class _FakeHandle:
+    """stands in for ops.UdfHandle on the CPU: parameters, the bucket layout the library wants, and a backward that writes
+    its gradients straight into the sink views the way ops._UdfFunction.backward does"""
+
+    def __init__(self, params):
+        self.ps = params
+        self.grad_sink = None
+
+    def sink_layout(self):
+        return [[self.ps[2]], [self.ps[0], self.ps[1]]]          # biases first, then the rest
+
+    def backward(self, values):
+        sink = self.grad_sink if (self.grad_sink is not None and self.grad_sink.begin()) else None
+        outs = []
+        for p, v in zip(self.ps, values):
+            g = sink.view(p) if sink is not None else torch.empty_like(p)
+            g.copy_(v)                                            # "kernel" writes in place
+            outs.append(g)
+        if sink is not None:
+            sink.ready()
+        for p, g in zip(self.ps, outs):                           # what autograd's AccumulateGrad does with a fresh gradient
+            p.grad = g if p.grad is None else p.grad + g
+
+
+class _FakeModule:
+    def __init__(self, h):
+        self._handle = h
+
+
+def _sink_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from neuraludf_b200 import dp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))]
+    b = [torch.nn.Parameter(torch.zeros(2, 2)), torch.nn.Parameter(torch.zeros(1)), torch.nn.Parameter(torch.zeros(2))]
+    loose = torch.nn.Parameter(torch.zeros(1))
+    ha, hb = _FakeHandle(a), _FakeHandle(b)
+    bucket = dp.GradBucket(a + b + [loose], modules=[_FakeModule(ha), _FakeModule(hb)], overlap=True)
+    assert bucket.flat.numel() == 6 + 4 + 3 + 4 + 1 + 2 + 1 and len(bucket.regions) == 2
+    res = []
+    for step in range(2):                                         # two steps: the regions must re-arm after zero_grad
+        for p in a + b + [loose]:
+            p.grad = None
+        hb.backward([torch.full_like(p, float(rank + 1 + step)) for p in b])     # colour-net-like region first (async)
+        ha.backward([torch.full_like(p, float(10 * (rank + 1))) for p in a])
+        loose.grad = torch.full((1,), float(rank))
+        # gradients must live inside the flat bucket (no pack / unpack copies)
+        assert a[0].grad.data_ptr() >= bucket.flat.data_ptr()
+        assert a[0].grad.data_ptr() < bucket.flat.data_ptr() + 4 * bucket.flat.numel()
+        bucket.allreduce_mean()
+        res.append((a[0].grad.clone(), b[2].grad.clone(), loose.grad.clone()))
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_gradient_sinks_allreduce_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sink_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        for step in range(2):
+            ga, gb, gl = out[r][step]
+            assert torch.allclose(ga, torch.full((3, 2), 15.0))                  # mean of 10 and 20
+            assert torch.allclose(gb, torch.full((2,), 1.5 + step))              # mean of (1 + step) and (2 + step)
+            assert torch.allclose(gl, torch.full((1,), 0.5))

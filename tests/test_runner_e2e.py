@@ -24,6 +24,11 @@ import sys
 sys.path.insert(0, {root!r})
 from tests import runner_env
 runner_env.install_stubs()
+import torch
+_load = torch.load
+# the reference targets torch 2.0: its checkpoints hold numpy scalars (`iter_step`, learning rates), which torch >= 2.6 refuses
+# under the new `weights_only=True` default of torch.load -- restore the old default for the runner's own load_checkpoint
+torch.load = lambda *a, **k: _load(*a, **dict(dict(weights_only=False), **k))
 from neuraludf_b200 import launch
 try:
     rc = launch.main({argv!r})
@@ -66,7 +71,7 @@ def test_unmodified_runner_trains_checkpoints_and_validates(tmp_path):
     exp_dir = os.path.join(tmp, "exp", "synth", "udf_dtu")
     ck = sorted(glob.glob(os.path.join(exp_dir, "checkpoints", "ckpt_*.pth")))
     assert [os.path.basename(c) for c in ck] == ["ckpt_000002.pth", "ckpt_000004.pth"], tail
-    sd = torch.load(ck[-1], map_location="cpu")
+    sd = torch.load(ck[-1], map_location="cpu", weights_only=False)
     assert sd["iter_step"] == 4
     assert set(sd) == {"nerf", "udf_network_fine", "variance_network_fine", "color_network_fine", "beta_network", "optimizer",
                        "iter_step"}
@@ -74,7 +79,7 @@ def test_unmodified_runner_trains_checkpoints_and_validates(tmp_path):
     assert "lin_base0.weight_g" in sd["color_network_fine"] and "pts_linears.5.weight" in sd["nerf"]
     assert all(torch.isfinite(v).all() for v in sd["udf_network_fine"].values())
     # the step changed the parameters (Adam ran on our gradients)
-    sd2 = torch.load(ck[0], map_location="cpu")
+    sd2 = torch.load(ck[0], map_location="cpu", weights_only=False)
     assert not torch.equal(sd["udf_network_fine"]["lin4.weight_v"], sd2["udf_network_fine"]["lin4.weight_v"])
     # validate() at iteration 3 wrote its images (exp_runner_blending.py:604-719)
     imgs = glob.glob(os.path.join(exp_dir, "**", "*.png"), recursive=True)
