@@ -401,13 +401,13 @@ __device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams
     for (int j = 0; j < 16; ++j) {
       const int col = col0 + j;
       float raw = z[j];
-      if (kind == ST_REV_SEED) raw = (col < S.n_main) ? sgn_scaled * __ldg(S.vec0 + col) : 0.f;
+      if (kind == ST_REV_SEED) raw = (col < S.N) ? sgn_scaled * __ldg(S.vec0 + col) : 0.f;   // S.N = width of the last layer's input
       gp[j] = raw * S.post_scale;
       nx[j] = (col < S.n_main) ? gp[j] * sig_from_softplus(a[j] * S.a_unscale) : 0.f;
     }
     if (do_store && row_ok) {
       if (S.out0 != nullptr && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, T, nx);
-      if (S.out1 != nullptr && kind == ST_REV && col0 + 16 > S.n_main && col0 < S.N) {       // skip layer: columns >= n_main go to Gpe
+      if (S.out1 != nullptr && col0 + 16 > S.n_main && col0 < S.N) {       // skip layer: columns >= n_main are the gradient w.r.t. PE
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = col0 + j;

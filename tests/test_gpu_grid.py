@@ -37,7 +37,14 @@ def test_grid_and_near_surface_cells_match_reference(golden):
         return g / (torch.linalg.norm(g, ord=2, dim=-1, keepdim=True) + 1e-5)
 
     em = _ref_extract_mesh()
-    df_ref, vec_ref, samples_ref = em.get_udf_normals_grid_slow(func, func_grad, N=N, max_batch=1 << 14)
+    # the reference mixes device-less tensors with .cuda() results and relies on the runner's global default
+    # (exp_runner_blending.py:872)
+    torch.set_default_tensor_type("torch.cuda.FloatTensor")
+    try:
+        df_ref, vec_ref, samples_ref = em.get_udf_normals_grid_slow(func, func_grad, N=N, max_batch=1 << 14)
+    finally:
+        torch.set_default_tensor_type("torch.FloatTensor")
+    df_ref, vec_ref, samples_ref = df_ref.cpu(), vec_ref.cpu(), samples_ref.cpu()
     df, vec, samples = grid.get_udf_normals_grid_slow(udf, N=N, max_batch=1 << 15)
     assert df.shape == df_ref.shape and vec.shape == vec_ref.shape and samples.shape == samples_ref.shape
     assert float((samples[:, :3] - samples_ref[:, :3]).abs().max()) < 1e-6          # lattice coordinates

@@ -78,9 +78,12 @@ def test_unmodified_runner_trains_checkpoints_and_validates(tmp_path):
     assert "lin8.weight_v" in sd["udf_network_fine"] and sd["udf_network_fine"]["lin8.weight_v"].shape == (257, 256)
     assert "lin_base0.weight_g" in sd["color_network_fine"] and "pts_linears.5.weight" in sd["nerf"]
     assert all(torch.isfinite(v).all() for v in sd["udf_network_fine"].values())
-    # the step changed the parameters (Adam ran on our gradients)
+    # the steps changed the parameters (Adam ran on our gradients).  The UDF network itself is frozen during the first
+    # `fix_geo_end` = 500 iterations (exp_runner_blending.py:80, 186-191), so look at the colour and NeRF++ networks
     sd2 = torch.load(ck[0], map_location="cpu", weights_only=False)
-    assert not torch.equal(sd["udf_network_fine"]["lin4.weight_v"], sd2["udf_network_fine"]["lin4.weight_v"])
+    assert not torch.equal(sd["color_network_fine"]["lin0.weight_v"], sd2["color_network_fine"]["lin0.weight_v"])
+    assert not torch.equal(sd["nerf"]["pts_linears.0.weight"], sd2["nerf"]["pts_linears.0.weight"])
+    assert torch.equal(sd["udf_network_fine"]["lin4.weight_v"], sd2["udf_network_fine"]["lin4.weight_v"])
     # validate() at iteration 3 wrote its images (exp_runner_blending.py:604-719)
     imgs = glob.glob(os.path.join(exp_dir, "**", "*.png"), recursive=True)
     assert len(imgs) >= 1, tail
