@@ -72,7 +72,11 @@ template <class Epi>
 static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int64_t K,
                           const Epi& epi, cudaStream_t st, int split_k, int chain = TC_WGRAD, float* colsum_a = nullptr,
                           bool t128 = false) {
-  if (t128 || (tc_on(chain) && M >= 32 && N >= 32 && K >= 128)) {
+  if (t128) {
+    const tc::TnPair pr{A, lda, B, ldb, colsum_a};
+    return tc::gemm_tn2(&pr, 1, M, N, K, epi, st);
+  }
+  if (tc_on(chain) && M >= 32 && N >= 32 && K >= 128) {
     // split the points so that (M tiles x N tiles x splits) fills the SMs once, with at least 8 slices of 64 points per CTA
     const int tiles = (int)(cdiv(M, 128) * cdiv(N, 256));
     int splits = tc::sm_count() / tiles;
@@ -84,6 +88,12 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
   if (int rc = gemm_simt<false, false, Epi>(A, lda, B, ldb, M, N, K, epi, st, split_k)) return rc;
   if (colsum_a != nullptr) return colsum(A, lda, nullptr, 1.f, K, M, colsum_a, st);
   return 0;
+}
+
+// T128 operands (fused UDF chains): up to two (A, B) pairs accumulate into the same C in one launch (tc::gemm_tn2)
+template <class Epi>
+static inline int gemm_tn_pairs(const tc::TnPair* pairs, int n_pairs, int M, int N, int64_t K, const Epi& epi, cudaStream_t st) {
+  return tc::gemm_tn2(pairs, n_pairs, M, N, K, epi, st);
 }
 
 }  // namespace nudf

@@ -1021,6 +1021,226 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradients from T128 operands (the tensors the fused UDF chains exchange, common.cuh), second generation:
+//     C[M x N] += sum over pairs p of  A_p[K x M]^T B_p[K x N]          (contraction over points, split over gridDim.z)
+// * up to two operand pairs per launch: the two contributions to one dW_l (D_l^T Adot_l from the tangent chain and Q_l^T A_l
+//   from the backward chain) share the TMEM accumulator and ONE split-K reduction;
+// * fp32 operands travel global -> shared with per-lane cp.async (LDGSTS, 16 B, zero-fill for pad rows) into a lane-private
+//   raw ring: the copies of slice i+1 are in flight while slice i is split to bf16 planes, no register staging;
+// * lane <-> point-pair mapping: a warp copy instruction covers 32 consecutive points x 4 features of two feature quads =
+//   two contiguous 512-byte runs of the T128 layout (every sector fully used);
+// * K is sliced by 32 points: the two halves (k < 32, k >= 32) of the K-major SWIZZLE_128B plane tile are the two pipeline
+//   stages, MMAs of one half overlap the split of the other.
+// warps 0-3 stage A (32 tile rows each), 4-11 stage B, all 12 run the split-K epilogue; warp 12 issues MMAs / owns TMEM.
+// ---------------------------------------------------------------------------------------------------------------
+struct TnPair {
+  const float* A; int64_t lda;
+  const float* B; int64_t ldb;
+  float* colsum_a;                 // optional: colsum_a[m] += sum_k A[k, m]  (bias gradient)
+};
+constexpr int T2_BK = 32;
+constexpr int T2_RING = 5;                                   // raw ring depth in half-slice granules (4 granules = 2 slices in flight)
+constexpr uint32_t T2_RAW_WARP = 32u * 64u;                  // 2 KB per granule: 4 x 16 B per lane
+constexpr uint32_t T2_RAW_GRAN = 12u * T2_RAW_WARP;          // 24 KB
+constexpr uint32_t T2_B_HALF = 256u * 128u;                  // fixed plane stride of the B tile (32 KB)
+constexpr uint32_t T2_PLANES = 2u * A_HALF_BYTES + 2u * T2_B_HALF;   // 96 KB
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// One granule = half a slice of one warp: 32 points x 16 of the warp's 32 columns.  Lane (rp = lane & 15, g2 = lane >> 4):
+// points k0 + 2 rp, k0 + 2 rp + 1; feature quads 4 half + 2 i + g2 (i = 0, 1).
+__device__ __forceinline__ void t2_issue(const float* __restrict__ X, int64_t ld, int col0, int half, int64_t k0, int64_t k_end,
+                                         uint32_t raw_lane, int lane) {
+  const int rp = lane & 15, g2 = lane >> 4;
+  const int64_t row = k0 + 2 * rp;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int col = col0 + 4 * (4 * half + 2 * i + g2);
+    const bool v0 = col < ld && row < k_end, v1 = col < ld && row + 1 < k_end;      // invalid: zero fill, source address unused
+    const float* src = X + (v0 ? t128_off(row, col, ld) : 0);
+    cp_async16(raw_lane + (uint32_t)(2 * i) * 512u, src, v0 ? 16u : 0u);
+    cp_async16(raw_lane + (uint32_t)(2 * i + 1) * 512u, v1 ? src + 4 : X, v1 ? 16u : 0u);
+  }
+}
+template <bool CSUM, int HALF>
+__device__ __forceinline__ void t2_convert(const uint8_t* raw_lane, uint8_t* s_hi, uint8_t* s_lo, int r0, int khalf, int lane, float* csum) {
+  const int rp = lane & 15, g2 = lane >> 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(raw_lane + (2 * i) * 512);
+    const float4 b = *reinterpret_cast<const float4*>(raw_lane + (2 * i + 1) * 512);
+    const float x0[4] = {a.x, a.y, a.z, a.w}, x1[4] = {b.x, b.y, b.z, b.w};
+    const int rbase = r0 + 4 * (4 * HALF + 2 * i + g2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t hi = pack_bf16(x0[j], x1[j]);
+      const uint32_t lo = pack_bf16(x0[j] - __uint_as_float(hi << 16), x1[j] - __uint_as_float(hi & 0xFFFF0000u));
+      const uint32_t off = sw128((uint32_t)(rbase + j), (uint32_t)(32 * khalf + 2 * rp));
+      *reinterpret_cast<uint32_t*>(s_hi + off) = hi;
+      *reinterpret_cast<uint32_t*>(s_lo + off) = lo;
+      if (CSUM) csum[8 * HALF + 4 * i + j] += x0[j] + x1[j];
+    }
+  }
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(TN_THREADS, 1)
+gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int64_t k_chunk, Epi epi) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * 256;
+  int rows_b = N - n0; rows_b = pad16(rows_b < 256 ? rows_b : 256);
+  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke = (kb + k_chunk < K) ? kb + k_chunk : K;
+  const int n_sl = (int)((ke - kb + T2_BK - 1) / T2_BK);       // slices per pair
+  const int total = n_sl * n_pairs;
+  uint8_t* planes = smem;                                       // [A hi | A lo | B hi | B lo]
+  uint8_t* raw = smem + T2_PLANES;                              // T2_RING granules x 12 warps x 2 KB
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + T2_PLANES + T2_RING * T2_RAW_GRAN);
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->full[s], TN_PROD); mbar_init(&ctl->empty[s], 1); }
+    mbar_init(&ctl->tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(&ctl->tmem_addr, tmem_cols_for(rows_b));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = ctl->tmem_addr;
+
+  if (warp < 12) {
+    const bool is_a = warp < 4;
+    const int r0 = is_a ? 32 * warp : 32 * (warp - 4);          // first tile row (= operand column) of this warp's block
+    const bool active = is_a || r0 < rows_b;
+    uint8_t* s_hi = planes + (is_a ? 0u : 2u * A_HALF_BYTES);
+    uint8_t* s_lo = s_hi + (is_a ? (uint32_t)A_HALF_BYTES : T2_B_HALF);
+    const uint8_t* raw_lane = raw + warp * T2_RAW_WARP + lane * 16;
+    const uint32_t raw_lane_s = smem_u32(raw_lane);
+    float csum[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) csum[j] = 0.f;
+    auto pair_of = [&](int i) -> const TnPair& { return i < n_sl ? p0 : p1; };
+    const int n_gran = 2 * total;
+    auto issue = [&](int h) {                                   // granule h = (slice h >> 1, half h & 1); always commits a group
+      if (active && h < n_gran) {
+        const int i = h >> 1;
+        const TnPair& pr = pair_of(i);
+        const int64_t k0 = kb + (int64_t)(i < n_sl ? i : i - n_sl) * T2_BK;
+        t2_issue(is_a ? pr.A : pr.B, is_a ? pr.lda : pr.ldb, (is_a ? m0 : n0) + r0, h & 1, k0, ke,
+                 raw_lane_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int h = 0; h < T2_RING - 1; ++h) issue(h);
+    for (int i = 0; i < total; ++i) {
+      const int s = i & 1;
+      const bool do_csum = is_a && blockIdx.y == 0 && pair_of(i).colsum_a != nullptr;
+      // half 0
+      issue(2 * i + T2_RING - 1);
+      cp_async_wait<T2_RING - 1>();
+      if (i >= 2) mbar_wait(&ctl->empty[s], (uint32_t)(((i >> 1) - 1) & 1));
+      if (active) {
+        const uint8_t* rl = raw_lane + (uint32_t)((2 * i) % T2_RING) * T2_RAW_GRAN;
+        if (do_csum) t2_convert<true, 0>(rl, s_hi, s_lo, r0, s, lane, csum);
+        else t2_convert<false, 0>(rl, s_hi, s_lo, r0, s, lane, csum);
+      }
+      // half 1
+      issue(2 * i + T2_RING);
+      cp_async_wait<T2_RING - 1>();
+      if (active) {
+        const uint8_t* rl = raw_lane + (uint32_t)((2 * i + 1) % T2_RING) * T2_RAW_GRAN;
+        if (do_csum) t2_convert<true, 1>(rl, s_hi, s_lo, r0, s, lane, csum);
+        else t2_convert<false, 1>(rl, s_hi, s_lo, r0, s, lane, csum);
+      }
+      fence_proxy_async();
+      mbar_arrive(&ctl->full[s]);
+      if (is_a && blockIdx.y == 0 && (i == n_sl - 1 || i == total - 1)) {       // end of a pair: flush its column sums
+        float* out = pair_of(i).colsum_a;
+        if (out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = csum[j];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            const int m = m0 + r0 + 4 * (2 * (j >> 2) + (lane >> 4)) + (j & 3);
+            if ((lane & 15) == 0 && m < M) atomicAdd(out + m, v);
+            csum[j] = 0.f;
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    if (total > 0) {
+      mbar_wait(&ctl->tmem_full, 0);
+      tcgen05_fence_after();
+      run_epilogue(tmem_base, warp & 3, lane, 32 * (warp >> 2), 96, 1, 0u, (int64_t)m0 + (warp & 3) * 32, (int64_t)M, n0, rows_b, N,
+                   reinterpret_cast<float*>(smem) + warp * EPI_WARP_FLOATS, epi, (int)blockIdx.z);
+      tcgen05_fence_before();
+    }
+  } else {
+    if (lane == 0 && total > 0) {
+      const uint32_t idesc = make_idesc((uint32_t)rows_b);
+      const uint32_t a_hi = smem_u32(planes), a_lo = a_hi + A_HALF_BYTES, b_hi = a_hi + 2u * A_HALF_BYTES, b_lo = b_hi + T2_B_HALF;
+      for (int i = 0; i < total; ++i) {
+        const int s = i & 1;
+        mbar_wait(&ctl->full[s], (uint32_t)((i >> 1) & 1));
+        tcgen05_fence_after();
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const uint32_t o = (uint32_t)(2 * s + jj) * 32u;
+          const uint64_t dah = make_desc(a_hi + o), dal = make_desc(a_lo + o), dbh = make_desc(b_hi + o), dbl = make_desc(b_lo + o);
+          mma_bf16(tmem_base, dal, dbh, idesc, (i == 0 && jj == 0) ? 0u : 1u);
+          mma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          mma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        }
+        mma_commit(&ctl->empty[s]);
+      }
+      mma_commit(&ctl->tmem_full);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols_for(rows_b));
+  }
+}
+
+template <class Epi>
+static inline int gemm_tn2(const TnPair* pairs, int n_pairs, int M, int N, int64_t K, const Epi& epi, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || n_pairs <= 0) return 0;
+  const int tiles = (int)(cdiv(M, BM) * cdiv(N, 256));
+  int splits = sm_count() / tiles;
+  const int max_splits = (int)cdiv(K, 256);                  // at least 8 slices of 32 points per CTA and pair
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int64_t k_chunk = round_up(cdiv(K, splits), T2_BK);
+  splits = (int)cdiv(K, k_chunk);
+  const size_t smem = (size_t)T2_PLANES + (size_t)T2_RING * T2_RAW_GRAN + sizeof(SmemCtl) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_tn2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, 256), (unsigned)splits);
+  LaunchTimer lt_(FAM_TC_WGRAD, st);
+  gemm_tn2_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(pairs[0], n_pairs > 1 ? pairs[1] : pairs[0], n_pairs > 1 ? 2 : 1, M, N, K, k_chunk, epi);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
 static inline int prep_weights(const float* W, int64_t ldw, int N, int K, int transposed, int np, uint16_t* img, cudaStream_t st) {
   int64_t total = 0;
   for (int t = 0; t < n_tiles(N, np); ++t) total += (int64_t)tile_rows(N, t, np) * pad64(K);

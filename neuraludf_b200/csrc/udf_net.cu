@@ -809,12 +809,6 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
       if (int rc = chain::launch_chain(cp, FAM_UDF_BWD_CHAIN, st)) return rc;
     }
     if (with_t) {
-      for (int l = 0; l < last; ++l) {              // dW_l += D_l^T Adot_l   (Adot_0 = Edot)
-        const float* adot = l == 0 ? scratch + s.edot : scratch + s.adot_l[l];
-        const int64_t ld_adot = l == 0 ? p.pe_ld : p.a_ld[l];
-        EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
-        if (int rc = gemm_tn(ctx + c.d[l], p.o_ld[l], adot, ld_adot, p.out_dim[l], p.in_dim[l], P, ew, st, split, TC_WGRAD, nullptr, true)) return rc;
-      }
       // g_last = W_last^T d_last with d_last = (sgn/scale) e_0  =>  dW_last[0,:] += sum_p (sgn/scale) Adot_last
       if (int rc = colsum(scratch + s.adot_l[last], p.a_ld[last], ctx + c.sgn, 1.0f / p.scale, P, p.in_dim[last], dwfold + p.w_off[last], st, true))
         return rc;
@@ -827,11 +821,15 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
       if (int rc = colsum(ctx + c.a[last], p.a_ld[last], z0, 1.0f, P, p.in_dim[last], dWl, st, true)) return rc;
       if (int rc = colsum(z0, 1, nullptr, 1.0f, P, 1, dbias + p.b_off[last], st)) return rc;
     }
-    for (int l = last - 1; l >= 0; --l) {           // dW_l += Zbar_l^T A_l, db_l = column sums of Zbar_l
-      const float* A = l == 0 ? ctx + c.e0 : ctx + c.a[l];
-      const int64_t lda = l == 0 ? p.pe_ld : p.a_ld[l];
+    // one launch per layer: dW_l += D_l^T Adot_l (tangent chain; Adot_0 = Edot)  +  Zbar_l^T A_l (backward chain), db_l = column
+    // sums of Zbar_l -- both contractions share the accumulator and the split-K reduction
+    for (int l = last - 1; l >= 0; --l) {
+      tc::TnPair pr[2];
+      int np = 0;
+      if (with_t) pr[np++] = tc::TnPair{ctx + c.d[l], p.o_ld[l], l == 0 ? scratch + s.edot : scratch + s.adot_l[l], l == 0 ? p.pe_ld : p.a_ld[l], nullptr};
+      pr[np++] = tc::TnPair{scratch + s.q[l], p.o_ld[l], l == 0 ? ctx + c.e0 : ctx + c.a[l], l == 0 ? p.pe_ld : p.a_ld[l], dbias + p.b_off[l]};
       EpiAtomicAdd ew{dwfold + p.w_off[l], p.w_ld[l]};
-      if (int rc = gemm_tn(scratch + s.q[l], p.o_ld[l], A, lda, p.out_dim[l], p.in_dim[l], P, ew, st, split, TC_WGRAD, dbias + p.b_off[l], true)) return rc;
+      if (int rc = gemm_tn_pairs(pr, np, p.out_dim[l], p.in_dim[l], P, ew, st)) return rc;
     }
     return 0;
   }
