@@ -1026,10 +1026,10 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
 //     C[M x N] += sum over pairs p of  A_p[K x M]^T B_p[K x N]          (contraction over points, split over gridDim.z)
 // * up to two operand pairs per launch: the two contributions to one dW_l (D_l^T Adot_l from the tangent chain and Q_l^T A_l
 //   from the backward chain) share the TMEM accumulator and ONE split-K reduction;
-// * fp32 operands travel global -> shared with per-lane cp.async (LDGSTS, 16 B, zero-fill for pad rows) into a lane-private
+// * fp32 operands travel global -> shared with per-lane cp.async (LDGSTS, 16 B, zero-fill for pad rows) into a warp-private
 //   raw ring: the copies of slice i+1 are in flight while slice i is split to bf16 planes, no register staging;
-// * lane <-> point-pair mapping: a warp copy instruction covers 32 consecutive points x 4 features of two feature quads =
-//   two contiguous 512-byte runs of the T128 layout (every sector fully used);
+// * a warp copy instruction covers 32 consecutive points x 4 features = 512 contiguous bytes of the T128 layout, every 32-byte
+//   sector requested once; the point-pair packing reads the raw tile back across lanes;
 // * K is sliced by 32 points: the two halves (k < 32, k >= 32) of the K-major SWIZZLE_128B plane tile are the two pipeline
 //   stages, MMAs of one half overlap the split of the other.
 // warps 0-3 stage A (32 tile rows each), 4-11 stage B, all 12 run the split-K epilogue; warp 12 issues MMAs / owns TMEM.
@@ -1053,30 +1053,31 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-// One granule = half a slice of one warp: 32 points x 16 of the warp's 32 columns.  Lane (rp = lane & 15, g2 = lane >> 4):
-// points k0 + 2 rp, k0 + 2 rp + 1; feature quads 4 half + 2 i + g2 (i = 0, 1).
+// One granule = half a slice of one warp: 32 points x 16 of the warp's 32 columns = 4 feature quads.  Copy: lane l moves point
+// k0 + l of each quad (16 B), so every warp instruction reads 512 contiguous bytes of the T128 layout -- each 32-byte sector
+// is requested exactly once (cp.async.cg bypasses L1: a mapping that splits a sector over two instructions fetches it twice
+// from L2).  Raw layout of a warp's granule: [quad][32 points][16 B].
 __device__ __forceinline__ void t2_issue(const float* __restrict__ X, int64_t ld, int col0, int half, int64_t k0, int64_t k_end,
-                                         uint32_t raw_lane, int lane) {
-  const int rp = lane & 15, g2 = lane >> 4;
-  const int64_t row = k0 + 2 * rp;
+                                         uint32_t raw_warp, int lane) {
+  const int64_t row = k0 + lane;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int col = col0 + 4 * (4 * half + 2 * i + g2);
-    const bool v0 = col < ld && row < k_end, v1 = col < ld && row + 1 < k_end;      // invalid: zero fill, source address unused
-    const float* src = X + (v0 ? t128_off(row, col, ld) : 0);
-    cp_async16(raw_lane + (uint32_t)(2 * i) * 512u, src, v0 ? 16u : 0u);
-    cp_async16(raw_lane + (uint32_t)(2 * i + 1) * 512u, v1 ? src + 4 : X, v1 ? 16u : 0u);
+  for (int q = 0; q < 4; ++q) {
+    const int col = col0 + 4 * (4 * half + q);
+    const bool v = col < ld && row < k_end;                      // invalid: zero fill, source address unused
+    cp_async16(raw_warp + (uint32_t)q * 512u + (uint32_t)lane * 16u, X + (v ? t128_off(row, col, ld) : 0), v ? 16u : 0u);
   }
 }
+// Split: lane (rp = lane & 15, g2 = lane >> 4) packs the point pair (2 rp, 2 rp + 1) of the quads g2 and g2 + 2.
 template <bool CSUM, int HALF>
-__device__ __forceinline__ void t2_convert(const uint8_t* raw_lane, uint8_t* s_hi, uint8_t* s_lo, int r0, int khalf, int lane, float* csum) {
+__device__ __forceinline__ void t2_convert(const uint8_t* raw_warp, uint8_t* s_hi, uint8_t* s_lo, int r0, int khalf, int lane, float* csum) {
   const int rp = lane & 15, g2 = lane >> 4;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const float4 a = *reinterpret_cast<const float4*>(raw_lane + (2 * i) * 512);
-    const float4 b = *reinterpret_cast<const float4*>(raw_lane + (2 * i + 1) * 512);
+    const int q = 2 * i + g2;
+    const float4 a = *reinterpret_cast<const float4*>(raw_warp + q * 512 + (2 * rp) * 16);
+    const float4 b = *reinterpret_cast<const float4*>(raw_warp + q * 512 + (2 * rp + 1) * 16);
     const float x0[4] = {a.x, a.y, a.z, a.w}, x1[4] = {b.x, b.y, b.z, b.w};
-    const int rbase = r0 + 4 * (4 * HALF + 2 * i + g2);
+    const int rbase = r0 + 4 * (4 * HALF + q);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t hi = pack_bf16(x0[j], x1[j]);
@@ -1123,8 +1124,8 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
     const bool active = is_a || r0 < rows_b;
     uint8_t* s_hi = planes + (is_a ? 0u : 2u * A_HALF_BYTES);
     uint8_t* s_lo = s_hi + (is_a ? (uint32_t)A_HALF_BYTES : T2_B_HALF);
-    const uint8_t* raw_lane = raw + warp * T2_RAW_WARP + lane * 16;
-    const uint32_t raw_lane_s = smem_u32(raw_lane);
+    const uint8_t* raw_warp = raw + warp * T2_RAW_WARP;
+    const uint32_t raw_warp_s = smem_u32(raw_warp);
     float csum[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) csum[j] = 0.f;
@@ -1136,7 +1137,7 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
         const TnPair& pr = pair_of(i);
         const int64_t k0 = kb + (int64_t)(i < n_sl ? i : i - n_sl) * T2_BK;
         t2_issue(is_a ? pr.A : pr.B, is_a ? pr.lda : pr.ldb, (is_a ? m0 : n0) + r0, h & 1, k0, ke,
-                 raw_lane_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
+                 raw_warp_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
       }
       cp_async_commit();
     };
@@ -1145,20 +1146,25 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
     for (int i = 0; i < total; ++i) {
       const int s = i & 1;
       const bool do_csum = is_a && blockIdx.y == 0 && pair_of(i).colsum_a != nullptr;
-      // half 0
+      // half 0.  __syncwarp before issue: every lane is done reading the ring slot that is refilled; after the wait: the other
+      // lanes' copies of this granule are visible
+      __syncwarp();
       issue(2 * i + T2_RING - 1);
       cp_async_wait<T2_RING - 1>();
+      __syncwarp();
       if (i >= 2) mbar_wait(&ctl->empty[s], (uint32_t)(((i >> 1) - 1) & 1));
       if (active) {
-        const uint8_t* rl = raw_lane + (uint32_t)((2 * i) % T2_RING) * T2_RAW_GRAN;
+        const uint8_t* rl = raw_warp + (uint32_t)((2 * i) % T2_RING) * T2_RAW_GRAN;
         if (do_csum) t2_convert<true, 0>(rl, s_hi, s_lo, r0, s, lane, csum);
         else t2_convert<false, 0>(rl, s_hi, s_lo, r0, s, lane, csum);
       }
       // half 1
+      __syncwarp();
       issue(2 * i + T2_RING);
       cp_async_wait<T2_RING - 1>();
+      __syncwarp();
       if (active) {
-        const uint8_t* rl = raw_lane + (uint32_t)((2 * i + 1) % T2_RING) * T2_RAW_GRAN;
+        const uint8_t* rl = raw_warp + (uint32_t)((2 * i + 1) % T2_RING) * T2_RAW_GRAN;
         if (do_csum) t2_convert<true, 1>(rl, s_hi, s_lo, r0, s, lane, csum);
         else t2_convert<false, 1>(rl, s_hi, s_lo, r0, s, lane, csum);
       }

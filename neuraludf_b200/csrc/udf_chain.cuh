@@ -56,6 +56,9 @@ constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;           // 512
 constexpr int CH_MMA_WARP = 16, CH_LOAD_WARP = 17;
 constexpr int CH_THREADS = 576;
 constexpr int CH_MAX_STEPS = 24;
+#ifndef CH_RING2
+#define CH_RING2 2
+#endif
 constexpr int CH_MAX_PE = 64;                               // positional-encoding width (K of layer 0) <= one K slice
 
 // what the epilogue does with the accumulator of a step (or, for steps without a GEMM, how the next operand is made)
@@ -97,6 +100,8 @@ struct ChainParams {
   const uint16_t* img;
   const float* pts; int64_t P; float scale; int n_freq, d_pe;
   const float* gbar;                     // T chain: upstream gradient of grad_x udf [P,3]
+  const float* pe_src; int pe_ld;        // the tensor the first step wrote (E0 / Edot): re-read for the skip layer's appended columns
+  int pe_cta;                            // 1: that tensor is a per-CTA stash of 128 rows (value-only launches keep no context)
   int t128;                              // 1: every [P, ld] tensor of the steps is stored in the T128 layout (common.cuh)
   float* udf_out; float inv_scale;       // value-only mode: udf_out[P] = |y_0| / scale
   long long* trace;                      // profiling aid (NUDF_CHAIN_TRACE=n): clock64() stamps of CTA 0, first point tile
@@ -331,136 +336,528 @@ struct ChainCtl {
 constexpr size_t CH_SMEM_BYTES = (size_t)CH_A_BYTES + (size_t)CH_NSLOT * CH_WSLOT + sizeof(ChainCtl);
 static_assert(CH_SMEM_BYTES <= 227 * 1024, "fused chain: shared-memory budget exceeded");
 
-// One 16-column group of one row: element-wise part of a step.  `z` = accumulator values already scaled (sl (M + C)), zeros for
-// steps without a GEMM.  Writes the value that continues the chain into nx[] (0 where nothing continues) and performs the
-// step's global stores when `do_store`.  col0 = first logical output column of the group.
-__device__ __forceinline__ void step_group(const ChainStep& S, const ChainParams& p, int64_t row, bool row_ok, int col0,
-                                           const float* z, const float* bv, const float* pe, float sgn_scaled, bool do_store,
-                                           float nx[16]) {
-  const int kind = S.kind;
-  const bool T = p.t128 != 0;
-  if (kind == ST_PE || kind == ST_EDOT) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.n_next) ? pe[col0 + j] : 0.f;
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.ld_out0) st_row16(S.out0, S.ld_out0, row, col0, S.ld_out0 - col0, T, nx);
-    return;
-  }
-  if (kind == ST_LOAD) {
-    if (row_ok && col0 < S.n_next) ld_row16(S.in0, S.ld_in0, row, col0, S.n_next - col0, T, nx);
-    else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) nx[j] = 0.f;
+// ---- epilogue -------------------------------------------------------------------------------------------------------
+// The epilogue walks a step's output in OCTETS (8 consecutive columns of the thread's row): per octet two tcgen05.ld.x8 (main and
+// correction accumulator), the element-wise part of the step, 16-byte global stores, one tcgen05.st.x8 that parks the value
+// which continues the chain.  Interior octets (all 8 columns inside the step's main column range, T128 tensors) take a
+// predicate-free fast path whose auxiliary global loads (saved activations, D, Q) are software-pipelined two octets ahead in a
+// 3-deep register ring -- the first two are issued before the accumulator-ready wait; boundary octets (skip-layer columns,
+// partial tiles) and row-major tensors go through one generic out-of-line routine.
+__device__ __forceinline__ void tmem_ld8x2(uint32_t ta, uint32_t tb, float v[8], float w[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  uint32_t* q = reinterpret_cast<uint32_t*>(w);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%17];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(q[0]), "=r"(q[1]),
+        "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+      : "r"(ta), "r"(tb)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t ta, float v[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(ta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t ta, const float v[8]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigma(100 z) recovered from the stored softplus output a = post softplus100(z):  1 - exp(-100 a / post) = 1 - 2^(ak a) with
+// ak = -100 log2(e) / post.  In the linear regime (100 z > 20) 2^(ak a) < 2.1e-9 and the result rounds to exactly 1, which is
+// what sig_from_softplus (common.cuh) returns there.
+__device__ __forceinline__ float sig_ak(float a, float ak) { return 1.0f - ex2_fast(a * ak); }
+
+struct EpiT {                         // per-thread constants of one point tile
+  int r_in, cq;
+  uint32_t t_lane;
+  int64_t row;                        // global row (point)
+  int64_t srow;                       // row inside the PE / Edot tensor (CTA-local stash in value-only launches)
+  bool row_ok, t128;
+};
+__device__ __forceinline__ int64_t row_off(int64_t ld, int64_t row, bool t128) {
+  return t128 ? ((row >> 7) * (ld >> 2) * 512 + (row & 127) * 4) : row * ld;
+}
+// T128 tensors, c % 8 == 0: the octet of this thread's row is two float4, 512 floats apart; rp = base + row_off
+__device__ __forceinline__ void ldg8(const float* rp, int c, float v[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(rp + c * 128);
+  const float4 b = *reinterpret_cast<const float4*>(rp + c * 128 + 512);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void stg8(float* rp, int c, const float v[8]) {
+  *reinterpret_cast<float4*>(rp + c * 128) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(rp + c * 128 + 512) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// 8 consecutive values -> 16 bytes of plane 0 / plane 1 into the A planes of K slice `sl_base`
+__device__ __forceinline__ void slice_store8(const float v[8], float inv, uint8_t* sl_base, int r_in, int kcol) {
+  uint4 p0, p1;
+  slice8(v, inv, p0, p1);
+  const uint32_t off = sw128((uint32_t)r_in, (uint32_t)kcol);
+  *reinterpret_cast<uint4*>(sl_base + off) = p0;
+  *reinterpret_cast<uint4*>(sl_base + CH_APLANE + off) = p1;
+}
+
+struct StepR {                        // the fields of a step the fast paths use, read once per step
+  int N, n_tiles, rows_override, n_main, n_next, n_cols, n_out_tiles;
+  float ps, ak, rz;
+  bool has_rowv;
+  const float* bias; const float* vec0;
+  const float* in0r; const float* in1r; float* out0r; float* out1r;      // row pointers (base + row_off) or null
+};
+__device__ __forceinline__ StepR load_step(const ChainStep& G, const EpiT& e) {
+  StepR S;
+  S.N = G.N; S.n_tiles = G.n_tiles; S.rows_override = G.rows_override; S.n_main = G.n_main; S.n_next = G.n_next;
+  int n_cols = G.n_next > G.N ? G.n_next : G.N;
+  if (G.kind == ST_TAN && G.n_main > n_cols) n_cols = G.n_main;
+  S.n_cols = n_cols;
+  S.n_out_tiles = (n_cols + CH_NT - 1) / CH_NT;
+  S.ps = G.post_scale;
+  S.ak = -144.26950408889634f * G.a_unscale;
+  S.has_rowv = G.rowv != nullptr;
+  S.rz = (G.rowv != nullptr && e.row_ok) ? G.rowv[e.row] : 0.f;
+  S.bias = G.bias; S.vec0 = G.vec0;
+  S.in0r = G.in0 ? G.in0 + row_off(G.ld_in0, e.row, e.t128) : nullptr;
+  S.in1r = G.in1 ? G.in1 + row_off(G.ld_in1, e.row, e.t128) : nullptr;
+  S.out0r = G.out0 ? G.out0 + row_off(G.ld_out0, e.row, e.t128) : nullptr;
+  S.out1r = G.out1 ? G.out1 + row_off(G.ld_out1, e.row, e.t128) : nullptr;
+  return S;
+}
+
+// Generic octet (any column range, any layout): z[8] in = scaled accumulator values (zeros for steps without a GEMM), out = the
+// value that continues the chain.  Performs the step's stores when do_store.  Out of line on purpose (boundary octets only).
+__device__ __noinline__ void octet_slow(const ChainStep* S, const ChainParams* p, int64_t row, int64_t srow, bool row_ok, int col0,
+                                        float sgn_scaled, bool do_store, float* z) {
+  const bool T = p->t128 != 0;
+  const int kind = S->kind;
+  const float ak = -144.26950408889634f * S->a_unscale;
+  const float ps = S->post_scale;
+  const bool st = do_store && row_ok;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const int col = col0 + j;
+    const float zz = z[j];
+    float nx = 0.f;
+    if (kind == ST_FWD) {
+      if (col < S->N) nx = softplus100_fast(zz + __ldg(S->bias + col)) * ps;
+      else if (col < S->n_next) nx = (row_ok ? p->pe_src[mat_off(T, srow, col - S->N, p->pe_ld)] : 0.f) * ps;
+      if (st && S->out0 != nullptr && col < S->n_next) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
+    } else if (kind == ST_FWD_LAST) {
+      if (col < S->N) {
+        nx = zz + __ldg(S->bias + col);
+        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
+      }
+    } else if (kind == ST_REV || kind == ST_REV_SEED) {
+      float raw = zz;
+      if (kind == ST_REV_SEED) raw = (col < S->N) ? sgn_scaled * __ldg(S->vec0 + col) : 0.f;     // S->N = width of the last layer's input
+      const float gp = raw * ps;
+      if (col < S->n_main) {
+        const float a = row_ok ? S->in0[mat_off(T, row, col, S->ld_in0)] : 0.f;
+        nx = gp * sig_ak(a, ak);
+        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
+      } else if (col < S->N && st && S->out1 != nullptr) {                  // skip layer: gradient w.r.t. the PE columns
+        S->out1[mat_off(T, row, col - S->n_main, S->ld_out1)] = gp;
+      }
+    } else if (kind == ST_REV_FINAL) {
+      if (col < S->N) {
+        const float g = (S->in1 != nullptr && row_ok) ? S->in1[mat_off(T, row, col, S->ld_in1)] : 0.f;
+        nx = zz + g;
+        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
+      }
+    } else if (kind == ST_TAN) {
+      if (col < S->N) {
+        const float a = row_ok ? S->in0[mat_off(T, row, col, S->ld_in0)] : 0.f;
+        const float d = row_ok ? S->in1[mat_off(T, row, col, S->ld_in1)] : 0.f;
+        const float s = sig_ak(a, ak);
+        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = zz * d * (100.0f * (1.0f - s));
+        nx = s * zz * ps;
+      } else if (col < S->n_main) {                  // Edot columns appended at the skip layer
+        nx = (row_ok ? p->pe_src[mat_off(T, srow, col - S->N, p->pe_ld)] : 0.f) * ps;
+      }
+      if (st && S->out1 != nullptr && col < S->n_main) S->out1[mat_off(T, row, col, S->ld_out1)] = nx;
+    } else if (kind == ST_BWD) {
+      if (col < S->n_main) {
+        const float a = row_ok ? S->in0[mat_off(T, row, col, S->ld_in0)] : 0.f;
+        const float q = row_ok ? S->in1[mat_off(T, row, col, S->ld_in1)] : 0.f;
+        float ab = zz;
+        if (S->rowv != nullptr) ab = fmaf(row_ok ? S->rowv[row] : 0.f, __ldg(S->vec0 + col), ab);
+        nx = ab * ps * sig_ak(a, ak) + q;
+        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
+      }
+    } else if (kind == ST_LOAD) {
+      if (row_ok && col < S->n_next) nx = S->in0[mat_off(T, row, col, S->ld_in0)];
     }
-    return;
+    z[j] = nx;
   }
-  if (kind == ST_FWD) {
-    const int n_valid = S.N;
+}
+
+// interior octet of a GEMM step (T128, col0 + 8 <= the step's main column count); a / b: prefetched auxiliary octets
+template <int KIND>
+__device__ __forceinline__ void octet_fast(const StepR& S, const EpiT& e, int col0, float z[8], const float a[8], float b[8]) {
+  if (KIND == ST_FWD) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(S.bias + col0)), b1 = __ldg(reinterpret_cast<const float4*>(S.bias + col0 + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int col = col0 + j;
-      float a = 0.f;
-      if (col < n_valid) a = softplus100_fast(z[j] + bv[j]) * S.post_scale;
-      else if (col < S.n_next) a = pe[col - n_valid] * S.post_scale;
-      nx[j] = a;
+    for (int j = 0; j < 8; ++j) z[j] = softplus100_fast(z[j] + bb[j]) * S.ps;
+    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
+  } else if (KIND == ST_FWD_LAST) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(S.bias + col0)), b1 = __ldg(reinterpret_cast<const float4*>(S.bias + col0 + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] += bb[j];
+    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
+  } else if (KIND == ST_REV || KIND == ST_REV_SEED) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = z[j] * S.ps * sig_ak(a[j], S.ak);
+    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
+  } else if (KIND == ST_TAN) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = sig_ak(a[j], S.ak);
+      b[j] = z[j] * b[j] * (100.0f * (1.0f - s));
+      z[j] = s * z[j] * S.ps;
     }
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_next) st_row16(S.out0, S.ld_out0, row, col0, S.n_next - col0, T, nx);
-    return;
-  }
-  if (kind == ST_FWD_LAST) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.N) ? z[j] + bv[j] : 0.f;
-    if (do_store && row_ok) {
-      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, T, nx);
-      if (p.udf_out != nullptr && col0 == 0) p.udf_out[row] = fabsf(nx[0]) * p.inv_scale;
+    if (e.row_ok) {
+      if (S.out0r != nullptr) stg8(S.out0r, col0, b);
+      if (S.out1r != nullptr) stg8(S.out1r, col0, z);
     }
-    return;
-  }
-  if (kind == ST_REV_FINAL) {
-    float g[16];
-    if (S.in1 != nullptr && row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, T, g);
-    else {
+  } else if (KIND == ST_BWD) {
+    if (S.has_rowv) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) g[j] = 0.f;
+      for (int j = 0; j < 8; ++j) z[j] = fmaf(S.rz, __ldg(S.vec0 + col0 + j), z[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) nx[j] = (col0 + j < S.N) ? z[j] + g[j] : 0.f;
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, T, nx);
-    return;
+    for (int j = 0; j < 8; ++j) z[j] = z[j] * S.ps * sig_ak(a[j], S.ak) + b[j];
+    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
   }
-  // the remaining kinds recover S = sigma(100 z_prev) from the stored softplus output in0 (= A of the right layer)
-  float a[16];
-  const int n_act = (kind == ST_TAN) ? S.N : S.n_main;           // columns that have an activation behind them
-  if (row_ok && col0 < n_act) ld_row16(S.in0, S.ld_in0, row, col0, n_act - col0, T, a);
-  else {
+}
+
+// row maximum exchange + per-row scale of the operand the step produced; returns after the barrier
+__device__ __forceinline__ void exchange_scale(ChainCtl* ctl, const EpiT& e, float rmax, uint32_t& lp, float& sa, float& inv) {
+  ctl->rowexp[lp][e.cq][e.r_in] = (uint8_t)expo_bits(rmax);
+  epi_bar_sync();            // all MMAs of this step are complete (every warp waited for every tile), all maxima are in
+  const uint32_t e01 = max((uint32_t)ctl->rowexp[lp][0][e.r_in], (uint32_t)ctl->rowexp[lp][1][e.r_in]);
+  const uint32_t e23 = max((uint32_t)ctl->rowexp[lp][2][e.r_in], (uint32_t)ctl->rowexp[lp][3][e.r_in]);
+  row_scale(max(e01, e23), sa, inv);
+  lp ^= 1;
+}
+
+#define CH_TRS(k) do { if (tr_on) p.trace[(tr_role * CH_MAX_STEPS + l) * 8 + (k)] = clock64(); } while (0)
+
+// ---- steps with a GEMM whose output is at most two N tiles wide (FWD, REV, TAN, BWD) ----
+template <int KIND>
+__device__ __forceinline__ void epi_step_gemm(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, uint8_t* a_smem, const EpiT& e,
+                                              uint32_t (&af_cnt)[2], uint32_t& lp, float& sa, float& inv, bool tr_on, int tr_role, int l) {
+  constexpr int NAUX = (KIND == ST_REV) ? 1 : ((KIND == ST_TAN || KIND == ST_BWD) ? 2 : 0);
+  const StepR S = load_step(G, e);
+  const float sl = sa * __ldg(G.wscale);                         // z = sl (M + C)
+  const int lim = (KIND == ST_FWD || KIND == ST_TAN) ? S.N : S.n_main;
+  constexpr int RD = (NAUX == 2) ? CH_RING2 : 3;            // ring depth; prefetch distance RD - 1 octets
+  float ax[RD][8], bx[RD][8];
+  auto col_of = [&](int g) { return CH_NT * (g >> 2) + 32 * e.cq + 8 * (g & 3); };
+  auto prefetch = [&](int g, float (&a)[8], float (&b)[8]) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = 0.f;
-  }
-  if (kind == ST_REV || kind == ST_REV_SEED) {
-    float gp[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int col = col0 + j;
-      float raw = z[j];
-      if (kind == ST_REV_SEED) raw = (col < S.N) ? sgn_scaled * __ldg(S.vec0 + col) : 0.f;   // S.N = width of the last layer's input
-      gp[j] = raw * S.post_scale;
-      nx[j] = (col < S.n_main) ? gp[j] * sig_from_softplus(a[j] * S.a_unscale) : 0.f;
+    for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
+    const int c = col_of(g);
+    if (NAUX >= 1 && e.t128 && e.row_ok && c + 8 <= lim) {
+      ldg8(S.in0r, c, a);
+      if (NAUX == 2) ldg8(S.in1r, c, b);
     }
-    if (do_store && row_ok) {
-      if (S.out0 != nullptr && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, T, nx);
-      if (S.out1 != nullptr && col0 + 16 > S.n_main && col0 < S.N) {       // skip layer: columns >= n_main are the gradient w.r.t. PE
+  };
+  float rmax = 0.f;
+  if (NAUX > 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = col0 + j;
-          if (col >= S.n_main && col < S.N) S.out1[mat_off(T, row, col - S.n_main, S.ld_out1)] = gp[j];
+    for (int g = 0; g < RD - 1; ++g) prefetch(g, ax[g], bx[g]);
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int t = g >> 2, o = g & 3;
+    if (t < S.n_out_tiles) {
+      const int slot = t & 1;
+      const bool has_acc = t < S.n_tiles;
+      if (o == 0 && has_acc) {
+        mbar_wait(&ctl->acc_full[slot], af_cnt[slot] & 1u);
+        ++af_cnt[slot];
+        tcgen05_fence_after();
+        if (t == 0) CH_TRS(1);
+      }
+      if (NAUX > 0 && g + RD - 1 < 8 && ((g + RD - 1) >> 2) < S.n_out_tiles) prefetch(g + RD - 1, ax[(g + RD - 1) % RD], bx[(g + RD - 1) % RD]);
+      const int c0 = 32 * e.cq + 8 * o, col0 = CH_NT * t + c0;
+      const uint32_t t_m = e.t_lane + (uint32_t)slot * 256u + (uint32_t)c0;
+      const int rows_t = has_acc ? (S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t)) : 0;
+      float z[8];
+      if (c0 < rows_t) {
+        float cc[8];
+        tmem_ld8x2(t_m, t_m + 128u, z, cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = (z[j] + cc[j]) * sl;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = 0.f;
+      }
+      if (col0 < S.n_cols) {
+        if (e.t128 && col0 + 8 <= lim) {
+          octet_fast<KIND>(S, e, col0, z, ax[g % RD], bx[g % RD]);
+        } else {
+          float zs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zs[j] = z[j];
+          octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, 0.f, true, zs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = zs[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = 0.f;
+      }
+      if (S.n_next > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rmax = fmaxf(rmax, fabsf(z[j]));
+        tmem_st8(t_m, z);                                            // parked in TMEM (over M) until the row scale is known
+      }
+      if (o == 3 && has_acc && S.n_next == 0) {                      // nothing continues: the accumulator pair is free again
+        tcgen05_fence_before();
+        mbar_arrive(&ctl->acc_empty[slot]);
+      }
+    }
+  }
+  CH_TRS(2);
+  if (S.n_next > 0) {
+    tmem_wait_st();
+    exchange_scale(ctl, e, rmax, lp, sa, inv);
+    CH_TRS(3);
+    // ---------------- pass 2: slice the new operand into the A planes ----------------
+    const int nks_next = pad64(S.n_next) / 64;
+    const int n_nx_tiles = (S.n_next + CH_NT - 1) / CH_NT;
+#pragma unroll 1
+    for (int t = 0; t < S.n_out_tiles; ++t) {
+      const int slot = t & 1;
+      const int s = 2 * t + (e.cq >> 1);                 // K slice of the next GEMM this warp's columns belong to
+      if (t < n_nx_tiles && s < nks_next) {
+        uint8_t* sl_base = a_smem + (size_t)s * 2 * CH_APLANE;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          float v[8];
+          tmem_ld8(e.t_lane + (uint32_t)slot * 256u + (uint32_t)(32 * e.cq + 8 * o), v);
+          slice_store8(v, inv, sl_base, e.r_in, (e.cq & 1) * 32 + 8 * o);
+        }
+        fence_proxy_async();
+        mbar_arrive(&ctl->a_ready[s]);
+      }
+      if (t < S.n_tiles) {
+        tcgen05_fence_before();
+        mbar_arrive(&ctl->acc_empty[slot]);
+      }
+    }
+  }
+}
+
+// ---- last layer of F (up to 3 N tiles, nothing continues) and last step of R (39 columns) ----
+template <int KIND>
+__device__ __forceinline__ void epi_step_tail(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, const EpiT& e, uint32_t (&af_cnt)[2],
+                                              float sa, bool tr_on, int tr_role, int l) {
+  const StepR S = load_step(G, e);
+  const float sl = sa * __ldg(G.wscale);
+  float dummy[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int t = 0; t < S.n_out_tiles; ++t) {
+    const int slot = t & 1;
+    const bool has_acc = t < S.n_tiles;
+    if (has_acc) {
+      mbar_wait(&ctl->acc_full[slot], af_cnt[slot] & 1u);
+      ++af_cnt[slot];
+      tcgen05_fence_after();
+      if (t == 0) CH_TRS(1);
+    }
+    const int rows_t = has_acc ? (S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t)) : 0;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int c0 = 32 * e.cq + 8 * o, col0 = CH_NT * t + c0;
+      if (col0 < S.n_cols && c0 < rows_t) {
+        const uint32_t t_m = e.t_lane + (uint32_t)slot * 256u + (uint32_t)c0;
+        float z[8], cc[8];
+        tmem_ld8x2(t_m, t_m + 128u, z, cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = (z[j] + cc[j]) * sl;
+        if (KIND == ST_FWD_LAST && e.t128 && col0 + 8 <= S.N) {
+          octet_fast<ST_FWD_LAST>(S, e, col0, z, dummy, dummy);
+        } else {
+          float zs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zs[j] = z[j];
+          octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, 0.f, true, zs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = zs[j];
+        }
+        if (KIND == ST_FWD_LAST && col0 == 0) {
+          const float y0 = z[0];
+          ctl->rowsgn[e.r_in] = (y0 > 0.f ? 1.f : (y0 < 0.f ? -1.f : 0.f)) * p.inv_scale;
+          if (p.udf_out != nullptr && e.row_ok) p.udf_out[e.row] = fabsf(y0) * p.inv_scale;
         }
       }
     }
-    return;
-  }
-  if (kind == ST_TAN) {
-    float d[16], q[16];
-    if (row_ok && col0 < S.N) ld_row16(S.in1, S.ld_in1, row, col0, S.N - col0, T, d);
-    else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) d[j] = 0.f;
+    if (has_acc) {
+      tcgen05_fence_before();
+      mbar_arrive(&ctl->acc_empty[slot]);
     }
+  }
+  CH_TRS(2);
+}
+
+// ---- steps without a GEMM that make an operand from global data: LOAD (zf), REV_SEED ----
+template <int KIND>
+__device__ __forceinline__ void epi_step_nogemm(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, uint8_t* a_smem, const EpiT& e,
+                                                uint32_t& lp, float& sa, float& inv, bool tr_on, int tr_role, int l) {
+  const StepR S = load_step(G, e);
+  const float sgn_scaled = (KIND == ST_REV_SEED) ? ctl->rowsgn[e.r_in] : 0.f;
+  const int lim = (KIND == ST_REV_SEED) ? S.n_main : S.n_next;
+  auto produce = [&](int col0, bool do_store, float (&z)[8]) {
+    if (col0 >= S.n_cols) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int col = col0 + j;
-      float n = 0.f;
-      q[j] = 0.f;
-      if (col < S.N) {
-        const float s = sig_from_softplus(a[j] * S.a_unscale);
-        q[j] = z[j] * d[j] * (100.0f * (1.0f - s));
-        n = s * z[j] * S.post_scale;
-      } else if (col < S.n_main) {                   // n_main = width of Adot[l+1] (Edot columns appended at the skip layer)
-        n = pe[col - S.N] * S.post_scale;
+      for (int j = 0; j < 8; ++j) z[j] = 0.f;
+      return;
+    }
+    if (e.t128 && col0 + 8 <= lim) {
+      if (KIND == ST_LOAD) {
+        if (e.row_ok) ldg8(S.in0r, col0, z);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = 0.f;
+        }
+      } else {
+        float a[8];
+        if (e.row_ok) ldg8(S.in0r, col0, a);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = sgn_scaled * __ldg(S.vec0 + col0 + j) * S.ps * sig_ak(a[j], S.ak);
+        if (do_store && S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
       }
-      nx[j] = n;
+    } else {
+      float zs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, sgn_scaled, do_store, zs);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = zs[j];
     }
-    if (do_store && row_ok) {
-      if (S.out0 != nullptr && col0 < S.N) st_row16(S.out0, S.ld_out0, row, col0, S.N - col0, T, q);
-      if (S.out1 != nullptr && col0 < S.n_main) st_row16(S.out1, S.ld_out1, row, col0, S.n_main - col0, T, nx);
+  };
+  float rmax = 0.f;
+#pragma unroll 1
+  for (int t = 0; t < S.n_out_tiles; ++t) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float z[8];
+      produce(CH_NT * t + 32 * e.cq + 8 * o, true, z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rmax = fmaxf(rmax, fabsf(z[j]));
     }
-    return;
   }
-  // ST_BWD
-  {
-    float q[16];
-    if (row_ok && col0 < S.n_main) ld_row16(S.in1, S.ld_in1, row, col0, S.n_main - col0, T, q);
-    else {
+  CH_TRS(2);
+  exchange_scale(ctl, e, rmax, lp, sa, inv);
+  CH_TRS(3);
+  const int nks_next = pad64(S.n_next) / 64;
+  const int n_nx_tiles = (S.n_next + CH_NT - 1) / CH_NT;
+#pragma unroll 1
+  for (int t = 0; t < n_nx_tiles; ++t) {
+    const int s = 2 * t + (e.cq >> 1);
+    if (s < nks_next) {
+      uint8_t* sl_base = a_smem + (size_t)s * 2 * CH_APLANE;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) q[j] = 0.f;
+      for (int o = 0; o < 4; ++o) {
+        float z[8];
+        produce(CH_NT * t + 32 * e.cq + 8 * o, false, z);           // cheap to recompute
+        slice_store8(z, inv, sl_base, e.r_in, (e.cq & 1) * 32 + 8 * o);
+      }
+      fence_proxy_async();
+      mbar_arrive(&ctl->a_ready[s]);
     }
-    const float rz = (S.rowv != nullptr && row_ok) ? S.rowv[row] : 0.f;
+  }
+}
+
+// ---- first step: PE(x) (models/embedder.py:22-36) for the F chain, Edot = scale J_e(x) gbar for the T chain ----
+// out[c], c < 3 + 6 n_freq: c < 3: x_c; then per frequency q: sin(2^q x_k) (k = 0..2), cos(2^q x_k); the JVP variant returns
+// the directional derivative along v.  Out of line and looped on purpose: sincosf is large, the step runs once per point tile.
+template <bool JVP>
+__device__ __noinline__ void pe_row(float x0, float x1, float x2, float v0, float v1, float v2, int n_freq, float* out) {
+  const float x[3] = {x0, x1, x2}, v[3] = {v0, v1, v2};
+  float f = 1.0f;
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) out[k] = JVP ? v[k] : x[k];
+#pragma unroll 1
+  for (int q = 0; q < n_freq; ++q) {
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+      float sn, cs;
+      sincosf(x[k] * f, &sn, &cs);
+      out[3 + 6 * q + k] = JVP ? f * cs * v[k] : sn;
+      out[3 + 6 * q + 3 + k] = JVP ? -f * sn * v[k] : cs;
+    }
+    f *= 2.0f;
+  }
+}
+template <bool JVP>
+__device__ __forceinline__ void pe_fill(const ChainParams& p, const EpiT& e, float (&vals)[4][8]) {
+  float x[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+  if (e.row_ok) {
+    x[0] = p.pts[e.row * 3 + 0] * p.scale; x[1] = p.pts[e.row * 3 + 1] * p.scale; x[2] = p.pts[e.row * 3 + 2] * p.scale;
+    if (JVP) { v[0] = p.gbar[e.row * 3 + 0] * p.scale; v[1] = p.gbar[e.row * 3 + 1] * p.scale; v[2] = p.gbar[e.row * 3 + 2] * p.scale; }
+  }
+  float row[CH_MAX_PE];
+#pragma unroll 1
+  for (int c = 0; c < CH_MAX_PE; ++c) row[c] = 0.f;
+  pe_row<JVP>(x[0], x[1], x[2], v[0], v[1], v[2], p.n_freq, row);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int col = col0 + j;
-      float ab = z[j];
-      if (S.rowv != nullptr && col < S.n_main) ab = fmaf(rz, __ldg(S.vec0 + col), ab);
-      nx[j] = (col < S.n_main) ? ab * S.post_scale * sig_from_softplus(a[j] * S.a_unscale) + q[j] : 0.f;
+  for (int o = 0; o < 4; ++o) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vals[o][j] = row[32 * e.cq + 8 * o + j];
+  }
+}
+template <bool JVP>
+__device__ __forceinline__ void epi_step_pe(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, uint8_t* a_smem, const EpiT& e,
+                                            uint32_t& lp, float& sa, float& inv, bool tr_on, int tr_role, int l) {
+  float vals[4][8];
+  float rmax = 0.f;
+  const bool mine = e.cq <= 1 && 32 * e.cq < G.n_next;           // the encoding is at most 64 columns wide: K slice 0 only
+  if (mine) {
+    pe_fill<JVP>(p, e, vals);
+    float* outr = G.out0 != nullptr ? G.out0 + row_off(G.ld_out0, e.srow, e.t128) : nullptr;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int col0 = 32 * e.cq + 8 * o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rmax = fmaxf(rmax, fabsf(vals[o][j]));
+      if (outr != nullptr && e.row_ok && col0 < G.ld_out0) {
+        if (e.t128) stg8(outr, col0, vals[o]);                  // columns >= d_pe are zeros: the tensor's padding
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (col0 + j < G.ld_out0) outr[col0 + j] = vals[o][j];
+        }
+      }
     }
-    if (do_store && S.out0 != nullptr && row_ok && col0 < S.n_main) st_row16(S.out0, S.ld_out0, row, col0, S.n_main - col0, T, nx);
+  }
+  CH_TRS(2);
+  exchange_scale(ctl, e, rmax, lp, sa, inv);
+  CH_TRS(3);
+  if (e.cq <= 1) {
+    if (mine) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) slice_store8(vals[o], inv, a_smem, e.r_in, 32 * e.cq + 8 * o);
+    }
+    fence_proxy_async();
+    mbar_arrive(&ctl->a_ready[0]);
   }
 }
 
@@ -488,157 +885,38 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
 
   if (warp < CH_EPI_WARPS) {
     // =========================================== epilogue warps ===========================================
-    const int quad = warp & 3, cq = warp >> 2;
-    const int r_in = quad * 32 + lane;                       // row of the tile = TMEM lane
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    EpiT e;
+    e.cq = warp >> 2;
+    e.r_in = (warp & 3) * 32 + lane;                         // row of the tile = TMEM lane
+    e.t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    e.t128 = p.t128 != 0;
     uint32_t af_cnt[2] = {0u, 0u};                           // completed waits on acc_full[slot]
     uint32_t lp = 0;                                         // parity of the row-exponent exchange buffers
     for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
       const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && pt == blockIdx.x && lane == 0 && (warp == 0 || warp == 12);
       const int tr_role = warp == 0 ? 0 : 1;
-      const int64_t row = pt * 128 + r_in;
-      const bool row_ok = row < p.P;
-      float x[3] = {0.f, 0.f, 0.f};
-      if (row_ok) { x[0] = p.pts[row * 3 + 0] * p.scale; x[1] = p.pts[row * 3 + 1] * p.scale; x[2] = p.pts[row * 3 + 2] * p.scale; }
-      // per-row local vector: PE(x) (models/embedder.py:22-36) for the F chain, Edot = scale J_e(x) gbar for the T chain
-      float pe[CH_MAX_PE];
-#pragma unroll
-      for (int j = 0; j < CH_MAX_PE; ++j) pe[j] = 0.f;
-      if (p.S[0].kind == ST_PE || p.S[0].kind == ST_EDOT) {
-        const bool jvp = p.S[0].kind == ST_EDOT;
-        float v[3] = {1.f, 1.f, 1.f};
-        if (jvp) {
-          v[0] = v[1] = v[2] = 0.f;
-          if (row_ok) { v[0] = p.gbar[row * 3 + 0] * p.scale; v[1] = p.gbar[row * 3 + 1] * p.scale; v[2] = p.gbar[row * 3 + 2] * p.scale; }
-        }
-        pe[0] = jvp ? v[0] : x[0]; pe[1] = jvp ? v[1] : x[1]; pe[2] = jvp ? v[2] : x[2];
-        float f = 1.0f;
-#pragma unroll 1
-        for (int q = 0; q < p.n_freq; ++q) {
-#pragma unroll 1
-          for (int c = 0; c < 3; ++c) {
-            float sn, cs;
-            sincosf(x[c] * f, &sn, &cs);
-            pe[3 + 6 * q + c] = jvp ? f * cs * v[c] : sn;
-            pe[3 + 6 * q + 3 + c] = jvp ? -f * sn * v[c] : cs;
-          }
-          f *= 2.0f;
-        }
-      }
+      e.row = pt * 128 + e.r_in;
+      e.row_ok = e.row < p.P;
+      e.srow = p.pe_cta ? (int64_t)blockIdx.x * 128 + e.r_in : e.row;
       float sa = 1.0f, inv = 1.0f;                           // scale of the operand currently in shared memory
       for (int l = 0; l < p.n_steps; ++l) {
-        const ChainStep& S = p.S[l];
-        CH_TR(tr_role, l, 0, clock64());
-        if (S.sync_before) epi_bar_sync();
-        const bool has_gemm = S.n_tiles > 0;
-        const float sl = has_gemm ? sa * __ldg(S.wscale) : 0.f;          // z = sl (M + C)
-        const float sgn_scaled = (S.kind == ST_REV_SEED) ? ctl->rowsgn[r_in] : 0.f;
-        int n_cols = S.n_next > S.N ? S.n_next : S.N;                   // logical columns this step's epilogue walks
-        if (S.kind == ST_TAN && S.n_main > n_cols) n_cols = S.n_main;
-        const int n_out_tiles = (n_cols + CH_NT - 1) / CH_NT;
-        float rmax = 0.f;
-        // ---------------- pass 1: element-wise part, stores, partial row maximum ----------------
-#pragma unroll 1
-        for (int t = 0; t < n_out_tiles; ++t) {
-          const bool has_acc = t < S.n_tiles;
-          const int slot = t & 1;
-          int rows_t = 0;
-          float bl = 0.f;
-          if (has_acc) {
-            rows_t = S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t);
-            if (S.bias != nullptr) bl = __ldg(S.bias + CH_NT * t + 32 * cq + lane);    // lane j: bias of this warp's column j
-            mbar_wait(&ctl->acc_full[slot], af_cnt[slot] & 1u);
-            ++af_cnt[slot];
-            tcgen05_fence_after();
-          }
-          if (t == 0) CH_TR(tr_role, l, 1, clock64());
-          const uint32_t t_m = t_lane + (uint32_t)slot * 256u;
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int c0 = 32 * cq + 16 * sub;                       // column inside the tile
-            const int col0 = CH_NT * t + c0;
-            float z[16], bv[16];
-            if (has_acc && c0 < rows_t) {
-              float cc[16];
-              tmem_ld16x2(t_m + (uint32_t)c0, t_m + 128u + (uint32_t)c0, z, cc);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) z[j] = (z[j] + cc[j]) * sl;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) z[j] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) bv[j] = __shfl_sync(0xffffffffu, bl, 16 * sub + j);
-            float nx[16];
-            step_group(S, p, row, row_ok, col0, z, bv, pe, sgn_scaled, true, nx);
-            if (S.kind == ST_FWD_LAST && col0 == 0) {
-              const float y0 = nx[0];
-              ctl->rowsgn[r_in] = (y0 > 0.f ? 1.f : (y0 < 0.f ? -1.f : 0.f)) * p.inv_scale;
-            }
-            if (S.n_next > 0) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) rmax = fmaxf(rmax, fabsf(nx[j]));
-              if (has_gemm) tmem_st16(t_m + (uint32_t)c0, nx);       // parked in TMEM (over M) until the row scale is known
-            }
-          }
-          if (has_acc && S.n_next == 0) {                            // nothing continues: the accumulator pair is free again
-            tcgen05_fence_before();
-            mbar_arrive(&ctl->acc_empty[slot]);
-          }
+        const ChainStep& G = p.S[l];
+        CH_TRS(0);
+        if (G.sync_before) epi_bar_sync();
+        switch (G.kind) {
+          case ST_PE: epi_step_pe<false>(G, p, ctl, a_smem, e, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_EDOT: epi_step_pe<true>(G, p, ctl, a_smem, e, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_FWD: epi_step_gemm<ST_FWD>(G, p, ctl, a_smem, e, af_cnt, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_REV: epi_step_gemm<ST_REV>(G, p, ctl, a_smem, e, af_cnt, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_TAN: epi_step_gemm<ST_TAN>(G, p, ctl, a_smem, e, af_cnt, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_BWD: epi_step_gemm<ST_BWD>(G, p, ctl, a_smem, e, af_cnt, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_FWD_LAST: epi_step_tail<ST_FWD_LAST>(G, p, ctl, e, af_cnt, sa, tr_on, tr_role, l); break;
+          case ST_REV_FINAL: epi_step_tail<ST_REV_FINAL>(G, p, ctl, e, af_cnt, sa, tr_on, tr_role, l); break;
+          case ST_LOAD: epi_step_nogemm<ST_LOAD>(G, p, ctl, a_smem, e, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_REV_SEED: epi_step_nogemm<ST_REV_SEED>(G, p, ctl, a_smem, e, lp, sa, inv, tr_on, tr_role, l); break;
+          default: break;
         }
-        CH_TR(tr_role, l, 2, clock64());
-        if (S.n_next > 0) {
-          if (has_gemm) tmem_wait_st();
-          ctl->rowexp[lp][cq][r_in] = (uint8_t)expo_bits(rmax);
-          epi_bar_sync();            // all MMAs of this step are complete (every warp waited for every tile), all maxima are in
-          CH_TR(tr_role, l, 3, clock64());
-          {
-            const uint32_t e01 = max((uint32_t)ctl->rowexp[lp][0][r_in], (uint32_t)ctl->rowexp[lp][1][r_in]);
-            const uint32_t e23 = max((uint32_t)ctl->rowexp[lp][2][r_in], (uint32_t)ctl->rowexp[lp][3][r_in]);
-            row_scale(max(e01, e23), sa, inv);
-          }
-          lp ^= 1;
-          // ---------------- pass 2: slice the new operand into the A planes ----------------
-          const int nks_next = pad64(S.n_next) / 64;
-          const int n_nx_tiles = (S.n_next + CH_NT - 1) / CH_NT;
-#pragma unroll 1
-          for (int t = 0; t < n_out_tiles; ++t) {
-            const int slot = t & 1;
-            const int s = 2 * t + (cq >> 1);                 // K slice of the next GEMM this warp's columns belong to
-            const uint32_t t_m = t_lane + (uint32_t)slot * 256u;
-            if (t < n_nx_tiles && s < nks_next) {
-              uint8_t* sl_base = a_smem + (size_t)s * 2 * CH_APLANE;
-#pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
-                const int c0 = 32 * cq + 16 * sub;
-                float v[16];
-                if (has_gemm) {
-                  tmem_ld16(t_m + (uint32_t)c0, v);
-                } else {
-                  float z[16], bv[16];
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) { z[j] = 0.f; bv[j] = 0.f; }
-                  step_group(S, p, row, row_ok, CH_NT * t + c0, z, bv, pe, sgn_scaled, false, v);   // cheap to recompute
-                }
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                  uint4 p0, p1;
-                  slice8(v + 8 * g, inv, p0, p1);
-                  const uint32_t off = sw128((uint32_t)r_in, (uint32_t)((cq & 1) * 32 + 16 * sub + 8 * g));
-                  *reinterpret_cast<uint4*>(sl_base + off) = p0;
-                  *reinterpret_cast<uint4*>(sl_base + CH_APLANE + off) = p1;
-                }
-              }
-              fence_proxy_async();
-              mbar_arrive(&ctl->a_ready[s]);
-            }
-            if (t < S.n_tiles) {
-              tcgen05_fence_before();
-              mbar_arrive(&ctl->acc_empty[slot]);
-            }
-          }
-        }
-        CH_TR(tr_role, l, 4, clock64());
+        CH_TRS(4);
       }
       epi_bar_sync();     // every MMA of this point tile has completed (all warps waited for the last N tile): the A planes
                           // may be overwritten by the next point tile's first operand

@@ -467,6 +467,7 @@ static void chain_common(const UdfPlan& p, const float* wfold, const float* pts,
   cp->img = img_base(p, wfold);
   cp->pts = pts; cp->P = P; cp->scale = p.scale; cp->n_freq = p.L; cp->d_pe = p.d_pe;
   cp->gbar = nullptr;
+  cp->pe_src = nullptr; cp->pe_ld = p.pe_ld; cp->pe_cta = 0;
   cp->t128 = fused_on(p) ? 1 : 0;
   cp->udf_out = nullptr; cp->inv_scale = 1.0f / p.scale;
   cp->trace = nullptr;
@@ -483,7 +484,10 @@ static void build_forward(const UdfPlan& p, const float* wfold, const float* pts
   cp->udf_out = udf;
   chain::ChainStep* S = add_step(cp, chain::ST_PE);
   S->n_next = p.d_pe;
-  if (!value_only) { S->out0 = ctx + c->e0; S->ld_out0 = p.pe_ld; }
+  // E0 is written for the weight gradients and re-read by the skip layer; a value-only launch keeps a 128-row stash per CTA in
+  // `ctx` (= the caller's work buffer) instead, in the T128 layout
+  if (!value_only) { S->out0 = ctx + c->e0; S->ld_out0 = p.pe_ld; cp->pe_src = ctx + c->e0; }
+  else if (p.skip >= 1) { S->out0 = ctx; S->ld_out0 = p.pe_ld; cp->pe_src = ctx; cp->pe_cta = 1; cp->t128 = 1; }
   for (int l = 0; l < last; ++l) {
     S = add_step(cp, chain::ST_FWD);
     set_gemm(S, p, wfold, l, p.in_dim[l], p.out_dim[l], p.img_chain[l]);
@@ -538,6 +542,7 @@ static void build_backward(const UdfPlan& p, const float* wfold, const float* pt
     S = add_step(cp, chain::ST_EDOT);
     S->n_next = p.d_pe;
     S->out0 = scr + s.edot; S->ld_out0 = p.pe_ld;
+    cp->pe_src = scr + s.edot;
     for (int l = 0; l < last; ++l) {
       S = add_step(cp, chain::ST_TAN);
       set_gemm(S, p, wfold, l, p.in_dim[l], p.out_dim[l], p.img_chain[l]);
@@ -752,12 +757,12 @@ int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts,
   if (P <= 0) return 0;
   NUDF_REQUIRE(wfold && pts && udf, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  NUDF_REQUIRE(work != nullptr, "null pointer (work)");
   if (p.chain_ok && tc_on(TC_FWD)) {
     chain::ChainParams cp;
-    build_forward(p, wfold, pts, P, nullptr, nullptr, udf, false, &cp);
+    build_forward(p, wfold, pts, P, work, nullptr, udf, false, &cp);     // work: per-CTA stash of the encoding (first ctx_rows x pe_ld floats)
     return chain::launch_chain(cp, FAM_UDF_FWD_CHAIN, st);
   }
-  NUDF_REQUIRE(work != nullptr, "null pointer (work)");
   UdfCtx c;
   ctx_layout(p, P, 0, &c);
   // value-only: the last layer needs only its row 0 (the udf head); the 256 feature rows are skipped.
