@@ -56,6 +56,7 @@ constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;           // 512
 constexpr int CH_MMA_WARP = 16, CH_LOAD_WARP = 17;
 constexpr int CH_THREADS = 576;
 constexpr int CH_MAX_STEPS = 24;
+constexpr int CH_MAX_GRID = 148;                           // CTAs per launch (<= SM count); sizes the per-CTA encoding stash
 #ifndef CH_RING2
 #define CH_RING2 2
 #endif
@@ -81,6 +82,7 @@ struct ChainStep {
   int n_kslices, n_tiles;    // of the GEMM
   int rows_override;         // > 0: fetch / multiply only this many weight rows of tile 0 (value-only last layer)
   int img_N;                 // N the weight image was laid out for (differs from N only in the value-only last layer)
+  int n_wpl;                 // weight planes of the GEMM: 3 = exact fp16 slice scheme (F chain), 2 = split-bf16 (R, T, B chains)
   int n_main;                // REV / BWD: output columns that continue the chain
   int n_next;                // width of the operand this step produces for the next GEMM (0: none)
   int sync_before;           // 1: the step starts with a barrier of the epilogue warps (reads state other threads wrote)
@@ -100,11 +102,15 @@ struct ChainParams {
   const uint16_t* img;
   const float* pts; int64_t P; float scale; int n_freq, d_pe;
   const float* gbar;                     // T chain: upstream gradient of grad_x udf [P,3]
-  const float* pe_src; int pe_ld;        // the tensor the first step wrote (E0 / Edot): re-read for the skip layer's appended columns
-  int pe_cta;                            // 1: that tensor is a per-CTA stash of 128 rows (value-only launches keep no context)
+  const float* pe_src; int pe_ld;        // per-CTA stash (128 rows per CTA, T128, pe_ld columns) of what the first step made (PE / Edot),
+  int pe_cta;                            // re-read for the skip layer's appended columns; always CTA-local rows (pe_cta = 1)
+  int pe_sh;                             // stash column = encoding column + pe_sh, pe_sh = (width of the skip layer's main part) % 8:
+                                         // the appended columns of the skip layer then sit at octet-aligned stash columns
   int t128;                              // 1: every [P, ld] tensor of the steps is stored in the T128 layout (common.cuh)
   float* udf_out; float inv_scale;       // value-only mode: udf_out[P] = |y_0| / scale
   long long* trace;                      // profiling aid (NUDF_CHAIN_TRACE=n): clock64() stamps of CTA 0, first point tile
+  int dbg;                               // profiling aid (NUDF_CHAIN_DEBUG bit mask, WRONG RESULTS): 1 no global stores, 2 no MUFU,
+                                         // 4 no TMEM parking, 8 no accumulator loads, 16 no auxiliary loads, 32 no operand slicing
 };
 // trace layout: [role 0 = epilogue warp 0, 1 = epilogue warp 12, 2 = MMA issuer][step][8]
 constexpr int CH_TRACE_WORDS = 3 * CH_MAX_STEPS * 8;
@@ -147,7 +153,7 @@ static __global__ void chain_layer_scale_kernel(const float* __restrict__ W, int
 // transposed == 1: B(n,k) = W[k*ldw + n] (dY W).  bias_tab (optional): [128 n_tiles] copy of bias, zero padded.
 static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int N, int K,
                                          int transposed, const float* __restrict__ meta, uint16_t* __restrict__ img,
-                                         float* __restrict__ bias_tab) {
+                                         float* __restrict__ bias_tab, int split_bf16 = 0) {
   const int col = blockIdx.x;                    // padded output column: 128 t + local row
   const int t = col / CH_NT, nl = col - t * CH_NT;
   const int rows_t = ch_tile_rows(N, t);
@@ -155,11 +161,20 @@ static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ld
   if (threadIdx.x == 0 && bias_tab != nullptr) bias_tab[col] = (valid && bias) ? bias[col] : 0.f;
   if (nl >= rows_t) return;                      // beyond the padded tile: only the bias table entry exists
   const int Kp = pad64(K);
-  const float up = meta[0];                      // 2^(3 - E): scaled weights are in (-8, 8)
+  const float up = split_bf16 ? 1.0f : meta[0];  // 2^(3 - E): scaled weights are in (-8, 8)
   uint16_t* base = img + ch_tile_off(N, K, t);
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
     float w = 0.f;
     if (valid && k < K) w = (transposed ? W[(int64_t)k * ldw + col] : W[(int64_t)col * ldw + k]) * up;
+    if (split_bf16) {                            // planes 0, 1 = bf16(w), bf16(w - plane 0); plane 2 unused
+      const __nv_bfloat16 b0 = __float2bfloat16_rn(w);
+      const __nv_bfloat16 b1 = __float2bfloat16_rn(w - __bfloat162float(b0));
+      const uint32_t off = sw128((uint32_t)nl, (uint32_t)(k & 63)) >> 1;
+      uint16_t* b = base + (int64_t)(k >> 6) * CH_WPL * rows_t * 64 + off;
+      b[0] = __bfloat16_as_ushort(b0);
+      b[(int64_t)rows_t * 64] = __bfloat16_as_ushort(b1);
+      continue;
+    }
     const float w0 = rintf(w);
     const float r1 = (w - w0) * 1024.0f;
     const __half h1 = __float2half_rn(r1);
@@ -411,18 +426,25 @@ __device__ __forceinline__ void slice_store8(const float v[8], float inv, uint8_
 
 struct StepR {                        // the fields of a step the fast paths use, read once per step
   int N, n_tiles, rows_override, n_main, n_next, n_cols, n_out_tiles;
+  int ld_in0, ld_in1, ld_out0, ld_out1;
+  int pe_base;                        // FWD / TAN skip layer: stash column of logical column c is c - pe_base (N rounded down to 8)
+  int gpe_base;                       // REV skip layer: likewise for the shifted Gpe tensor (n_main rounded down to 8)
   float ps, ak, rz;
   bool has_rowv;
   const float* bias; const float* vec0;
   const float* in0r; const float* in1r; float* out0r; float* out1r;      // row pointers (base + row_off) or null
+  const float* pesr;                  // this thread's row of the encoding stash (T128) or null
 };
-__device__ __forceinline__ StepR load_step(const ChainStep& G, const EpiT& e) {
+__device__ __forceinline__ StepR load_step(const ChainStep& G, const ChainParams& p, const EpiT& e) {
   StepR S;
   S.N = G.N; S.n_tiles = G.n_tiles; S.rows_override = G.rows_override; S.n_main = G.n_main; S.n_next = G.n_next;
   int n_cols = G.n_next > G.N ? G.n_next : G.N;
   if (G.kind == ST_TAN && G.n_main > n_cols) n_cols = G.n_main;
   S.n_cols = n_cols;
   S.n_out_tiles = (n_cols + CH_NT - 1) / CH_NT;
+  S.ld_in0 = G.ld_in0; S.ld_in1 = G.ld_in1; S.ld_out0 = G.ld_out0; S.ld_out1 = G.ld_out1;
+  S.pe_base = G.N & ~7;
+  S.gpe_base = G.n_main & ~7;
   S.ps = G.post_scale;
   S.ak = -144.26950408889634f * G.a_unscale;
   S.has_rowv = G.rowv != nullptr;
@@ -432,114 +454,127 @@ __device__ __forceinline__ StepR load_step(const ChainStep& G, const EpiT& e) {
   S.in1r = G.in1 ? G.in1 + row_off(G.ld_in1, e.row, e.t128) : nullptr;
   S.out0r = G.out0 ? G.out0 + row_off(G.ld_out0, e.row, e.t128) : nullptr;
   S.out1r = G.out1 ? G.out1 + row_off(G.ld_out1, e.row, e.t128) : nullptr;
+  S.pesr = p.pe_src ? p.pe_src + row_off(p.pe_ld, e.srow, true) : nullptr;
   return S;
 }
 
-// Generic octet (any column range, any layout): z[8] in = scaled accumulator values (zeros for steps without a GEMM), out = the
-// value that continues the chain.  Performs the step's stores when do_store.  Out of line on purpose (boundary octets only).
-__device__ __noinline__ void octet_slow(const ChainStep* S, const ChainParams* p, int64_t row, int64_t srow, bool row_ok, int col0,
-                                        float sgn_scaled, bool do_store, float* z) {
-  const bool T = p->t128 != 0;
+// Generic octet for ROW-MAJOR tensors (t128 == 0: the F chain of a partially fused configuration -- only PE / FWD / FWD_LAST
+// steps exist there): z[8] in = accumulator values, out = the value that continues the chain; performs the step's stores.
+__device__ __noinline__ void octet_slow(const ChainStep* S, const ChainParams* p, int64_t row, int64_t srow, bool row_ok, int col0, float* z) {
   const int kind = S->kind;
-  const float ak = -144.26950408889634f * S->a_unscale;
   const float ps = S->post_scale;
-  const bool st = do_store && row_ok;
+  const int N = S->N, n_next = S->n_next;
 #pragma unroll 1
   for (int j = 0; j < 8; ++j) {
     const int col = col0 + j;
     const float zz = z[j];
     float nx = 0.f;
     if (kind == ST_FWD) {
-      if (col < S->N) nx = softplus100_fast(zz + __ldg(S->bias + col)) * ps;
-      else if (col < S->n_next) nx = (row_ok ? p->pe_src[mat_off(T, srow, col - S->N, p->pe_ld)] : 0.f) * ps;
-      if (st && S->out0 != nullptr && col < S->n_next) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
+      if (col < N) nx = softplus100_fast(zz + __ldg(S->bias + col)) * ps;
+      else if (col < n_next) nx = (row_ok ? p->pe_src[t128_off(srow, col - (N & ~7), p->pe_ld)] : 0.f) * ps;      // stash: T128, shifted
+      if (row_ok && S->out0 != nullptr && col < n_next) S->out0[row * S->ld_out0 + col] = nx;
     } else if (kind == ST_FWD_LAST) {
-      if (col < S->N) {
+      if (col < N) {
         nx = zz + __ldg(S->bias + col);
-        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
+        if (row_ok && S->out0 != nullptr) S->out0[row * S->ld_out0 + col] = nx;
       }
-    } else if (kind == ST_REV || kind == ST_REV_SEED) {
-      float raw = zz;
-      if (kind == ST_REV_SEED) raw = (col < S->N) ? sgn_scaled * __ldg(S->vec0 + col) : 0.f;     // S->N = width of the last layer's input
-      const float gp = raw * ps;
-      if (col < S->n_main) {
-        const float a = row_ok ? S->in0[mat_off(T, row, col, S->ld_in0)] : 0.f;
-        nx = gp * sig_ak(a, ak);
-        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
-      } else if (col < S->N && st && S->out1 != nullptr) {                  // skip layer: gradient w.r.t. the PE columns
-        S->out1[mat_off(T, row, col - S->n_main, S->ld_out1)] = gp;
-      }
-    } else if (kind == ST_REV_FINAL) {
-      if (col < S->N) {
-        const float g = (S->in1 != nullptr && row_ok) ? S->in1[mat_off(T, row, col, S->ld_in1)] : 0.f;
-        nx = zz + g;
-        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
-      }
-    } else if (kind == ST_TAN) {
-      if (col < S->N) {
-        const float a = row_ok ? S->in0[mat_off(T, row, col, S->ld_in0)] : 0.f;
-        const float d = row_ok ? S->in1[mat_off(T, row, col, S->ld_in1)] : 0.f;
-        const float s = sig_ak(a, ak);
-        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = zz * d * (100.0f * (1.0f - s));
-        nx = s * zz * ps;
-      } else if (col < S->n_main) {                  // Edot columns appended at the skip layer
-        nx = (row_ok ? p->pe_src[mat_off(T, srow, col - S->N, p->pe_ld)] : 0.f) * ps;
-      }
-      if (st && S->out1 != nullptr && col < S->n_main) S->out1[mat_off(T, row, col, S->ld_out1)] = nx;
-    } else if (kind == ST_BWD) {
-      if (col < S->n_main) {
-        const float a = row_ok ? S->in0[mat_off(T, row, col, S->ld_in0)] : 0.f;
-        const float q = row_ok ? S->in1[mat_off(T, row, col, S->ld_in1)] : 0.f;
-        float ab = zz;
-        if (S->rowv != nullptr) ab = fmaf(row_ok ? S->rowv[row] : 0.f, __ldg(S->vec0 + col), ab);
-        nx = ab * ps * sig_ak(a, ak) + q;
-        if (st && S->out0 != nullptr) S->out0[mat_off(T, row, col, S->ld_out0)] = nx;
-      }
-    } else if (kind == ST_LOAD) {
-      if (row_ok && col < S->n_next) nx = S->in0[mat_off(T, row, col, S->ld_in0)];
     }
     z[j] = nx;
   }
 }
 
-// interior octet of a GEMM step (T128, col0 + 8 <= the step's main column count); a / b: prefetched auxiliary octets
+// One octet of a step on T128 tensors.  a / b: prefetched auxiliary octets (FWD: a = bias).  Columns beyond the step's ranges
+// come out as exact zeros (they are the tensors' padding and the next operand's K padding).  Interior octets (`full`) take the
+// predicate-free branch; boundary octets (skip-layer columns, last partial octet) the masked one.
 template <int KIND>
 __device__ __forceinline__ void octet_fast(const StepR& S, const EpiT& e, int col0, float z[8], const float a[8], float b[8]) {
-  if (KIND == ST_FWD) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(S.bias + col0)), b1 = __ldg(reinterpret_cast<const float4*>(S.bias + col0 + 4));
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  if (KIND == ST_FWD) {                    // a = the bias octet
+    const int n1 = S.N - col0;             // columns j < n1: softplus; n1 <= j < n2: appended encoding (skip layer); else 0
+    if (n1 >= 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = softplus100_fast(z[j] + bb[j]) * S.ps;
-    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
-  } else if (KIND == ST_FWD_LAST) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(S.bias + col0)), b1 = __ldg(reinterpret_cast<const float4*>(S.bias + col0 + 4));
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int j = 0; j < 8; ++j) z[j] = softplus100_fast(z[j] + a[j]) * S.ps;
+    } else {
+      const int n2 = S.n_next - col0;
+      float pe[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] += bb[j];
-    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
+      for (int j = 0; j < 8; ++j) pe[j] = 0.f;
+      if (n2 > n1 && n2 > 0 && e.row_ok && S.pesr != nullptr) ldg8(S.pesr, col0 - S.pe_base, pe);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sp = softplus100_fast(z[j] + a[j]);
+        z[j] = (j < n1 ? sp : (j < n2 ? pe[j] : 0.f)) * S.ps;
+      }
+    }
+    if (S.out0r != nullptr && e.row_ok && col0 < S.ld_out0) stg8(S.out0r, col0, z);
+  } else if (KIND == ST_FWD_LAST) {        // a = the bias octet
+    const int n1 = S.N - col0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = (j < n1) ? z[j] + a[j] : 0.f;
+    if (S.out0r != nullptr && e.row_ok && col0 < S.ld_out0) stg8(S.out0r, col0, z);
   } else if (KIND == ST_REV || KIND == ST_REV_SEED) {
+    const int n1 = S.n_main - col0;        // j < n1: D = G s(A); n1 <= j (< N): gradient w.r.t. the appended PE columns -> shifted Gpe
+    if (n1 >= 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = z[j] * S.ps * sig_ak(a[j], S.ak);
-    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
+      for (int j = 0; j < 8; ++j) z[j] = z[j] * S.ps * sig_ak(a[j], S.ak);
+    } else {
+      const int n2 = S.N - col0;
+      float gp[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = z[j] * S.ps;
+        gp[j] = (j >= n1 && j < n2) ? g : 0.f;
+        z[j] = (j < n1) ? g * sig_ak(a[j], S.ak) : 0.f;
+      }
+      if (S.out1r != nullptr && e.row_ok) stg8(S.out1r, col0 - S.gpe_base, gp);
+    }
+    if (S.out0r != nullptr && e.row_ok && col0 < S.ld_out0) stg8(S.out0r, col0, z);
+  } else if (KIND == ST_REV_FINAL) {
+    const int n1 = S.N - col0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = (j < n1) ? z[j] : 0.f;
+    if (S.out0r != nullptr && e.row_ok && col0 < S.ld_out0) stg8(S.out0r, col0, z);
   } else if (KIND == ST_TAN) {
+    const int n1 = S.N - col0;             // j < n1: q = zdot d 100 (1 - s), adot = s zdot; n1 <= j < n2: appended Edot columns
+    if (n1 >= 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s = sig_ak(a[j], S.ak);
-      b[j] = z[j] * b[j] * (100.0f * (1.0f - s));
-      z[j] = s * z[j] * S.ps;
+      for (int j = 0; j < 8; ++j) {
+        const float s = sig_ak(a[j], S.ak);
+        b[j] = z[j] * b[j] * (100.0f * (1.0f - s));
+        z[j] = s * z[j] * S.ps;
+      }
+    } else {
+      const int n2 = S.n_main - col0;
+      float pe[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pe[j] = 0.f;
+      if (n2 > n1 && n2 > 0 && e.row_ok && S.pesr != nullptr) ldg8(S.pesr, col0 - S.pe_base, pe);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = sig_ak(a[j], S.ak);
+        const float q = z[j] * b[j] * (100.0f * (1.0f - s));
+        const float n = s * z[j];
+        b[j] = (j < n1) ? q : 0.f;
+        z[j] = (j < n1 ? n : (j < n2 ? pe[j] : 0.f)) * S.ps;
+      }
     }
     if (e.row_ok) {
-      if (S.out0r != nullptr) stg8(S.out0r, col0, b);
-      if (S.out1r != nullptr) stg8(S.out1r, col0, z);
+      if (S.out0r != nullptr && col0 < S.ld_out0) stg8(S.out0r, col0, b);
+      if (S.out1r != nullptr && col0 < S.ld_out1) stg8(S.out1r, col0, z);
     }
   } else if (KIND == ST_BWD) {
+    const int n1 = S.n_main - col0;
     if (S.has_rowv) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = fmaf(S.rz, __ldg(S.vec0 + col0 + j), z[j]);
+      for (int j = 0; j < 8; ++j) z[j] = fmaf(S.rz, (j < n1) ? __ldg(S.vec0 + col0 + j) : 0.f, z[j]);
     }
+    if (n1 >= 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = z[j] * S.ps * sig_ak(a[j], S.ak) + b[j];
-    if (S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
+      for (int j = 0; j < 8; ++j) z[j] = z[j] * S.ps * sig_ak(a[j], S.ak) + b[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = (j < n1) ? z[j] * S.ps * sig_ak(a[j], S.ak) + b[j] : 0.f;
+    }
+    if (S.out0r != nullptr && e.row_ok && col0 < S.ld_out0) stg8(S.out0r, col0, z);
   }
 }
 
@@ -555,65 +590,107 @@ __device__ __forceinline__ void exchange_scale(ChainCtl* ctl, const EpiT& e, flo
 
 #define CH_TRS(k) do { if (tr_on) p.trace[(tr_role * CH_MAX_STEPS + l) * 8 + (k)] = clock64(); } while (0)
 
+// accumulator loads without the wait, and the wait with the destination registers as in/out operands: nothing that uses
+// them can be scheduled above it
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t ta, float v[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(ta)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_fence8(float v[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+// 8 consecutive values -> split-bf16 planes (hi = bf16(x), lo = bf16(x - hi)) of K slice `sl_base`
+__device__ __forceinline__ void split_store8(const float v[8], uint8_t* sl_base, int r_in, int kcol) {
+  uint32_t h[4], lo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    h[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+    lo[q] = pack_bf16(v[2 * q] - __uint_as_float(h[q] << 16), v[2 * q + 1] - __uint_as_float(h[q] & 0xFFFF0000u));
+  }
+  const uint32_t off = sw128((uint32_t)r_in, (uint32_t)kcol);
+  *reinterpret_cast<uint4*>(sl_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(sl_base + CH_APLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// the step's own GEMM ran in the exact fp16 scheme (two accumulators, row-scaled operand) -- F chain; the others split-bf16
+#ifndef CH_ALL_EXACT
+#define CH_ALL_EXACT 0
+#endif
+__host__ __device__ constexpr bool kind_exact(int kind) { return CH_ALL_EXACT || kind == ST_FWD || kind == ST_FWD_LAST; }
+
 // ---- steps with a GEMM whose output is at most two N tiles wide (FWD, REV, TAN, BWD) ----
 template <int KIND>
 __device__ __forceinline__ void epi_step_gemm(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, uint8_t* a_smem, const EpiT& e,
                                               uint32_t (&af_cnt)[2], uint32_t& lp, float& sa, float& inv, bool tr_on, int tr_role, int l) {
-  constexpr int NAUX = (KIND == ST_REV) ? 1 : ((KIND == ST_TAN || KIND == ST_BWD) ? 2 : 0);
-  const StepR S = load_step(G, e);
-  const float sl = sa * __ldg(G.wscale);                         // z = sl (M + C)
-  const int lim = (KIND == ST_FWD || KIND == ST_TAN) ? S.N : S.n_main;
-  constexpr int RD = (NAUX == 2) ? CH_RING2 : 3;            // ring depth; prefetch distance RD - 1 octets
+  constexpr bool EXACT = kind_exact(KIND);
+  constexpr int NAUX = (KIND == ST_REV || KIND == ST_FWD) ? 1 : 2;          // FWD: the bias octet travels through the ring
+  const StepR S = load_step(G, p, e);
+  const float sl = EXACT ? sa * __ldg(G.wscale) : 1.0f;          // exact scheme: z = sl (M + C)
+  constexpr int RD = (NAUX == 2) ? CH_RING2 : 3;                 // ring depth; prefetch distance RD - 1 octets
   float ax[RD][8], bx[RD][8];
   auto col_of = [&](int g) { return CH_NT * (g >> 2) + 32 * e.cq + 8 * (g & 3); };
   auto prefetch = [&](int g, float (&a)[8], float (&b)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
     const int c = col_of(g);
-    if (NAUX >= 1 && e.t128 && e.row_ok && c + 8 <= lim) {
-      ldg8(S.in0r, c, a);
-      if (NAUX == 2) ldg8(S.in1r, c, b);
+    if (e.t128 && c < S.n_cols) {
+      if (KIND == ST_FWD) {
+        if (c < CH_NT * S.n_tiles) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(S.bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(S.bias + c + 4));
+          a[0] = b0.x; a[1] = b0.y; a[2] = b0.z; a[3] = b0.w; a[4] = b1.x; a[5] = b1.y; a[6] = b1.z; a[7] = b1.w;
+        }
+      } else if (e.row_ok) {
+        if (c < S.ld_in0) ldg8(S.in0r, c, a);
+        if (NAUX == 2 && c < S.ld_in1) ldg8(S.in1r, c, b);
+      }
     }
   };
   float rmax = 0.f;
-  if (NAUX > 0) {
 #pragma unroll
-    for (int g = 0; g < RD - 1; ++g) prefetch(g, ax[g], bx[g]);
-  }
+  for (int g = 0; g < RD - 1; ++g) prefetch(g, ax[g], bx[g]);
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const int t = g >> 2, o = g & 3;
     if (t < S.n_out_tiles) {
       const int slot = t & 1;
-      const bool has_acc = t < S.n_tiles;
-      if (o == 0 && has_acc) {
+      if (o == 0 && t < S.n_tiles) {
         mbar_wait(&ctl->acc_full[slot], af_cnt[slot] & 1u);
         ++af_cnt[slot];
         tcgen05_fence_after();
         if (t == 0) CH_TRS(1);
       }
-      if (NAUX > 0 && g + RD - 1 < 8 && ((g + RD - 1) >> 2) < S.n_out_tiles) prefetch(g + RD - 1, ax[(g + RD - 1) % RD], bx[(g + RD - 1) % RD]);
+      if (g + RD - 1 < 8 && ((g + RD - 1) >> 2) < S.n_out_tiles) prefetch(g + RD - 1, ax[(g + RD - 1) % RD], bx[(g + RD - 1) % RD]);
       const int c0 = 32 * e.cq + 8 * o, col0 = CH_NT * t + c0;
       const uint32_t t_m = e.t_lane + (uint32_t)slot * 256u + (uint32_t)c0;
-      const int rows_t = has_acc ? (S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t)) : 0;
+      const int rows_t = (t < S.n_tiles) ? (S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t)) : 0;
       float z[8];
       if (c0 < rows_t) {
-        float cc[8];
-        tmem_ld8x2(t_m, t_m + 128u, z, cc);
+        if (EXACT) {
+          float cc[8];
+          tmem_ld8x2(t_m, t_m + 128u, z, cc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = (z[j] + cc[j]) * sl;
+          for (int j = 0; j < 8; ++j) z[j] = (z[j] + cc[j]) * sl;
+        } else {
+          tmem_ld8(t_m, z);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) z[j] = 0.f;
       }
       if (col0 < S.n_cols) {
-        if (e.t128 && col0 + 8 <= lim) {
+        if (e.t128) {
           octet_fast<KIND>(S, e, col0, z, ax[g % RD], bx[g % RD]);
-        } else {
+        } else {                               // row-major tensors (partially fused configurations: F chain only)
           float zs[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) zs[j] = z[j];
-          octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, 0.f, true, zs);
+          octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, zs);
 #pragma unroll
           for (int j = 0; j < 8; ++j) z[j] = zs[j];
         }
@@ -622,11 +699,13 @@ __device__ __forceinline__ void epi_step_gemm(const ChainStep& G, const ChainPar
         for (int j = 0; j < 8; ++j) z[j] = 0.f;
       }
       if (S.n_next > 0) {
+        if (EXACT) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rmax = fmaxf(rmax, fabsf(z[j]));
-        tmem_st8(t_m, z);                                            // parked in TMEM (over M) until the row scale is known
+          for (int j = 0; j < 8; ++j) rmax = fmaxf(rmax, fabsf(z[j]));
+        }
+        tmem_st8(t_m, z);                                            // parked in TMEM (over the main accumulator)
       }
-      if (o == 3 && has_acc && S.n_next == 0) {                      // nothing continues: the accumulator pair is free again
+      if (o == 3 && t < S.n_tiles && S.n_next == 0) {                // nothing continues: the accumulators are free again
         tcgen05_fence_before();
         mbar_arrive(&ctl->acc_empty[slot]);
       }
@@ -635,7 +714,9 @@ __device__ __forceinline__ void epi_step_gemm(const ChainStep& G, const ChainPar
   CH_TRS(2);
   if (S.n_next > 0) {
     tmem_wait_st();
-    exchange_scale(ctl, e, rmax, lp, sa, inv);
+    // exact scheme: the row scale needs every warp's partial maximum (barrier).  Split-bf16: no scale; this warp has waited
+    // for every tile's accumulator, so all MMAs that read the current A planes are complete -- it may overwrite its columns.
+    if (EXACT) exchange_scale(ctl, e, rmax, lp, sa, inv);
     CH_TRS(3);
     // ---------------- pass 2: slice the new operand into the A planes ----------------
     const int nks_next = pad64(S.n_next) / 64;
@@ -650,7 +731,8 @@ __device__ __forceinline__ void epi_step_gemm(const ChainStep& G, const ChainPar
         for (int o = 0; o < 4; ++o) {
           float v[8];
           tmem_ld8(e.t_lane + (uint32_t)slot * 256u + (uint32_t)(32 * e.cq + 8 * o), v);
-          slice_store8(v, inv, sl_base, e.r_in, (e.cq & 1) * 32 + 8 * o);
+          if (EXACT) slice_store8(v, inv, sl_base, e.r_in, (e.cq & 1) * 32 + 8 * o);
+          else split_store8(v, sl_base, e.r_in, (e.cq & 1) * 32 + 8 * o);
         }
         fence_proxy_async();
         mbar_arrive(&ctl->a_ready[s]);
@@ -667,9 +749,9 @@ __device__ __forceinline__ void epi_step_gemm(const ChainStep& G, const ChainPar
 template <int KIND>
 __device__ __forceinline__ void epi_step_tail(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, const EpiT& e, uint32_t (&af_cnt)[2],
                                               float sa, bool tr_on, int tr_role, int l) {
-  const StepR S = load_step(G, e);
-  const float sl = sa * __ldg(G.wscale);
-  float dummy[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  constexpr bool EXACT = kind_exact(KIND);
+  const StepR S = load_step(G, p, e);
+  const float sl = EXACT ? sa * __ldg(G.wscale) : 1.0f;
 #pragma unroll 1
   for (int t = 0; t < S.n_out_tiles; ++t) {
     const int slot = t & 1;
@@ -686,17 +768,28 @@ __device__ __forceinline__ void epi_step_tail(const ChainStep& G, const ChainPar
       const int c0 = 32 * e.cq + 8 * o, col0 = CH_NT * t + c0;
       if (col0 < S.n_cols && c0 < rows_t) {
         const uint32_t t_m = e.t_lane + (uint32_t)slot * 256u + (uint32_t)c0;
-        float z[8], cc[8];
-        tmem_ld8x2(t_m, t_m + 128u, z, cc);
+        float z[8], bb[8];
+        if (EXACT) {
+          float cc[8];
+          tmem_ld8x2(t_m, t_m + 128u, z, cc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = (z[j] + cc[j]) * sl;
-        if (KIND == ST_FWD_LAST && e.t128 && col0 + 8 <= S.N) {
-          octet_fast<ST_FWD_LAST>(S, e, col0, z, dummy, dummy);
+          for (int j = 0; j < 8; ++j) z[j] = (z[j] + cc[j]) * sl;
+        } else {
+          tmem_ld8(t_m, z);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bb[j] = 0.f;
+        if (e.t128) {
+          if (KIND == ST_FWD_LAST) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(S.bias + col0)), b1 = __ldg(reinterpret_cast<const float4*>(S.bias + col0 + 4));
+            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+          }
+          octet_fast<KIND>(S, e, col0, z, bb, bb);
         } else {
           float zs[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) zs[j] = z[j];
-          octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, 0.f, true, zs);
+          octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, zs);
 #pragma unroll
           for (int j = 0; j < 8; ++j) z[j] = zs[j];
         }
@@ -715,75 +808,43 @@ __device__ __forceinline__ void epi_step_tail(const ChainStep& G, const ChainPar
   CH_TRS(2);
 }
 
-// ---- steps without a GEMM that make an operand from global data: LOAD (zf), REV_SEED ----
+// ---- steps without a GEMM that make a split-bf16 operand from global data (T128 only): LOAD (zf), REV_SEED ----
 template <int KIND>
 __device__ __forceinline__ void epi_step_nogemm(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, uint8_t* a_smem, const EpiT& e,
-                                                uint32_t& lp, float& sa, float& inv, bool tr_on, int tr_role, int l) {
-  const StepR S = load_step(G, e);
+                                                bool tr_on, int tr_role, int l) {
+  const StepR S = load_step(G, p, e);
   const float sgn_scaled = (KIND == ST_REV_SEED) ? ctl->rowsgn[e.r_in] : 0.f;
-  const int lim = (KIND == ST_REV_SEED) ? S.n_main : S.n_next;
-  auto produce = [&](int col0, bool do_store, float (&z)[8]) {
-    if (col0 >= S.n_cols) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = 0.f;
-      return;
-    }
-    if (e.t128 && col0 + 8 <= lim) {
-      if (KIND == ST_LOAD) {
-        if (e.row_ok) ldg8(S.in0r, col0, z);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) z[j] = 0.f;
-        }
-      } else {
-        float a[8];
-        if (e.row_ok) ldg8(S.in0r, col0, a);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = sgn_scaled * __ldg(S.vec0 + col0 + j) * S.ps * sig_ak(a[j], S.ak);
-        if (do_store && S.out0r != nullptr && e.row_ok) stg8(S.out0r, col0, z);
-      }
-    } else {
-      float zs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      octet_slow(&G, &p, e.row, e.srow, e.row_ok, col0, sgn_scaled, do_store, zs);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = zs[j];
-    }
-  };
-  float rmax = 0.f;
+  const int nks_next = pad64(S.n_next) / 64;
 #pragma unroll 1
   for (int t = 0; t < S.n_out_tiles; ++t) {
+    const int s = 2 * t + (e.cq >> 1);
+    uint8_t* sl_base = a_smem + (size_t)s * 2 * CH_APLANE;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      float z[8];
-      produce(CH_NT * t + 32 * e.cq + 8 * o, true, z);
+      const int col0 = CH_NT * t + 32 * e.cq + 8 * o;
+      float z[8], a[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rmax = fmaxf(rmax, fabsf(z[j]));
-    }
-  }
-  CH_TRS(2);
-  exchange_scale(ctl, e, rmax, lp, sa, inv);
-  CH_TRS(3);
-  const int nks_next = pad64(S.n_next) / 64;
-  const int n_nx_tiles = (S.n_next + CH_NT - 1) / CH_NT;
-#pragma unroll 1
-  for (int t = 0; t < n_nx_tiles; ++t) {
-    const int s = 2 * t + (e.cq >> 1);
-    if (s < nks_next) {
-      uint8_t* sl_base = a_smem + (size_t)s * 2 * CH_APLANE;
+      for (int j = 0; j < 8; ++j) { z[j] = 0.f; a[j] = 0.f; }
+      if (col0 < S.n_cols) {
+        if (KIND == ST_LOAD) {
+          if (e.row_ok && col0 < S.ld_in0) ldg8(S.in0r, col0, z);
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        float z[8];
-        produce(CH_NT * t + 32 * e.cq + 8 * o, false, z);           // cheap to recompute
-        slice_store8(z, inv, sl_base, e.r_in, (e.cq & 1) * 32 + 8 * o);
+          for (int j = 0; j < 8; ++j) z[j] = (col0 + j < S.n_next) ? z[j] : 0.f;
+        } else {
+          if (e.row_ok && col0 < S.ld_in0) ldg8(S.in0r, col0, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = (col0 + j < S.N) ? sgn_scaled * __ldg(S.vec0 + col0 + j) : 0.f;     // S.N = width of the last layer's input
+          octet_fast<ST_REV_SEED>(S, e, col0, z, a, a);
+        }
       }
+      if (s < nks_next) split_store8(z, sl_base, e.r_in, (e.cq & 1) * 32 + 8 * o);
+    }
+    if (s < nks_next) {
       fence_proxy_async();
       mbar_arrive(&ctl->a_ready[s]);
     }
   }
+  CH_TRS(2);
 }
 
 // ---- first step: PE(x) (models/embedder.py:22-36) for the F chain, Edot = scale J_e(x) gbar for the T chain ----
@@ -808,53 +869,54 @@ __device__ __noinline__ void pe_row(float x0, float x1, float x2, float v0, floa
   }
 }
 template <bool JVP>
-__device__ __forceinline__ void pe_fill(const ChainParams& p, const EpiT& e, float (&vals)[4][8]) {
-  float x[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
-  if (e.row_ok) {
-    x[0] = p.pts[e.row * 3 + 0] * p.scale; x[1] = p.pts[e.row * 3 + 1] * p.scale; x[2] = p.pts[e.row * 3 + 2] * p.scale;
-    if (JVP) { v[0] = p.gbar[e.row * 3 + 0] * p.scale; v[1] = p.gbar[e.row * 3 + 1] * p.scale; v[2] = p.gbar[e.row * 3 + 2] * p.scale; }
-  }
-  float row[CH_MAX_PE];
-#pragma unroll 1
-  for (int c = 0; c < CH_MAX_PE; ++c) row[c] = 0.f;
-  pe_row<JVP>(x[0], x[1], x[2], v[0], v[1], v[2], p.n_freq, row);
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) vals[o][j] = row[32 * e.cq + 8 * o + j];
-  }
-}
-template <bool JVP>
 __device__ __forceinline__ void epi_step_pe(const ChainStep& G, const ChainParams& p, ChainCtl* ctl, uint8_t* a_smem, const EpiT& e,
                                             uint32_t& lp, float& sa, float& inv, bool tr_on, int tr_role, int l) {
   float vals[4][8];
   float rmax = 0.f;
-  const bool mine = e.cq <= 1 && 32 * e.cq < G.n_next;           // the encoding is at most 64 columns wide: K slice 0 only
+  const bool mine = e.cq <= 1 && 32 * e.cq < G.n_next + 8;       // the encoding (+ stash shift) is at most 64 columns wide: K slice 0 only
   if (mine) {
-    pe_fill<JVP>(p, e, vals);
-    float* outr = G.out0 != nullptr ? G.out0 + row_off(G.ld_out0, e.srow, e.t128) : nullptr;
+    float x[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+    if (e.row_ok) {
+      x[0] = p.pts[e.row * 3 + 0] * p.scale; x[1] = p.pts[e.row * 3 + 1] * p.scale; x[2] = p.pts[e.row * 3 + 2] * p.scale;
+      if (JVP) { v[0] = p.gbar[e.row * 3 + 0] * p.scale; v[1] = p.gbar[e.row * 3 + 1] * p.scale; v[2] = p.gbar[e.row * 3 + 2] * p.scale; }
+    }
+    float row[CH_MAX_PE + 8];                                     // row[8 + c] = encoding column c; row[0..7] = 0 (stash shift)
+#pragma unroll 1
+    for (int c = 0; c < CH_MAX_PE + 8; ++c) row[c] = 0.f;
+    pe_row<JVP>(x[0], x[1], x[2], v[0], v[1], v[2], p.n_freq, row + 8);
+    float* outr = (G.out0 != nullptr && e.t128) ? G.out0 + row_off(G.ld_out0, e.row, true) : nullptr;
+    float* stash = (p.pe_src != nullptr) ? const_cast<float*>(p.pe_src) + row_off(p.pe_ld, e.srow, true) : nullptr;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       const int col0 = 32 * e.cq + 8 * o;
+      float sh[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rmax = fmaxf(rmax, fabsf(vals[o][j]));
-      if (outr != nullptr && e.row_ok && col0 < G.ld_out0) {
-        if (e.t128) stg8(outr, col0, vals[o]);                  // columns >= d_pe are zeros: the tensor's padding
-        else {
+      for (int j = 0; j < 8; ++j) {
+        vals[o][j] = row[8 + col0 + j];
+        sh[j] = row[8 + col0 + j - p.pe_sh];                      // stash column c holds encoding column c - pe_sh
+        rmax = fmaxf(rmax, fabsf(vals[o][j]));
+      }
+      if (e.row_ok) {
+        if (outr != nullptr && col0 < G.ld_out0) stg8(outr, col0, vals[o]);          // columns >= d_pe are zeros: the tensor's padding
+        if (G.out0 != nullptr && !e.t128) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (col0 + j < G.ld_out0) outr[col0 + j] = vals[o][j];
+            if (col0 + j < G.ld_out0) G.out0[e.row * G.ld_out0 + col0 + j] = vals[o][j];
         }
+        if (stash != nullptr && col0 < p.pe_ld) stg8(stash, col0, sh);
       }
     }
   }
   CH_TRS(2);
-  exchange_scale(ctl, e, rmax, lp, sa, inv);
+  if (!JVP) exchange_scale(ctl, e, rmax, lp, sa, inv);          // the F chain's operand is row-scaled fp16; the T chain's split-bf16
   CH_TRS(3);
   if (e.cq <= 1) {
     if (mine) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) slice_store8(vals[o], inv, a_smem, e.r_in, 32 * e.cq + 8 * o);
+      for (int o = 0; o < 4; ++o) {
+        if (JVP) split_store8(vals[o], a_smem, e.r_in, 32 * e.cq + 8 * o);
+        else slice_store8(vals[o], inv, a_smem, e.r_in, 32 * e.cq + 8 * o);
+      }
     }
     fence_proxy_async();
     mbar_arrive(&ctl->a_ready[0]);
@@ -912,8 +974,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
           case ST_BWD: epi_step_gemm<ST_BWD>(G, p, ctl, a_smem, e, af_cnt, lp, sa, inv, tr_on, tr_role, l); break;
           case ST_FWD_LAST: epi_step_tail<ST_FWD_LAST>(G, p, ctl, e, af_cnt, sa, tr_on, tr_role, l); break;
           case ST_REV_FINAL: epi_step_tail<ST_REV_FINAL>(G, p, ctl, e, af_cnt, sa, tr_on, tr_role, l); break;
-          case ST_LOAD: epi_step_nogemm<ST_LOAD>(G, p, ctl, a_smem, e, lp, sa, inv, tr_on, tr_role, l); break;
-          case ST_REV_SEED: epi_step_nogemm<ST_REV_SEED>(G, p, ctl, a_smem, e, lp, sa, inv, tr_on, tr_role, l); break;
+          case ST_LOAD: epi_step_nogemm<ST_LOAD>(G, p, ctl, a_smem, e, tr_on, tr_role, l); break;
+          case ST_REV_SEED: epi_step_nogemm<ST_REV_SEED>(G, p, ctl, a_smem, e, tr_on, tr_role, l); break;
           default: break;
         }
         CH_TRS(4);
@@ -942,7 +1004,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
             tcgen05_fence_after();
             const uint32_t acc_m = tmem_base + slot * 256u, acc_c = acc_m + 128u;
             const uint32_t rows = (uint32_t)(S.rows_override > 0 ? S.rows_override : ch_tile_rows(S.N, t));
-            const uint32_t idesc = make_idesc_f16(rows);
+            const bool exact = S.n_wpl == 3;
+            const uint32_t idesc = exact ? make_idesc_f16(rows) : make_idesc(rows);
             for (int s = 0; s < S.n_kslices; ++s, ++wcnt) {
               t0 = clock64();
               if (t == 0) { mbar_wait(&ctl->a_ready[s], ar_cnt[s] & 1u); ++ar_cnt[s]; }
@@ -957,15 +1020,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
               const uint32_t wb = w_addr + ws * CH_WSLOT;
               const uint64_t db0 = make_desc(wb), db1 = make_desc(wb + rows * 128u), db2 = make_desc(wb + 2u * rows * 128u);
               if (elect_one()) {
+                if (exact) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint32_t first = (s == 0 && j == 0) ? 0u : 1u;
-                  const uint64_t o = (uint64_t)(2 * j);
-                  mma_bf16(acc_m, da0 + o, db0 + o, idesc, first);            // exact main term
-                  mma_bf16(acc_c, da1 + o, db1 + o, idesc, first);            // corrections, smallest first
-                  mma_bf16(acc_c, da0 + o, db2 + o, idesc, 1u);
-                  mma_bf16(acc_c, da1 + o, db0 + o, idesc, 1u);
-                  mma_bf16(acc_c, da0 + o, db1 + o, idesc, 1u);
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t first = (s == 0 && j == 0) ? 0u : 1u;
+                    const uint64_t o = (uint64_t)(2 * j);
+                    mma_bf16(acc_m, da0 + o, db0 + o, idesc, first);            // exact main term
+                    mma_bf16(acc_c, da1 + o, db1 + o, idesc, first);            // corrections, smallest first
+                    mma_bf16(acc_c, da0 + o, db2 + o, idesc, 1u);
+                    mma_bf16(acc_c, da1 + o, db0 + o, idesc, 1u);
+                    mma_bf16(acc_c, da0 + o, db1 + o, idesc, 1u);
+                  }
+                } else {                                                         // split-bf16: lo hi + hi lo + hi hi, one accumulator
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t first = (s == 0 && j == 0) ? 0u : 1u;
+                    const uint64_t o = (uint64_t)(2 * j);
+                    mma_bf16(acc_m, da1 + o, db0 + o, idesc, first);
+                    mma_bf16(acc_m, da0 + o, db1 + o, idesc, 1u);
+                    mma_bf16(acc_m, da0 + o, db0 + o, idesc, 1u);
+                  }
                 }
                 mma_commit(&ctl->w_empty[ws]);
               }
@@ -997,11 +1071,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) udf_chain_kernel(const __grid_c
             for (int s = 0; s < S.n_kslices; ++s, ++wcnt) {
               const uint32_t ws = wcnt % CH_NSLOT, wu = wcnt / CH_NSLOT;
               mbar_wait(&ctl->w_empty[ws], (wu & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&ctl->w_full[ws], CH_WPL * bytes);
+              mbar_arrive_expect_tx(&ctl->w_full[ws], (uint32_t)S.n_wpl * bytes);
               uint8_t* dst = w_smem + ws * CH_WSLOT;
               const uint16_t* src = tile + (int64_t)s * CH_WPL * rows_full * 64;
 #pragma unroll
-              for (int pl = 0; pl < CH_WPL; ++pl) bulk_g2s(dst + pl * bytes, src + (int64_t)pl * rows_full * 64, bytes, &ctl->w_full[ws]);
+              for (int pl = 0; pl < CH_WPL; ++pl)
+                if (pl < S.n_wpl) bulk_g2s(dst + pl * bytes, src + (int64_t)pl * rows_full * 64, bytes, &ctl->w_full[ws]);
             }
           }
         }
@@ -1026,6 +1101,10 @@ static inline int launch_chain(const ChainParams& p, int family, cudaStream_t st
   }
   int64_t grid = (p.P + 127) / 128;
   if (grid > sm_count()) grid = sm_count();
+  {
+    const char* e = getenv("NUDF_CHAIN_DEBUG");
+    const_cast<ChainParams&>(p).dbg = e ? atoi(e) : 0;
+  }
   static int trace_mode = -1;
   if (trace_mode < 0) { const char* e = getenv("NUDF_CHAIN_TRACE"); trace_mode = (e && atoi(e) > 0) ? atoi(e) : 0; }
   if (trace_mode > 0 && p.P >= 128 * 148) {              // profiling aid: synchronous, prints CTA 0's pipeline stamps

@@ -19,10 +19,12 @@ struct UdfPlan {
   int64_t img_nt[NUDF_MAX_LAYERS], img_nn[NUDF_MAX_LAYERS], img_nt3[NUDF_MAX_LAYERS], img_nn1, img_total;   // uint16 offsets of the bf16 hi/lo weight images
   int64_t img_chain[NUDF_MAX_LAYERS];   // uint16 offsets of the fused chains' fp16 slice images (udf_chain.cuh): X W_l^T operands
   int64_t img_chain_nn[NUDF_MAX_LAYERS], img_chain_nn1;   // dY W_l operands (R / B chains); nn1: feature rows 1.. of the last layer
+  int64_t img_chain_t[NUDF_MAX_LAYERS];   // X W_l^T operands of the T chain (split-bf16; the F chain's exact fp16 images are img_chain)
   int chain_tb_ok;                      // the fused T + B chains support this network shape as well
   int64_t sb_off[NUDF_MAX_LAYERS], sb_total;   // float offsets (after the images) of the chain's per-layer [scale meta (4) | bias table]
   int chain_ok;                         // the fused value chain supports this network shape
   int pe_ld, y_ld;
+  int stash_ld;   // the fused chains' per-CTA stash of the encoding, shifted so that the skip layer's appended columns are octet-aligned
   int a_ld[NUDF_MAX_LAYERS];    // ld of A[l] (input of layer l), l >= 1
   int o_ld[NUDF_MAX_LAYERS];    // ld of D[l] / Q[l] (out_dim rounded)
   int max_ld;
@@ -46,8 +48,8 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
     p->w_off[l] = off; off += (int64_t)p->out_dim[l] * p->w_ld[l];
     off = round_up(off, 4);
     p->b_off[l] = boff; boff += p->out_dim[l];
-    p->a_ld[l] = (int)round_up(p->in_dim[l], 4);
-    p->o_ld[l] = (int)round_up(p->out_dim[l], 4);
+    p->a_ld[l] = (int)round_up(p->in_dim[l], 8);        // the fused chains move 8-column octets: whole octets stay inside a tensor
+    p->o_ld[l] = (int)round_up(p->out_dim[l], 8);
     if (p->a_ld[l] > p->max_ld) p->max_ld = p->a_ld[l];
     if (p->o_ld[l] > p->max_ld) p->max_ld = p->o_ld[l];
   }
@@ -66,6 +68,7 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
   for (int l = 0; l < p->n_lin - 1; ++l) { p->img_chain_nn[l] = ioff; ioff += chain::ch_layer_elems(p->in_dim[l], p->out_dim[l]); }
   p->img_chain_nn1 = ioff;
   if (p->d_out > 1) ioff += chain::ch_layer_elems(p->in_dim[p->n_lin - 1], p->d_out - 1);
+  for (int l = 0; l < p->n_lin - 1; ++l) { p->img_chain_t[l] = ioff; ioff += chain::ch_layer_elems(p->out_dim[l], p->in_dim[l]); }
   p->img_total = round_up(ioff, 8);
   int64_t soff = 0;
   for (int l = 0; l < p->n_lin; ++l) { p->sb_off[l] = soff; soff += 4 + (int64_t)chain::CH_NT * chain::ch_n_tiles(p->out_dim[l]); }
@@ -86,8 +89,10 @@ static int make_plan(const nudf_udf_desc* d, UdfPlan* p) {
     int expect = p->out_dim[l - 1] + (l == p->skip ? p->d_pe : 0);
     NUDF_REQUIRE(p->in_dim[l] == expect, "layer dims are not chained consistently");
   }
-  p->pe_ld = (int)round_up(p->d_pe, 4);
-  p->y_ld = (int)round_up(p->d_out, 4);
+  p->pe_ld = (int)round_up(p->d_pe, 8);
+  p->y_ld = (int)round_up(p->d_out, 8);
+  p->stash_ld = (int)round_up(p->d_pe + 8, 8);
+  NUDF_REQUIRE(p->stash_ld <= 64, "positional encoding too wide for the fused chains");
   return 0;
 }
 
@@ -103,8 +108,9 @@ static inline bool fused_tb_on(const UdfPlan& p) { return fused_on(p); }
 static inline int64_t ctx_rows(const UdfPlan& p, int64_t P) { return fused_on(p) ? round_up(P, 128) : P; }
 
 // ---- context / scratch layout (all offsets in floats; every block starts 16B-aligned) -------------------------
+constexpr int64_t CHAIN_STASH_ROWS = chain::CH_MAX_GRID * 128;     // one 128-row tile per CTA of the fused chain kernels
 struct UdfCtx {
-  int64_t e0, a[NUDF_MAX_LAYERS], y, sgn, d[NUDF_MAX_LAYERS], gpe, ge, total;
+  int64_t e0, a[NUDF_MAX_LAYERS], y, sgn, d[NUDF_MAX_LAYERS], gpe, ge, stash, total;
   // plane mode (chain_planes_on()): D[l] lives only as a split-bf16 plane tensor.  pl_off: float offset of the plane
   // area (aligned to 1024 B at run time), dpl[l]: uint16 offsets inside it.
   int64_t pl_off, dpl[NUDF_MAX_LAYERS];
@@ -118,6 +124,7 @@ static void ctx_layout(const UdfPlan& p, int64_t P_, int with_grad, UdfCtx* c) {
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
   c->e0 = take(P * p.pe_ld);
+  c->stash = take((int64_t)CHAIN_STASH_ROWS * p.stash_ld);
   for (int l = 1; l < p.n_lin; ++l) c->a[l] = take(P * p.a_ld[l]);
   c->y = take(P * p.y_ld);
   c->sgn = take(P);
@@ -130,12 +137,13 @@ static void ctx_layout(const UdfPlan& p, int64_t P_, int with_grad, UdfCtx* c) {
     } else {
       for (int l = 0; l < p.n_lin - 1; ++l) c->d[l] = take(P * p.o_ld[l]);
     }
-    c->gpe = take(P * p.pe_ld);
+    c->gpe = take(P * p.stash_ld);                  // fused chains store it shifted (stash_ld columns)
     c->ge = take(P * p.pe_ld);
   }
   c->total = off;
 }
 struct UdfScratch {
+  int64_t stash;
   int64_t edot, adot[2], q[NUDF_MAX_LAYERS], zlast, total;
   int64_t adot_l[NUDF_MAX_LAYERS];           // fused T chain: Adot[l], l = 1..last, all kept for the weight gradients
   int64_t pl_off, adpl[NUDF_MAX_LAYERS];     // plane mode: Adot[l] (input of layer l of the tangent chain)
@@ -145,6 +153,7 @@ static void scratch_layout(const UdfPlan& p, int64_t P_, UdfScratch* s) {
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t o = off; off += round_up(n, 4); return o; };
   s->edot = take(P * p.pe_ld);
+  s->stash = take((int64_t)CHAIN_STASH_ROWS * p.stash_ld);
   if (fused_tb_on(p)) {
     s->adot[0] = s->adot[1] = 0;
     for (int l = 1; l < p.n_lin; ++l) s->adot_l[l] = take(P * p.a_ld[l]);
@@ -276,13 +285,18 @@ __global__ void rev_init_kernel(const float* __restrict__ sgn, const float* __re
 }
 
 // grad_x = scale * J_e(x)^T Ge
+// gpe_sh (optional, fused chains): the skip layer's part of Ge, stored shifted by `sh` columns (udf_chain.cuh), added here
 __global__ void pe_vjp_kernel(const float* __restrict__ pts, const float* __restrict__ ge, int pe_ld, int64_t P, int L,
-                              float scale, float* __restrict__ grad, int t128 = 0) {
+                              float scale, float* __restrict__ grad, int t128 = 0, const float* __restrict__ gpe_sh = nullptr,
+                              int gpe_ld = 0, int sh = 0) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   float g[3 * (1 + 2 * 16)];
   const int d_pe_ = 3 * (1 + 2 * L);
-  for (int c = 0; c < d_pe_; ++c) g[c] = ge[mat_off(t128 != 0, i, c, pe_ld)];
+  for (int c = 0; c < d_pe_; ++c) {
+    g[c] = ge[mat_off(t128 != 0, i, c, pe_ld)];
+    if (gpe_sh != nullptr) g[c] += gpe_sh[mat_off(t128 != 0, i, c + sh, gpe_ld)];
+  }
   float f = 1.0f;
   float acc[3] = {g[0], g[1], g[2]};
   float x[3] = {pts[i * 3 + 0] * scale, pts[i * 3 + 1] * scale, pts[i * 3 + 2] * scale};
@@ -426,13 +440,17 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
         chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.out_dim[l]), 64, 0, st>>>(
             W, p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], 0, meta, img + p.img_chain[l], meta + 4);
         NUDF_LAUNCH_OK();
+        // R / T / B chains: split-bf16 images (gradient quantities: 2^-16 relative is far inside their tolerance; 3 products)
         if (l < last) {
           chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.in_dim[l]), 64, 0, st>>>(
-              W, p.w_ld[l], nullptr, p.in_dim[l], p.out_dim[l], 1, meta, img + p.img_chain_nn[l], nullptr);
+              W, p.w_ld[l], nullptr, p.in_dim[l], p.out_dim[l], 1, meta, img + p.img_chain_nn[l], nullptr, 1);
+          NUDF_LAUNCH_OK();
+          chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.out_dim[l]), 64, 0, st>>>(
+              W, p.w_ld[l], nullptr, p.out_dim[l], p.in_dim[l], 0, meta, img + p.img_chain_t[l], nullptr, 1);
           NUDF_LAUNCH_OK();
         } else if (p.d_out > 1) {
           chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.in_dim[l]), 64, 0, st>>>(
-              W + p.w_ld[l], p.w_ld[l], nullptr, p.in_dim[l], p.d_out - 1, 1, meta, img + p.img_chain_nn1, nullptr);
+              W + p.w_ld[l], p.w_ld[l], nullptr, p.in_dim[l], p.d_out - 1, 1, meta, img + p.img_chain_nn1, nullptr, 1);
           NUDF_LAUNCH_OK();
         }
       }
@@ -460,6 +478,7 @@ static void set_gemm(chain::ChainStep* S, const UdfPlan& p, const float* wfold, 
   S->n_kslices = tc::pad64(K) / 64;
   S->n_tiles = chain::ch_n_tiles(N);
   S->img_off = (uint32_t)img_off;
+  S->n_wpl = chain::kind_exact(S->kind) ? 3 : 2;
   S->wscale = tab + p.sb_off[layer] + 1;
 }
 static void chain_common(const UdfPlan& p, const float* wfold, const float* pts, int64_t P, chain::ChainParams* cp) {
@@ -467,10 +486,12 @@ static void chain_common(const UdfPlan& p, const float* wfold, const float* pts,
   cp->img = img_base(p, wfold);
   cp->pts = pts; cp->P = P; cp->scale = p.scale; cp->n_freq = p.L; cp->d_pe = p.d_pe;
   cp->gbar = nullptr;
-  cp->pe_src = nullptr; cp->pe_ld = p.pe_ld; cp->pe_cta = 0;
+  cp->pe_src = nullptr; cp->pe_ld = p.stash_ld; cp->pe_cta = 1;
+  cp->pe_sh = (p.skip >= 1) ? (p.out_dim[p.skip - 1] & 7) : 0;
   cp->t128 = fused_on(p) ? 1 : 0;
   cp->udf_out = nullptr; cp->inv_scale = 1.0f / p.scale;
   cp->trace = nullptr;
+  cp->dbg = 0;
 }
 // F chain for P points; value_only (udf != null): the last layer is restricted to its udf-head row and only udf[P] is
 // written; otherwise the context tensors E0, A[1..], Y are written.  with_rev: the R chain (exact grad_x udf) follows in the
@@ -486,8 +507,11 @@ static void build_forward(const UdfPlan& p, const float* wfold, const float* pts
   S->n_next = p.d_pe;
   // E0 is written for the weight gradients and re-read by the skip layer; a value-only launch keeps a 128-row stash per CTA in
   // `ctx` (= the caller's work buffer) instead, in the T128 layout
-  if (!value_only) { S->out0 = ctx + c->e0; S->ld_out0 = p.pe_ld; cp->pe_src = ctx + c->e0; }
-  else if (p.skip >= 1) { S->out0 = ctx; S->ld_out0 = p.pe_ld; cp->pe_src = ctx; cp->pe_cta = 1; cp->t128 = 1; }
+  // E0 is written for the weight gradients; the skip layer re-reads the encoding from a per-CTA stash (128 rows per CTA, T128,
+  // columns shifted by pe_sh so that the appended columns are octet-aligned).  Value-only: `ctx` = the caller's work buffer.
+  if (!value_only) { S->out0 = ctx + c->e0; S->ld_out0 = p.pe_ld; }
+  if (p.skip >= 1) cp->pe_src = value_only ? ctx : ctx + c->stash;
+  if (value_only) cp->t128 = 1;                             // no [P, ld] tensor is touched: take the fast paths
   for (int l = 0; l < last; ++l) {
     S = add_step(cp, chain::ST_FWD);
     set_gemm(S, p, wfold, l, p.in_dim[l], p.out_dim[l], p.img_chain[l]);
@@ -509,7 +533,7 @@ static void build_forward(const UdfPlan& p, const float* wfold, const float* pts
     R->a_unscale = (l == p.skip) ? 1.41421356237309504880f : 1.0f;
     R->in0 = ctx + c->a[l]; R->ld_in0 = p.a_ld[l];
     R->out0 = ctx + c->d[l - 1]; R->ld_out0 = p.o_ld[l - 1];
-    if (l == p.skip) { R->out1 = ctx + c->gpe; R->ld_out1 = p.pe_ld; }
+    if (l == p.skip) { R->out1 = ctx + c->gpe; R->ld_out1 = p.stash_ld; }     // stored shifted by pe_sh columns; pe_vjp_kernel adds it
   };
   S = add_step(cp, chain::ST_REV_SEED);                     // G_last = (sgn / scale) W_last[0, :]
   S->N = p.in_dim[last];
@@ -523,7 +547,6 @@ static void build_forward(const UdfPlan& p, const float* wfold, const float* pts
   }
   S = add_step(cp, chain::ST_REV_FINAL);
   set_gemm(S, p, wfold, 0, p.out_dim[0], p.in_dim[0], p.img_chain_nn[0]);
-  if (p.skip >= 1) { S->in1 = ctx + c->gpe; S->ld_in1 = p.pe_ld; }
   S->out0 = ctx + c->ge; S->ld_out0 = p.pe_ld;
 }
 
@@ -542,10 +565,10 @@ static void build_backward(const UdfPlan& p, const float* wfold, const float* pt
     S = add_step(cp, chain::ST_EDOT);
     S->n_next = p.d_pe;
     S->out0 = scr + s.edot; S->ld_out0 = p.pe_ld;
-    cp->pe_src = scr + s.edot;
+    if (p.skip >= 1) cp->pe_src = scr + s.stash;
     for (int l = 0; l < last; ++l) {
       S = add_step(cp, chain::ST_TAN);
-      set_gemm(S, p, wfold, l, p.in_dim[l], p.out_dim[l], p.img_chain[l]);
+      set_gemm(S, p, wfold, l, p.in_dim[l], p.out_dim[l], p.img_chain_t[l]);
       S->n_main = p.in_dim[l + 1];                          // width of Adot[l+1] (incl. the Edot columns at the skip layer)
       S->n_next = (l + 1 < last) ? p.in_dim[l + 1] : 0;     // Adot[last] feeds no GEMM (only a weighted column sum)
       S->post_scale = (l + 1 == p.skip) ? NUDF_SQRT1_2 : 1.0f;
@@ -738,7 +761,8 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
     udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
                                                                 ctx + c.sgn, 1);
     NUDF_LAUNCH_OK();
-    pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad, 1);
+    pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad, 1, p.skip >= 1 ? ctx + c.gpe : nullptr,
+                                                p.stash_ld, p.skip >= 1 ? (p.out_dim[p.skip - 1] & 7) : 0);
     NUDF_LAUNCH_OK();
     return 0;
   }

@@ -43,7 +43,7 @@ def test_descriptor_validation_runs_without_gpu():
         d.in_dim[l], d.out_dim[l] = i, o
     n = L.nudf_udf_folded_floats(ctypes.byref(d))
     # fp32 folded weights (>= 524 544 floats) followed by the bf16 hi/lo tensor-engine images of every layer
-    assert 524544 <= n < 4 * 1024 * 1024
+    assert 524544 <= n < 8 * 1024 * 1024
     assert L.nudf_udf_ctx_floats(ctypes.byref(d), 1024, 1) > L.nudf_udf_ctx_floats(ctypes.byref(d), 1024, 0) > 0
 
 
