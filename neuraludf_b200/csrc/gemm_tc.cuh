@@ -1056,35 +1056,41 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // One granule = half a slice of one warp: 32 points x 16 of the warp's 32 columns = 4 feature quads.  Copy: lane l moves point
 // k0 + l of each quad (16 B), so every warp instruction reads 512 contiguous bytes of the T128 layout -- each 32-byte sector
 // is requested exactly once (cp.async.cg bypasses L1: a mapping that splits a sector over two instructions fetches it twice
-// from L2).  Raw layout of a warp's granule: [quad][32 points][16 B].
-__device__ __forceinline__ void t2_issue(const float* __restrict__ X, int64_t ld, int col0, int half, int64_t k0, int64_t k_end,
+// from L2).  Raw layout of a warp's granule: [quad][slot(point)][16 B] with slot(p) = p ^ ((p >> 3) & 1): both the copy (lane = point)
+// and the split (lane = point pair, two 16-byte loads) are bank-conflict free per quarter warp.  `src` = address of (point k0 + lane, first column of quad 0 of this half), or null for a
+// column block beyond ld; consecutive quads are 512 floats apart in the T128 layout.
+__device__ __forceinline__ void t2_issue(const float* __restrict__ src, const float* __restrict__ any, int n_quads_valid, bool row_ok,
                                          uint32_t raw_warp, int lane) {
-  const int64_t row = k0 + lane;
+  const uint32_t dst = raw_warp + (uint32_t)(lane ^ ((lane >> 3) & 1)) * 16u;      // slot(point) = point ^ ((point >> 3) & 1)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int col = col0 + 4 * (4 * half + q);
-    const bool v = col < ld && row < k_end;                      // invalid: zero fill, source address unused
-    cp_async16(raw_warp + (uint32_t)q * 512u + (uint32_t)lane * 16u, X + (v ? t128_off(row, col, ld) : 0), v ? 16u : 0u);
+    const bool v = row_ok && q < n_quads_valid;                  // invalid: zero fill, source address unused
+    cp_async16(dst + (uint32_t)q * 512u, v ? src + q * 512 : any, v ? 16u : 0u);
   }
 }
 // Split: lane (rp = lane & 15, g2 = lane >> 4) packs the point pair (2 rp, 2 rp + 1) of the quads g2 and g2 + 2.
+// pre[j]: byte offset of (tile row 4 g2 + j, k = 2 rp) inside an 8-row swizzle atom, without the k half (added by the caller).
 template <bool CSUM, int HALF>
-__device__ __forceinline__ void t2_convert(const uint8_t* raw_warp, uint8_t* s_hi, uint8_t* s_lo, int r0, int khalf, int lane, float* csum) {
+__device__ __forceinline__ void t2_convert(const uint8_t* raw_warp, uint8_t* s_hi, uint8_t* s_lo, const uint32_t (&pre)[4], int lane,
+                                           float* csum) {
   const int rp = lane & 15, g2 = lane >> 4;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int q = 2 * i + g2;
-    const float4 a = *reinterpret_cast<const float4*>(raw_warp + q * 512 + (2 * rp) * 16);
-    const float4 b = *reinterpret_cast<const float4*>(raw_warp + q * 512 + (2 * rp + 1) * 16);
+    const int sw = (rp >> 2) & 1;                                // points 2 rp, 2 rp + 1 -> slots (2 rp) ^ sw, (2 rp + 1) ^ sw
+    const float4 a = *reinterpret_cast<const float4*>(raw_warp + q * 512 + ((2 * rp) ^ sw) * 16);
+    const float4 b = *reinterpret_cast<const float4*>(raw_warp + q * 512 + ((2 * rp + 1) ^ sw) * 16);
     const float x0[4] = {a.x, a.y, a.z, a.w}, x1[4] = {b.x, b.y, b.z, b.w};
-    const int rbase = r0 + 4 * (4 * HALF + q);
+    // tile rows r0 + 16 HALF + 4 q + j = 8-row atom (r0 / 8 + 2 HALF + i), row-in-atom 4 g2 + j: s_hi / s_lo already point at
+    // the warp's first atom
+    uint8_t* h = s_hi + (2 * HALF + i) * 1024;
+    uint8_t* l = s_lo + (2 * HALF + i) * 1024;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t hi = pack_bf16(x0[j], x1[j]);
       const uint32_t lo = pack_bf16(x0[j] - __uint_as_float(hi << 16), x1[j] - __uint_as_float(hi & 0xFFFF0000u));
-      const uint32_t off = sw128((uint32_t)(rbase + j), (uint32_t)(32 * khalf + 2 * rp));
-      *reinterpret_cast<uint32_t*>(s_hi + off) = hi;
-      *reinterpret_cast<uint32_t*>(s_lo + off) = lo;
+      *reinterpret_cast<uint32_t*>(h + pre[j]) = hi;
+      *reinterpret_cast<uint32_t*>(l + pre[j]) = lo;
       if (CSUM) csum[8 * HALF + 4 * i + j] += x0[j] + x1[j];
     }
   }
@@ -1131,16 +1137,32 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
     for (int j = 0; j < 16; ++j) csum[j] = 0.f;
     auto pair_of = [&](int i) -> const TnPair& { return i < n_sl ? p0 : p1; };
     const int n_gran = 2 * total;
+    const int col0 = (is_a ? m0 : n0) + r0;                     // first operand column of this warp
+    // k_chunk is a multiple of 128 (launcher): slice i of a pair starts at point kb + 32 i, 4 slices per 128-point block of the
+    // T128 layout; inside a block consecutive points are 4 floats apart, the next block is (ld / 4) * 512 floats further
     auto issue = [&](int h) {                                   // granule h = (slice h >> 1, half h & 1); always commits a group
       if (active && h < n_gran) {
         const int i = h >> 1;
         const TnPair& pr = pair_of(i);
-        const int64_t k0 = kb + (int64_t)(i < n_sl ? i : i - n_sl) * T2_BK;
-        t2_issue(is_a ? pr.A : pr.B, is_a ? pr.lda : pr.ldb, (is_a ? m0 : n0) + r0, h & 1, k0, ke,
-                 raw_warp_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
+        const int isl = i < n_sl ? i : i - n_sl;
+        const float* X = is_a ? pr.A : pr.B;
+        const int64_t ld = is_a ? pr.lda : pr.ldb;
+        const int64_t row = kb + (int64_t)isl * T2_BK + lane;
+        const int cq0 = (col0 >> 2) + 4 * (h & 1);              // first quad of this half
+        int nq = (int)(ld >> 2) - cq0;                          // quads of this half that exist
+        const float* src = X + ((row >> 7) * (ld >> 2) + cq0) * 512 + (row & 127) * 4;
+        t2_issue(src, X, nq, row < ke, raw_warp_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
       }
       cp_async_commit();
     };
+    // swizzled offsets of this lane's four tile rows (4 g2 + j) at k = 2 rp, per k half
+    uint32_t pre[2][4];
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre[kh][j] = sw128((uint32_t)(4 * (lane >> 4) + j), (uint32_t)(32 * kh + 2 * (lane & 15)));
+    uint8_t* w_hi = s_hi + (r0 >> 3) * 1024;
+    uint8_t* w_lo = s_lo + (r0 >> 3) * 1024;
 #pragma unroll
     for (int h = 0; h < T2_RING - 1; ++h) issue(h);
     for (int i = 0; i < total; ++i) {
@@ -1155,8 +1177,11 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
       if (i >= 2) mbar_wait(&ctl->empty[s], (uint32_t)(((i >> 1) - 1) & 1));
       if (active) {
         const uint8_t* rl = raw_warp + (uint32_t)((2 * i) % T2_RING) * T2_RAW_GRAN;
-        if (do_csum) t2_convert<true, 0>(rl, s_hi, s_lo, r0, s, lane, csum);
-        else t2_convert<false, 0>(rl, s_hi, s_lo, r0, s, lane, csum);
+        if (s == 0) {
+          if (do_csum) t2_convert<true, 0>(rl, w_hi, w_lo, pre[0], lane, csum); else t2_convert<false, 0>(rl, w_hi, w_lo, pre[0], lane, csum);
+        } else {
+          if (do_csum) t2_convert<true, 0>(rl, w_hi, w_lo, pre[1], lane, csum); else t2_convert<false, 0>(rl, w_hi, w_lo, pre[1], lane, csum);
+        }
       }
       // half 1
       __syncwarp();
@@ -1165,8 +1190,11 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
       __syncwarp();
       if (active) {
         const uint8_t* rl = raw_warp + (uint32_t)((2 * i + 1) % T2_RING) * T2_RAW_GRAN;
-        if (do_csum) t2_convert<true, 1>(rl, s_hi, s_lo, r0, s, lane, csum);
-        else t2_convert<false, 1>(rl, s_hi, s_lo, r0, s, lane, csum);
+        if (s == 0) {
+          if (do_csum) t2_convert<true, 1>(rl, w_hi, w_lo, pre[0], lane, csum); else t2_convert<false, 1>(rl, w_hi, w_lo, pre[0], lane, csum);
+        } else {
+          if (do_csum) t2_convert<true, 1>(rl, w_hi, w_lo, pre[1], lane, csum); else t2_convert<false, 1>(rl, w_hi, w_lo, pre[1], lane, csum);
+        }
       }
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
@@ -1232,7 +1260,7 @@ static inline int gemm_tn2(const TnPair* pairs, int n_pairs, int M, int N, int64
   const int max_splits = (int)cdiv(K, 256);                  // at least 8 slices of 32 points per CTA and pair
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  const int64_t k_chunk = round_up(cdiv(K, splits), T2_BK);
+  const int64_t k_chunk = round_up(cdiv(K, splits), 128);      // whole 128-point blocks of the T128 layout per CTA
   splits = (int)cdiv(K, k_chunk);
   const size_t smem = (size_t)T2_PLANES + (size_t)T2_RING * T2_RAW_GRAN + sizeof(SmemCtl) + 64;
   static bool attr_set = false;
