@@ -62,20 +62,24 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-def ncu_traffic(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of a kernel from the newest committed
-    `ncu --set full` summary under profiles/ (None if not captured)."""
+def ncu_traffic(kernel_substr, launch=0):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the `launch`-th captured launch of a kernel from the
+    newest committed `ncu --set full` summary under profiles/ (None if not captured)."""
     import glob
     best = None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    norm = lambda t: t.replace("nudf::", "").replace("tc::", "").replace(" ", "")
+    norm = lambda t: t.replace("nudf::", "").replace("tc::", "").replace("chain::", "").replace(" ", "")
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_kernels.txt")) +
-                    glob.glob(os.path.join(ROOT, "profiles", "r*_kernels.txt"))):
-        cur, rd, wr = None, None, None
+                    glob.glob(os.path.join(ROOT, "profiles", "r*_kernel.txt"))):
+        cur, rd, wr, seen, found = None, None, None, -1, None
         for line in open(f):
             if line.startswith("== "):
-                cur, rd, wr = line, None, None
-            elif cur and norm(kernel_substr) in norm(cur):
+                cur, rd, wr = None, None, None
+                if norm(kernel_substr) in norm(line):
+                    seen += 1
+                    if seen == launch:
+                        cur = line
+            elif cur:
                 parts = line.split()
                 if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     v = float(parts[1].replace(",", "")) * unit.get(parts[2], 1.0)
@@ -84,8 +88,10 @@ def ncu_traffic(kernel_substr):
                     else:
                         wr = v
                 if rd is not None and wr is not None:
-                    best = rd + wr
+                    found = rd + wr
                     cur = None
+        if found is not None:
+            best = found
     return best
 
 
@@ -419,7 +425,8 @@ def run_ours(args):
         dom = max(tens, key=lambda k: tens[k]["share"]) if tens else None
         kernel_of = {"udf_fwd_chain_fused": "udf_chain_kernel", "udf_bwd_chain_fused": "udf_chain_kernel", "tc_layer_reverse_sweep": "gemm_wr_kernel<nudf::EpiRev>",
                      "tc_layer_tangent": "gemm_wr_kernel<nudf::EpiTan>", "tc_layer_backward": "gemm_wr_kernel<nudf::EpiBwd>",
-                     "tc_weight_gradient": "gemm_tn_kernel"}
+                     "tc_weight_gradient": "gemm_tn2_kernel"}
+        launch_of = {"udf_bwd_chain_fused": 1}         # profiles/r02_chain_kernel.txt: launch 0 = F + R, launch 1 = T + B
         roof = None
         if dom is not None:
             r = tens[dom]
@@ -427,7 +434,7 @@ def run_ours(args):
                         dom, kernel_of[dom], r["launches_per_step"], r["us_per_launch"]),
                     "achieved": r["algorithmic_tflops"], "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": r["algorithmic_tflops"] / pk["bf16_sustained"], "share_of_step": r["share"],
-                    "traffic": ncu_traffic(kernel_of[dom]),
+                    "traffic": ncu_traffic(kernel_of[dom], launch_of.get(dom, 0)),
                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/)",
                     "peak_source": pk["source"] + ", bf16 sustained (kernel timed inside the step)",
                     "how": "largest-share family of the timed step; duration = cudaEvent pairs recorded by the library on the "

@@ -109,8 +109,6 @@ struct ChainParams {
   int t128;                              // 1: every [P, ld] tensor of the steps is stored in the T128 layout (common.cuh)
   float* udf_out; float inv_scale;       // value-only mode: udf_out[P] = |y_0| / scale
   long long* trace;                      // profiling aid (NUDF_CHAIN_TRACE=n): clock64() stamps of CTA 0, first point tile
-  int dbg;                               // profiling aid (NUDF_CHAIN_DEBUG bit mask, WRONG RESULTS): 1 no global stores, 2 no MUFU,
-                                         // 4 no TMEM parking, 8 no accumulator loads, 16 no auxiliary loads, 32 no operand slicing
 };
 // trace layout: [role 0 = epilogue warp 0, 1 = epilogue warp 12, 2 = MMA issuer][step][8]
 constexpr int CH_TRACE_WORDS = 3 * CH_MAX_STEPS * 8;
@@ -1101,10 +1099,6 @@ static inline int launch_chain(const ChainParams& p, int family, cudaStream_t st
   }
   int64_t grid = (p.P + 127) / 128;
   if (grid > sm_count()) grid = sm_count();
-  {
-    const char* e = getenv("NUDF_CHAIN_DEBUG");
-    const_cast<ChainParams&>(p).dbg = e ? atoi(e) : 0;
-  }
   static int trace_mode = -1;
   if (trace_mode < 0) { const char* e = getenv("NUDF_CHAIN_TRACE"); trace_mode = (e && atoi(e) > 0) ? atoi(e) : 0; }
   if (trace_mode > 0 && p.P >= 128 * 148) {              // profiling aid: synchronous, prints CTA 0's pipeline stamps

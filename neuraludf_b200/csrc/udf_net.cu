@@ -491,7 +491,6 @@ static void chain_common(const UdfPlan& p, const float* wfold, const float* pts,
   cp->t128 = fused_on(p) ? 1 : 0;
   cp->udf_out = nullptr; cp->inv_scale = 1.0f / p.scale;
   cp->trace = nullptr;
-  cp->dbg = 0;
 }
 // F chain for P points; value_only (udf != null): the last layer is restricted to its udf-head row and only udf[P] is
 // written; otherwise the context tensors E0, A[1..], Y are written.  with_rev: the R chain (exact grad_x udf) follows in the

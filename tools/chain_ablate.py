@@ -1,5 +1,8 @@
-"""Profiling aid: time the fused F+R and T+B launches of one C2 step with parts of the epilogue switched off
-(NUDF_CHAIN_DEBUG bit mask; results are WRONG under a non-zero mask, only the timing is meaningful)."""
+"""Profiling aid: times the fused F+R and T+B launches (and the weight gradients) of 65 536 points through the library's own
+per-family event pairs.  `python tools/chain_ablate.py 0` is the plain A/B timer used to compare library builds on one box.
+The masks 1..63 were the NUDF_CHAIN_DEBUG ablation switches of an instrumented intermediate build of udf_chain.cuh (no global
+stores / no MUFU / no TMEM parking / no accumulator loads / no auxiliary loads / no operand slicing): the shipped kernel carries
+no instrumentation and ignores them; the recorded ablation is profiles/r02_chain_ablation.txt."""
 import os
 import sys
 
