@@ -279,25 +279,47 @@ def run_ours(args):
     bucket = GradBucket(params, modules=(udf, col))      # backward kernels write dg / dv / db straight into the flat bucket
     opt = make_optimizer(udf, (col, var, beta))
 
-    def step(o_, d_, z_):
+    def compute(o_, d_, z_):
         opt.zero_grad(set_to_none=True)
         ret = ren.render_core(o_, d_, z_, sd, udf, var, col, beta_network=beta, cos_anneal_ratio=0.5)
         loss = loss_fn(ret, tgt)
         loss.backward()
+        return loss
+
+    def step(o_, d_, z_):
+        loss = compute(o_, d_, z_)
         if world > 1:
             bucket.allreduce_mean()                    # NCCL all-reduce of the flat gradient bucket over NVLink
         opt.step()                                     # Adam: parameters change => fold + weight images rebuilt next step
         return loss
+
+    # CUDA-graph replay.  One GPU: the whole step (forward, backward, Adam) is one graph.  Several GPUs: the graph holds forward
+    # + backward only; the NCCL all-reduce of the flat bucket and Adam are launched after each replay (NCCL calls are kept out
+    # of captured graphs; the per-region overlap of the eager path is given up for one 2.8 MB collective).
+    def graph_body(o_, d_, z_):
+        return step(o_, d_, z_) if world == 1 else compute(o_, d_, z_)
+
+    def replay_step():
+        graph.replay()
+        if world > 1:
+            bucket.allreduce_replayed()
+            opt.step()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def stage(msg):                                    # NUDF_BENCH_TRACE=1: progress on stderr (multi-GPU debugging aid)
+        if os.environ.get("NUDF_BENCH_TRACE"):
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
     clocks = Clocks(local) if rank == 0 else None
+    stage("warm-up")
     for _ in range(max(args.warmup, 3)):
         step(o, d, z)
     barrier()
+    stage("eager loop")
     # ---- eager loop: every kernel launched from Python (ctypes / torch) each step ----
     l0 = lib.nudf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,25 +332,31 @@ def run_ours(args):
     ms_eager = e0.elapsed_time(e1)
     launches = lib.nudf_launch_count() - l0
     # ---- the same step captured ONCE into a CUDA graph and replayed (no host work per step; the step has no host read) ----
-    graph, g_in, g_loss, graph_err = None, None, None, None
+    graph, g_in, g_loss, graph_err, static_grads = None, None, None, None, []
+    stage("graph capture")
     if not args.no_graph:
         try:
             g_in = [t.clone() for t in (o, d, z)]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
+            bucket.overlap = world == 1                # no collective is issued from inside backward while capturing
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    step(*g_in)
+                    graph_body(*g_in)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                g_loss = step(*g_in)
+                g_loss = graph_body(*g_in)
+            static_grads = [(p, p.grad) for p in params]     # the tensors the captured kernels write
             for _ in range(3):
-                graph.replay()
+                replay_step()
             barrier()
         except Exception as e:                         # capture not possible here: the eager number stands
             graph, graph_err = None, "%s: %s" % (type(e).__name__, str(e)[:200])
             torch.cuda.synchronize()
+        if graph is None:
+            bucket.overlap = True
+    stage("timed loop (graph=%s)" % (graph is not None))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if clocks:
         clocks.begin()
@@ -336,7 +364,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         if graph is not None:
-            graph.replay()
+            replay_step()
         else:
             step(o, d, z)
     e1.record()
@@ -357,13 +385,19 @@ def run_ours(args):
         return None
 
     # ---- the same steps again with the library's per-family event pairs switched on ----
+    # (every rank runs the steps -- they contain the gradient all-reduce --, rank 0 alone records the events)
+    stage("family timing")
     fam = None
+    n_fam_steps = min(args.steps, 10)
     if rank == 0:
-        n_fam_steps = min(args.steps, 10)
         lib.nudf_set_launch_timing(1)
-        for _ in range(n_fam_steps):
-            step(o, d, z)
-        torch.cuda.synchronize()
+    for _ in range(n_fam_steps):
+        step(o, d, z)
+    torch.cuda.synchronize()
+    if graph is not None:                              # the eager steps re-created the .grad tensors: point the parameters back
+        for p, g in static_grads:                      # at the ones the graph writes (the eager finish of replay_step reads them)
+            p.grad = g
+    if rank == 0:
         fam = read_families(lib, n_fam_steps, ms / args.steps, N_RAYS * N_SAMPLES, peaks())
         lib.nudf_set_launch_timing(0)
     barrier()
@@ -374,10 +408,11 @@ def run_ours(args):
     def e2e_step():
         if graph is not None:                          # H2D into the graph's static inputs, replay, D2H of the loss
             g_in[0].copy_(ho, non_blocking=True); g_in[1].copy_(hd, non_blocking=True); g_in[2].copy_(hz, non_blocking=True)
-            graph.replay()
+            replay_step()
             return g_loss
         return step(ho.to(dev, non_blocking=True), hd.to(dev, non_blocking=True), hz.to(dev, non_blocking=True))
 
+    stage("e2e")
     for _ in range(2):
         l = e2e_step()
     barrier()
@@ -393,6 +428,7 @@ def run_ours(args):
     wall_e2e = (time.perf_counter() - t0) * 1e3
     ms_e2e = max(ms_e2e, wall_e2e)                     # host-driven loop: wall clock bounds it from above
 
+    stage("reduce times")
     times = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -406,6 +442,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         sub = argparse.Namespace(steps=5, warmup=3)
         for name, fn in (("c1", run_c1), ("c3", run_c3), ("c4", run_c4), ("c5", run_c5)):
+            stage("workload " + name)
             try:
                 extra[name] = fn(sub, dev, lib, rank, world)
             except Exception as e:                     # a secondary workload must never take the headline down with it

@@ -121,6 +121,29 @@ class GradBucket:
         t.mul_(1.0 / self.world())
         return w
 
+    def allreduce_replayed(self):
+        """All-reduce after a CUDA-graph REPLAY of forward + backward: the kernels have written every region of the flat
+        buffer, but the Python bookkeeping of the sinks (begin() / ready()) did not run, so nothing is in flight and nothing
+        may be zeroed.  Packs the loose tail, ONE collective over the whole buffer, unpacks the tail.  (NCCL calls are kept
+        out of captured graphs on purpose: the capture then holds only this library's and torch's kernels.)"""
+        if self.world() == 1:
+            return
+        off = self.loose_lo
+        for p in self.loose:
+            n = p.numel()
+            if p.grad is None:
+                self.flat.narrow(0, off, n).zero_()
+            else:
+                self.flat.narrow(0, off, n).copy_(p.grad.reshape(-1))
+            off += n
+        self._reduce(self.flat)
+        off = self.loose_lo
+        for p in self.loose:
+            n = p.numel()
+            if p.grad is not None:
+                p.grad.copy_(self.flat.narrow(0, off, n).view_as(p))
+            off += n
+
     def allreduce_mean(self, group=None):
         if group is not None:
             self.group = group
