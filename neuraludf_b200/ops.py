@@ -12,10 +12,21 @@ from . import _lib as L
 
 
 def _require_cuda(*ts):
+    """Every libnudf call launches on the CURRENT device's current stream: tensors must live there.  (One process per GPU --
+    `torch.cuda.set_device(local_rank)` -- is the supported arrangement; a tensor on another device would otherwise be touched
+    by kernels of the wrong device without any stream ordering.)"""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("neuraludf_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path"
                                % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError("neuraludf_b200: tensor on %s but the current CUDA device is cuda:%d; call "
+                               "torch.cuda.set_device(...) (one process per GPU)" % (t.device, cur))
 
 
 def _f32c(t):
@@ -90,6 +101,11 @@ class UdfHandle:
         """parameter groups in the order a gradient bucket must lay them out: the biases first, contiguous and in layer
         order (nudf_udf_backward writes dbias as ONE array), then g / v of every layer"""
         return [[m.bias for m in self.layers], [p for m in self.layers for p in (m.weight_g, m.weight_v)]]
+
+    def invalidate(self):
+        """Forget the folded weights.  The cache is keyed on (data_ptr, Tensor._version) of every parameter: optimisers and
+        `load_state_dict` bump the version, writes through `param.data` do NOT -- call this after such an update."""
+        self._key = None
 
     def refresh(self):
         ps = self.params()
@@ -232,6 +248,10 @@ class ColorHandle:
         """biases first in the library's order (base layers, then main layers: nudf_color_backward's dbias), then g / v"""
         mods = list(self.base) + list(self.main)
         return [[m.bias for m in mods], [p for m in mods for p in (m.weight_g, m.weight_v)]]
+
+    def invalidate(self):
+        """see UdfHandle.invalidate"""
+        self._key = None
 
     def refresh(self):
         ps = self.params()
