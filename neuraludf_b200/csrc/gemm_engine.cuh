@@ -76,6 +76,10 @@ static inline int gemm_tn(const float* A, int64_t lda, const float* B, int64_t l
     const tc::TnPair pr{A, lda, B, ldb, colsum_a};
     return tc::gemm_tn2(&pr, 1, M, N, K, epi, st);
   }
+  if (tc_on(chain) && M >= 32 && N >= 32 && K >= 1024 && (lda & 3) == 0 && (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(B) & 15u) == 0) {
+    const tc::TnPair pr{A, lda, B, ldb, colsum_a};        // row-major operands through the cp.async-fed kernel
+    return tc::gemm_tn2(&pr, 1, M, N, K, epi, st, true);
+  }
   if (tc_on(chain) && M >= 32 && N >= 32 && K >= 128) {
     // split the points so that (M tiles x N tiles x splits) fills the SMs once, with at least 8 slices of 64 points per CTA
     const int tiles = (int)(cdiv(M, 128) * cdiv(N, 256));

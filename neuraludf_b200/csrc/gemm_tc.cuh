@@ -1096,7 +1096,50 @@ __device__ __forceinline__ void t2_convert(const uint8_t* raw_warp, uint8_t* s_h
   }
 }
 
-template <class Epi>
+// ---- row-major operands (colour / NeRF++ networks): a granule = 16 points x the warp's 32 columns -------------------------
+// Copy: lane l moves the 16-byte column quad (l & 7) of point 4 i + (l >> 3), i = 0..3: every warp instruction reads four
+// 128-byte row segments (whole sectors).  Raw layout [point][quad ^ (point >> 1)][16 B]: conflict-free for the copy (8 lanes =
+// one point, 8 distinct quads) and for the split (8 lanes = 8 point pairs of one quad).
+__device__ __forceinline__ void t2_issue_rm(const float* __restrict__ X, int64_t ld, int col0, int64_t k0, int64_t k_end, uint32_t raw_warp,
+                                            int lane) {
+  const int c = lane & 7;
+  const bool col_ok = col0 + 4 * c < ld;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pl = 4 * i + (lane >> 3);
+    const int64_t row = k0 + pl;
+    const bool v = col_ok && row < k_end;
+    cp_async16(raw_warp + (uint32_t)pl * 128u + (uint32_t)((c ^ (pl >> 1)) & 7) * 16u, v ? X + row * ld + col0 + 4 * c : X, v ? 16u : 0u);
+  }
+}
+// Split: lane (p = lane & 7, g = lane >> 3) packs the point pair (2 p, 2 p + 1) of the quads g and g + 4.
+// pre[j]: swizzled byte offset of (row-in-atom 4 (g & 1) + j, k = 2 p) for k half 0 / granule 0; the k position of the granule
+// only flips bits of the 16-byte chunk index: offset ^= (4 khalf + 2 gran) << 4.
+template <bool CSUM>
+__device__ __forceinline__ void t2_convert_rm(const uint8_t* raw_warp, uint8_t* w_hi, uint8_t* w_lo, const uint32_t (&pre)[4], uint32_t kflip,
+                                              int lane, float* csum) {
+  const int p = lane & 7, g = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = g + 4 * i;
+    const float4 a = *reinterpret_cast<const float4*>(raw_warp + (2 * p) * 128 + ((q ^ p) & 7) * 16);
+    const float4 b = *reinterpret_cast<const float4*>(raw_warp + (2 * p + 1) * 128 + ((q ^ p) & 7) * 16);
+    const float x0[4] = {a.x, a.y, a.z, a.w}, x1[4] = {b.x, b.y, b.z, b.w};
+    // tile rows r0 + 4 q + j = atom (r0 / 8 + 2 i + (g >> 1)), row-in-atom 4 (g & 1) + j
+    uint8_t* h = w_hi + (2 * i + (g >> 1)) * 1024;
+    uint8_t* l = w_lo + (2 * i + (g >> 1)) * 1024;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t hi = pack_bf16(x0[j], x1[j]);
+      const uint32_t lo = pack_bf16(x0[j] - __uint_as_float(hi << 16), x1[j] - __uint_as_float(hi & 0xFFFF0000u));
+      *reinterpret_cast<uint32_t*>(h + (pre[j] ^ kflip)) = hi;
+      *reinterpret_cast<uint32_t*>(l + (pre[j] ^ kflip)) = lo;
+      if (CSUM) csum[4 * i + j] += x0[j] + x1[j];
+    }
+  }
+}
+
+template <class Epi, bool RM>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int64_t k_chunk, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1147,6 +1190,11 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
         const int isl = i < n_sl ? i : i - n_sl;
         const float* X = is_a ? pr.A : pr.B;
         const int64_t ld = is_a ? pr.lda : pr.ldb;
+        if (RM) {                                               // granule = points [16 (h & 1), +16) of the slice, all 32 columns
+          t2_issue_rm(X, ld, col0, kb + (int64_t)isl * T2_BK + 16 * (h & 1), ke, raw_warp_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
+          cp_async_commit();
+          return;
+        }
         const int64_t row = kb + (int64_t)isl * T2_BK + lane;
         const int cq0 = (col0 >> 2) + 4 * (h & 1);              // first quad of this half
         int nq = (int)(ld >> 2) - cq0;                          // quads of this half that exist
@@ -1161,6 +1209,9 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
     for (int kh = 0; kh < 2; ++kh)
 #pragma unroll
       for (int j = 0; j < 4; ++j) pre[kh][j] = sw128((uint32_t)(4 * (lane >> 4) + j), (uint32_t)(32 * kh + 2 * (lane & 15)));
+    uint32_t pre_rm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre_rm[j] = sw128((uint32_t)(4 * ((lane >> 3) & 1) + j), (uint32_t)(2 * (lane & 7)));
     uint8_t* w_hi = s_hi + (r0 >> 3) * 1024;
     uint8_t* w_lo = s_lo + (r0 >> 3) * 1024;
 #pragma unroll
@@ -1177,7 +1228,10 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
       if (i >= 2) mbar_wait(&ctl->empty[s], (uint32_t)(((i >> 1) - 1) & 1));
       if (active) {
         const uint8_t* rl = raw_warp + (uint32_t)((2 * i) % T2_RING) * T2_RAW_GRAN;
-        if (s == 0) {
+        if (RM) {
+          if (do_csum) t2_convert_rm<true>(rl, w_hi, w_lo, pre_rm, (uint32_t)(4 * s) << 4, lane, csum);
+          else t2_convert_rm<false>(rl, w_hi, w_lo, pre_rm, (uint32_t)(4 * s) << 4, lane, csum);
+        } else if (s == 0) {
           if (do_csum) t2_convert<true, 0>(rl, w_hi, w_lo, pre[0], lane, csum); else t2_convert<false, 0>(rl, w_hi, w_lo, pre[0], lane, csum);
         } else {
           if (do_csum) t2_convert<true, 0>(rl, w_hi, w_lo, pre[1], lane, csum); else t2_convert<false, 0>(rl, w_hi, w_lo, pre[1], lane, csum);
@@ -1190,7 +1244,10 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
       __syncwarp();
       if (active) {
         const uint8_t* rl = raw_warp + (uint32_t)((2 * i + 1) % T2_RING) * T2_RAW_GRAN;
-        if (s == 0) {
+        if (RM) {
+          if (do_csum) t2_convert_rm<true>(rl, w_hi, w_lo, pre_rm, (uint32_t)(4 * s + 2) << 4, lane, csum);
+          else t2_convert_rm<false>(rl, w_hi, w_lo, pre_rm, (uint32_t)(4 * s + 2) << 4, lane, csum);
+        } else if (s == 0) {
           if (do_csum) t2_convert<true, 1>(rl, w_hi, w_lo, pre[0], lane, csum); else t2_convert<false, 1>(rl, w_hi, w_lo, pre[0], lane, csum);
         } else {
           if (do_csum) t2_convert<true, 1>(rl, w_hi, w_lo, pre[1], lane, csum); else t2_convert<false, 1>(rl, w_hi, w_lo, pre[1], lane, csum);
@@ -1200,7 +1257,18 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
       mbar_arrive(&ctl->full[s]);
       if (is_a && blockIdx.y == 0 && (i == n_sl - 1 || i == total - 1)) {       // end of a pair: flush its column sums
         float* out = pair_of(i).colsum_a;
-        if (out != nullptr) {
+        if (out != nullptr && RM) {                     // lanes (p, g): columns r0 + 4 (g + 4 i) + j in csum[4 i + j]; reduce over p
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = csum[j];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            const int m = m0 + r0 + 4 * ((lane >> 3) + 4 * (j >> 2)) + (j & 3);
+            if ((lane & 7) == 0 && m < M) atomicAdd(out + m, v);
+            csum[j] = 0.f;
+          }
+        } else if (out != nullptr) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float v = csum[j];
@@ -1252,8 +1320,9 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
   }
 }
 
+// row_major: operands are plain [K, ld] row-major fp32 (ld % 4 == 0, 16-byte aligned bases); else T128 (common.cuh)
 template <class Epi>
-static inline int gemm_tn2(const TnPair* pairs, int n_pairs, int M, int N, int64_t K, const Epi& epi, cudaStream_t st) {
+static inline int gemm_tn2(const TnPair* pairs, int n_pairs, int M, int N, int64_t K, const Epi& epi, cudaStream_t st, bool row_major = false) {
   if (M <= 0 || N <= 0 || K <= 0 || n_pairs <= 0) return 0;
   const int tiles = (int)(cdiv(M, BM) * cdiv(N, 256));
   int splits = sm_count() / tiles;
@@ -1263,14 +1332,17 @@ static inline int gemm_tn2(const TnPair* pairs, int n_pairs, int M, int N, int64
   const int64_t k_chunk = round_up(cdiv(K, splits), 128);      // whole 128-point blocks of the T128 layout per CTA
   splits = (int)cdiv(K, k_chunk);
   const size_t smem = (size_t)T2_PLANES + (size_t)T2_RING * T2_RAW_GRAN + sizeof(SmemCtl) + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_tn2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[row_major ? 1 : 0]) {
+    if (row_major) NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_tn2_kernel<Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else NUDF_CUDA_OK(cudaFuncSetAttribute(gemm_tn2_kernel<Epi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[row_major ? 1 : 0] = true;
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(N, 256), (unsigned)splits);
   LaunchTimer lt_(FAM_TC_WGRAD, st);
-  gemm_tn2_kernel<Epi><<<grid, TN_THREADS, smem, st>>>(pairs[0], n_pairs > 1 ? pairs[1] : pairs[0], n_pairs > 1 ? 2 : 1, M, N, K, k_chunk, epi);
+  const TnPair& q1 = n_pairs > 1 ? pairs[1] : pairs[0];
+  if (row_major) gemm_tn2_kernel<Epi, true><<<grid, TN_THREADS, smem, st>>>(pairs[0], q1, n_pairs > 1 ? 2 : 1, M, N, K, k_chunk, epi);
+  else gemm_tn2_kernel<Epi, false><<<grid, TN_THREADS, smem, st>>>(pairs[0], q1, n_pairs > 1 ? 2 : 1, M, N, K, k_chunk, epi);
   NUDF_LAUNCH_OK();
   return 0;
 }
