@@ -80,12 +80,20 @@ __global__ void color_head_kernel(const float* __restrict__ ym, int ld_ym, int d
 
 __global__ void pack_pts_feat_kernel(const float* __restrict__ pts, const float* __restrict__ feat, int64_t ld_feat, int F,
                                      int64_t P, float* __restrict__ xb, int ld_xb) {
+  // one thread = 4 consecutive columns of one row (ld_xb % 4 == 0: one 16-byte store; the reads of the odd-width feature
+  // tensor stay scalar but consecutive across the warp)
+  const int q4 = ld_xb >> 2;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int w = 3 + F;
-  int64_t row = idx / w;
-  int c = (int)(idx - row * w);
+  int64_t row = idx / q4;
+  int c = (int)(idx - row * q4) * 4;
   if (row >= P) return;
-  xb[row * ld_xb + c] = c < 3 ? pts[row * 3 + c] : feat[row * ld_feat + (c - 3)];
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cj = c + j;
+    v[j] = cj < 3 ? pts[row * 3 + cj] : (cj < 3 + F ? feat[row * ld_feat + (cj - 3)] : 0.f);
+  }
+  *reinterpret_cast<float4*>(xb + row * ld_xb + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // Weight gradient of a narrow head (n_out <= 16: colour / density heads): dW[m, n] += sum_p dZ[p, m] X[p, n], db[m] += sum_p dZ[p, m].
@@ -343,7 +351,7 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
   color_ctx_layout(p, P, &c);
   float* xb = ctx + c.xb;
   float* xm = ctx + c.xm;
-  pack_pts_feat_kernel<<<ew_blocks(P * (3 + p.F), 256), 256, 0, st>>>(pts, feat, ld_feat, p.F, P, xb, p.ld_xb);
+  pack_pts_feat_kernel<<<ew_blocks(P * (p.ld_xb / 4), 256), 256, 0, st>>>(pts, feat, ld_feat, p.F, P, xb, p.ld_xb);
   NUDF_LAUNCH_OK();
   ew_pe_kernel<<<ew_blocks(P, 128), 128, 0, st>>>(dirs, 3, p.Lv, spr, P, xm, p.ld_xm, 0, nullptr, 0, 0);
   NUDF_LAUNCH_OK();

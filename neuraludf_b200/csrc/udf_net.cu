@@ -405,6 +405,72 @@ __global__ void zlast_split_kernel(const float* __restrict__ ob, int64_t ld_ob, 
   else zf[mat_off(t128 != 0, row, c - 1, F)] = v;
 }
 
+// Tiled versions for the T128 layout (fused chains): a CTA moves a 128-point x 32-column tile through shared memory so that
+// BOTH sides are coalesced -- 16-byte accesses with the points innermost on the T128 side, 128-byte column runs on the row-major
+// side (the torch-facing [P, 257] tensors: odd width, no vector access possible).  grid = (point tiles, column tiles).
+// out[P, ld_out] <- cat(|y0| / scale, y[1:]);  sgn <- sign(y0)
+__global__ void __launch_bounds__(256) udf_finalize_t128_kernel(const float* __restrict__ y, int y_ld, int d_out, int64_t P, float inv_scale,
+                                                               float* __restrict__ out, int64_t ld_out, float* __restrict__ sgn) {
+  __shared__ float tile[128][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 128;
+  const int c0 = blockIdx.y * 32;
+  const int t = threadIdx.x;
+  {
+    const int r = t & 127;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int q = (t >> 7) + 2 * k;                       // column quad of the tile
+      const int c = c0 + 4 * q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < P && c < y_ld) v = *reinterpret_cast<const float4*>(y + t128_off(r0 + r, c, y_ld));
+      tile[r][4 * q + 0] = v.x; tile[r][4 * q + 1] = v.y; tile[r][4 * q + 2] = v.z; tile[r][4 * q + 3] = v.w;
+    }
+  }
+  __syncthreads();
+  const int cc = t & 31;
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const int r = (t >> 5) + 8 * k;
+    const int64_t row = r0 + r;
+    const int c = c0 + cc;
+    if (row < P && c < d_out) {
+      float v = tile[r][cc];
+      if (c == 0) {
+        if (sgn) sgn[row] = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
+        v = fabsf(v) * inv_scale;
+      }
+      if (out) out[row * ld_out + c] = v;
+    }
+  }
+}
+// zf[:, j] (T128, ld F) <- ob[:, 1 + j];  z0 <- sgn * ob[:, 0] / scale
+__global__ void __launch_bounds__(256) zlast_split_t128_kernel(const float* __restrict__ ob, int64_t ld_ob, const float* __restrict__ sgn,
+                                                              float inv_scale, int F, int64_t P, float* __restrict__ zf, float* __restrict__ z0) {
+  __shared__ float tile[128][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 128;
+  const int c0 = blockIdx.y * 32;                           // feature columns [c0, c0 + 32) of zf = columns 1 + c0 .. of ob
+  const int t = threadIdx.x;
+  const int cc = t & 31;
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const int r = (t >> 5) + 8 * k;
+    const int64_t row = r0 + r;
+    float v = 0.f;
+    if (row < P && c0 + cc < F) v = ob[row * ld_ob + 1 + c0 + cc];
+    tile[r][cc] = v;
+    if (blockIdx.y == 0 && cc == 0 && row < P) z0[row] = ob[row * ld_ob] * sgn[row] * inv_scale;
+  }
+  __syncthreads();
+  const int r = t & 127;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int q = (t >> 7) + 2 * k;
+    const int c = c0 + 4 * q;
+    if (r0 + r < P && c < F)
+      *reinterpret_cast<float4*>(zf + t128_off(r0 + r, c, F)) = make_float4(tile[r][4 * q], tile[r][4 * q + 1], tile[r][4 * q + 2], tile[r][4 * q + 3]);
+  }
+}
+
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)cdiv(n, t); }
 
 // ---- host orchestration -----------------------------------------------------------------------------------------
@@ -757,8 +823,8 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
     chain::ChainParams cp;
     build_forward(p, wfold, pts, P, ctx, &c, nullptr, true, &cp);
     if (int rc = chain::launch_chain(cp, FAM_UDF_FWD_CHAIN, st)) return rc;
-    udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
-                                                                ctx + c.sgn, 1);
+    udf_finalize_t128_kernel<<<dim3(nblk(P, 128), nblk(p.d_out, 32)), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
+                                                                                    ctx + c.sgn);
     NUDF_LAUNCH_OK();
     pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad, 1, p.skip >= 1 ? ctx + c.gpe : nullptr,
                                                 p.stash_ld, p.skip >= 1 ? (p.out_dim[p.skip - 1] & 7) : 0);
@@ -823,7 +889,7 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
     float* zf = scratch + s.zlast;                  // [P, F] feature part of the upstream gradient of the last layer
     float* z0 = zf + ctx_rows(p, P) * F;            // [P]    udf-head part, times sgn / scale
     if (out_bar) {
-      zlast_split_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0, 1);
+      zlast_split_t128_kernel<<<dim3(nblk(P, 128), nblk(F, 32)), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
       NUDF_LAUNCH_OK();
     } else {
       NUDF_CUDA_OK(cudaMemsetAsync(zf, 0, sizeof(float) * (ctx_rows(p, P) * F + P), st));
