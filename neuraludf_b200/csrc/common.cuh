@@ -123,5 +123,74 @@ static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- weight-norm fold / unfold of ALL layers of a network in one launch ------------------------------------------------------
+// W = g v / ||v||  (row-wise; torch._weight_norm(v, g, dim=0), reference models/fields.py:110-113) and its adjoint
+// dg = <dW, v>/||v||, dv = g/||v|| (dW - dg v/||v||).  A job = one layer; grid = (max rows over the jobs, number of jobs).
+constexpr int NUDF_MAX_JOBS = 32;
+struct FoldJob {
+  const float* g; const float* v;      // [out], [out, in]
+  const float* dw; float* dg; float* dv;   // unfold only
+  float* w;                            // fold only: [out, ld], columns >= in zero-filled
+  int out, in, ld;
+};
+struct FoldJobs { int n; FoldJob j[NUDF_MAX_JOBS]; };
+
+static __global__ void fold_jobs_kernel(const __grid_constant__ FoldJobs jobs) {
+  const FoldJob& J = jobs.j[blockIdx.y];
+  const int row = blockIdx.x;
+  if (row >= J.out) return;
+  const float* vr = J.v + (int64_t)row * J.in;
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < J.in; k += blockDim.x) ss += vr[k] * vr[k];
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float s = J.g[row] / sqrtf(red[0]);
+  for (int k = threadIdx.x; k < J.ld; k += blockDim.x) J.w[(int64_t)row * J.ld + k] = k < J.in ? vr[k] * s : 0.f;
+}
+static __global__ void unfold_jobs_kernel(const __grid_constant__ FoldJobs jobs) {
+  const FoldJob& J = jobs.j[blockIdx.y];
+  const int row = blockIdx.x;
+  if (row >= J.out) return;
+  const float* vr = J.v + (int64_t)row * J.in;
+  const float* dr = J.dw + (int64_t)row * J.ld;
+  float ss = 0.f, dot = 0.f;
+  for (int k = threadIdx.x; k < J.in; k += blockDim.x) { ss += vr[k] * vr[k]; dot += vr[k] * dr[k]; }
+  __shared__ float red[2][32];
+  for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t0 = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.f;
+    float t1 = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+    if (threadIdx.x == 0) { red[0][0] = t0; red[1][0] = t1; }
+  }
+  __syncthreads();
+  const float n = sqrtf(red[0][0]);
+  const float dgv = red[1][0] / n;
+  if (threadIdx.x == 0) J.dg[row] = dgv;
+  const float gn = J.g[row] / n;
+  for (int k = threadIdx.x; k < J.in; k += blockDim.x) J.dv[(int64_t)row * J.in + k] = gn * (dr[k] - dgv * vr[k] / n);
+}
+// host: launch all jobs at once
+static inline int run_fold_jobs(const FoldJobs& jobs, bool unfold, cudaStream_t st) {
+  if (jobs.n <= 0) return 0;
+  int max_out = 0;
+  for (int i = 0; i < jobs.n; ++i) max_out = jobs.j[i].out > max_out ? jobs.j[i].out : max_out;
+  const dim3 grid((unsigned)max_out, (unsigned)jobs.n);
+  if (unfold) unfold_jobs_kernel<<<grid, 128, 0, st>>>(jobs);
+  else fold_jobs_kernel<<<grid, 128, 0, st>>>(jobs);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace nudf
 #endif

@@ -51,13 +51,13 @@ __host__ __device__ inline int64_t tile_offset(int N, int K, int t, int np) {
 __host__ __device__ inline int64_t image_elems(int N, int K, int np) { return tile_offset(N, K, n_tiles(N, np), np); }
 
 // transposed == 0: B(n,k) = W[n*ldw + k]   (X W^T)      transposed == 1: B(n,k) = W[k*ldw + n]   (dY W)
-static __global__ void tc_prep_weights_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int transposed, int np,
-                                              uint16_t* __restrict__ img) {
+static __device__ __forceinline__ void tc_prep_weights_body(const float* __restrict__ W, int64_t ldw, int N, int K, int transposed, int np,
+                                                            uint16_t* __restrict__ img, int64_t start, int64_t stride) {
   const int Kp = pad64(K);
   const int nt = n_tiles(N, np);
   int64_t total = 0;
   for (int t = 0; t < nt; ++t) total += (int64_t)tile_rows(N, t, np) * Kp;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t idx = start; idx < total; idx += stride) {
     int64_t rem = idx;
     int t = 0;
     while (rem >= (int64_t)tile_rows(N, t, np) * Kp) { rem -= (int64_t)tile_rows(N, t, np) * Kp; ++t; }
@@ -76,6 +76,10 @@ static __global__ void tc_prep_weights_kernel(const float* __restrict__ W, int64
       r -= __bfloat162float(h);
     }
   }
+}
+static __global__ void tc_prep_weights_kernel(const float* __restrict__ W, int64_t ldw, int N, int K, int transposed, int np,
+                                              uint16_t* __restrict__ img) {
+  tc_prep_weights_body(W, ldw, N, K, transposed, np, img, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -1343,6 +1347,31 @@ static inline int gemm_tn2(const TnPair* pairs, int n_pairs, int M, int N, int64
   const TnPair& q1 = n_pairs > 1 ? pairs[1] : pairs[0];
   if (row_major) gemm_tn2_kernel<Epi, true><<<grid, TN_THREADS, smem, st>>>(pairs[0], q1, n_pairs > 1 ? 2 : 1, M, N, K, k_chunk, epi);
   else gemm_tn2_kernel<Epi, false><<<grid, TN_THREADS, smem, st>>>(pairs[0], q1, n_pairs > 1 ? 2 : 1, M, N, K, k_chunk, epi);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
+// several weight images in one launch: grid.y = job
+struct PrepWJob { const float* W; uint16_t* img; int ldw, N, K, transposed, np; };
+struct PrepWJobs { int n; PrepWJob j[48]; };
+static __device__ __forceinline__ void tc_prep_weights_body(const float* __restrict__ W, int64_t ldw, int N, int K, int transposed, int np,
+                                                            uint16_t* __restrict__ img, int64_t start, int64_t stride);
+static __global__ void tc_prep_weights_jobs_kernel(const __grid_constant__ PrepWJobs jobs) {
+  const PrepWJob& J = jobs.j[blockIdx.y];
+  tc_prep_weights_body(J.W, J.ldw, J.N, J.K, J.transposed, J.np, J.img, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                       (int64_t)gridDim.x * blockDim.x);
+}
+static inline int prep_weights_jobs(const PrepWJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return 0;
+  int64_t mx = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    int64_t total = 0;
+    for (int t = 0; t < n_tiles(jobs.j[i].N, jobs.j[i].np); ++t) total += (int64_t)tile_rows(jobs.j[i].N, t, jobs.j[i].np) * pad64(jobs.j[i].K);
+    mx = total > mx ? total : mx;
+  }
+  int blocks = (int)((mx + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  tc_prep_weights_jobs_kernel<<<dim3((unsigned)blocks, (unsigned)jobs.n), 256, 0, st>>>(jobs);
   NUDF_LAUNCH_OK();
   return 0;
 }

@@ -302,22 +302,26 @@ int nudf_color_fold_weights(const nudf_color_desc* d, float* wfold, void* stream
   ColorPlan p;
   if (int rc = color_plan(d, &p)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int l = 0; l < p.n_lin; ++l) {
-    fold_kernel2<<<p.dims_b[l + 1], 128, 0, st>>>(d->base_g[l], d->base_v[l], p.dims_b[l + 1], p.dims_b[l], p.wb_ld[l],
-                                                   wfold + p.wb_off[l]);
-    NUDF_LAUNCH_OK();
-    fold_kernel2<<<p.dims_m[l + 1], 128, 0, st>>>(d->main_g[l], d->main_v[l], p.dims_m[l + 1], p.dims_m[l], p.wm_ld[l],
-                                                   wfold + p.wm_off[l]);
-    NUDF_LAUNCH_OK();
+  {                                                     // all layers of both stacks: one launch
+    FoldJobs jobs;
+    jobs.n = 0;
+    for (int l = 0; l < p.n_lin; ++l) {
+      jobs.j[jobs.n++] = FoldJob{d->base_g[l], d->base_v[l], nullptr, nullptr, nullptr, wfold + p.wb_off[l], p.dims_b[l + 1], p.dims_b[l], (int)p.wb_ld[l]};
+      jobs.j[jobs.n++] = FoldJob{d->main_g[l], d->main_v[l], nullptr, nullptr, nullptr, wfold + p.wm_off[l], p.dims_m[l + 1], p.dims_m[l], (int)p.wm_ld[l]};
+    }
+    if (int rc = run_fold_jobs(jobs, false, st)) return rc;
   }
   if (get_engine() == 1) {
     uint16_t* img = reinterpret_cast<uint16_t*>(wfold + p.w_total);
+    tc::PrepWJobs pj;
+    pj.n = 0;
     for (int l = 0; l < p.n_lin; ++l) {
-      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l + 1], p.dims_b[l], 0, 2, img + p.ib_nt[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.wb_off[l], p.wb_ld[l], p.dims_b[l], p.dims_b[l + 1], 1, 2, img + p.ib_nn[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l + 1], p.dims_m[l], 0, 2, img + p.im_nt[l], st)) return rc;
-      if (int rc = tc::prep_weights(wfold + p.wm_off[l], p.wm_ld[l], p.dims_m[l], p.dims_m[l + 1], 1, 2, img + p.im_nn[l], st)) return rc;
+      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wb_off[l], img + p.ib_nt[l], (int)p.wb_ld[l], p.dims_b[l + 1], p.dims_b[l], 0, 2};
+      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wb_off[l], img + p.ib_nn[l], (int)p.wb_ld[l], p.dims_b[l], p.dims_b[l + 1], 1, 2};
+      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wm_off[l], img + p.im_nt[l], (int)p.wm_ld[l], p.dims_m[l + 1], p.dims_m[l], 0, 2};
+      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wm_off[l], img + p.im_nn[l], (int)p.wm_ld[l], p.dims_m[l], p.dims_m[l + 1], 1, 2};
     }
+    if (int rc = tc::prep_weights_jobs(pj, st)) return rc;
   }
   return 0;
 }
@@ -472,15 +476,13 @@ int nudf_color_unfold_grads(const nudf_color_desc* d, const float* dwfold, float
   ColorPlan p;
   if (int rc = color_plan(d, &p)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  FoldJobs jobs;
+  jobs.n = 0;
   for (int l = 0; l < p.n_lin; ++l) {
-    unfold_kernel2<<<p.dims_b[l + 1], 128, 0, st>>>(d->base_g[l], d->base_v[l], dwfold + p.wb_off[l], p.dims_b[l + 1],
-                                                     p.dims_b[l], p.wb_ld[l], dg_base[l], dv_base[l]);
-    NUDF_LAUNCH_OK();
-    unfold_kernel2<<<p.dims_m[l + 1], 128, 0, st>>>(d->main_g[l], d->main_v[l], dwfold + p.wm_off[l], p.dims_m[l + 1],
-                                                     p.dims_m[l], p.wm_ld[l], dg_main[l], dv_main[l]);
-    NUDF_LAUNCH_OK();
+    jobs.j[jobs.n++] = FoldJob{d->base_g[l], d->base_v[l], dwfold + p.wb_off[l], dg_base[l], dv_base[l], nullptr, p.dims_b[l + 1], p.dims_b[l], (int)p.wb_ld[l]};
+    jobs.j[jobs.n++] = FoldJob{d->main_g[l], d->main_v[l], dwfold + p.wm_off[l], dg_main[l], dv_main[l], nullptr, p.dims_m[l + 1], p.dims_m[l], (int)p.wm_ld[l]};
   }
-  return 0;
+  return run_fold_jobs(jobs, true, st);
 }
 
 // =================================================================================================================

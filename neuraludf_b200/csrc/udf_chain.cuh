@@ -149,10 +149,10 @@ static __global__ void chain_layer_scale_kernel(const float* __restrict__ W, int
 }
 // one block per padded operand row n of B(n, k), n < N, k < K.  transposed == 0: B(n,k) = W[n*ldw + k] (X W^T);
 // transposed == 1: B(n,k) = W[k*ldw + n] (dY W).  bias_tab (optional): [128 n_tiles] copy of bias, zero padded.
-static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int N, int K,
-                                         int transposed, const float* __restrict__ meta, uint16_t* __restrict__ img,
-                                         float* __restrict__ bias_tab, int split_bf16 = 0) {
-  const int col = blockIdx.x;                    // padded output column: 128 t + local row
+static __device__ __forceinline__ void chain_prep_row(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int N, int K,
+                                                      int transposed, const float* __restrict__ meta, uint16_t* __restrict__ img,
+                                                      float* __restrict__ bias_tab, int split_bf16, int col) {
+  // col = padded output column: 128 t + local row
   const int t = col / CH_NT, nl = col - t * CH_NT;
   const int rows_t = ch_tile_rows(N, t);
   const bool valid = col < N;
@@ -185,6 +185,51 @@ static __global__ void chain_prep_kernel(const float* __restrict__ W, int64_t ld
     b[(int64_t)rows_t * 64] = __half_as_ushort(h1);
     b[(int64_t)2 * rows_t * 64] = __half_as_ushort(h2);
   }
+}
+
+// all layers of a network in one launch each: grid.y = job
+struct ScaleJob { const float* W; float* meta; int ldw, rows, cols; };
+struct ScaleJobs { int n; ScaleJob j[16]; };
+struct PrepJob { const float* W; const float* bias; const float* meta; uint16_t* img; float* bias_tab; int ldw, N, K, transposed, split; };
+struct PrepJobs { int n; PrepJob j[48]; };
+static __global__ void chain_scale_jobs_kernel(const __grid_constant__ ScaleJobs jobs) {
+  const ScaleJob& J = jobs.j[blockIdx.x];
+  float mx = 0.f;
+  for (int64_t i = threadIdx.x; i < (int64_t)J.rows * J.cols; i += blockDim.x) mx = fmaxf(mx, fabsf(J.W[(i / J.cols) * J.ldw + (i % J.cols)]));
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+    int e = 0;
+    if (mx > 1e-30f && mx < 1e30f) e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;
+    J.meta[0] = __uint_as_float((uint32_t)(3 - e + 127) << 23);
+    J.meta[1] = __uint_as_float((uint32_t)(e - 13 + 127) << 23);
+  }
+}
+static __device__ __forceinline__ void chain_prep_row(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int N, int K,
+                                                      int transposed, const float* __restrict__ meta, uint16_t* __restrict__ img,
+                                                      float* __restrict__ bias_tab, int split_bf16, int col);
+static __global__ void chain_prep_jobs_kernel(const __grid_constant__ PrepJobs jobs) {
+  const PrepJob& J = jobs.j[blockIdx.y];
+  const int col = blockIdx.x;
+  if (col >= CH_NT * ch_n_tiles(J.N)) return;
+  chain_prep_row(J.W, J.ldw, J.bias, J.N, J.K, J.transposed, J.meta, J.img, J.bias_tab, J.split, col);
+}
+
+static inline int run_prep_jobs(const ScaleJobs& sj, const PrepJobs& pj, cudaStream_t st) {
+  if (sj.n > 0) {
+    chain_scale_jobs_kernel<<<sj.n, 256, 0, st>>>(sj);
+    NUDF_LAUNCH_OK();
+  }
+  if (pj.n > 0) {
+    int mx = 0;
+    for (int i = 0; i < pj.n; ++i) { const int c = CH_NT * ch_n_tiles(pj.j[i].N); mx = c > mx ? c : mx; }
+    chain_prep_jobs_kernel<<<dim3((unsigned)mx, (unsigned)pj.n), 64, 0, st>>>(pj);
+    NUDF_LAUNCH_OK();
+  }
+  return 0;
 }
 
 // ---- device helpers ----------------------------------------------------------------------------------------------------

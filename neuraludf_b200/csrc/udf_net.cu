@@ -476,10 +476,12 @@ static inline unsigned nblk(int64_t n, int t) { return (unsigned)cdiv(n, t); }
 // ---- host orchestration -----------------------------------------------------------------------------------------
 
 static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cudaStream_t st) {
-  for (int l = 0; l < p.n_lin; ++l) {
-    fold_kernel<<<p.out_dim[l], 128, 0, st>>>(d->weight_g[l], d->weight_v[l], p.out_dim[l], p.in_dim[l], p.w_ld[l],
-                                               wfold + p.w_off[l]);
-    NUDF_LAUNCH_OK();
+  {
+    FoldJobs jobs;
+    jobs.n = p.n_lin;
+    for (int l = 0; l < p.n_lin; ++l)
+      jobs.j[l] = FoldJob{d->weight_g[l], d->weight_v[l], nullptr, nullptr, nullptr, wfold + p.w_off[l], p.out_dim[l], p.in_dim[l], (int)p.w_ld[l]};
+    if (int rc = run_fold_jobs(jobs, false, st)) return rc;
   }
   if (get_engine() == 1) {
     uint16_t* img = reinterpret_cast<uint16_t*>(wfold + p.w_total);
@@ -495,31 +497,31 @@ static int fold_all(const UdfPlan& p, const nudf_udf_desc* d, float* wfold, cuda
           return rc;
     }
     if (p.chain_ok) {
-      // fused chains (udf_chain.cuh): fp16 slice images of W_l as the X W^T operand (F, T) and as the dY W operand (R, B),
-      // one power-of-two scale per layer, bias tables
+      // fused chains (udf_chain.cuh): exact fp16 slice images of W_l as the X W^T operand of the F chain (one power-of-two
+      // scale per layer, bias tables) and split-bf16 images for the R / B chains (dY W operand) and the T chain (X W^T) --
+      // gradient quantities: 2^-16 relative is far inside their tolerance, 3 products.  Two launches for all layers.
       float* tab = wfold + p.w_total + p.img_total / 2;     // per layer: [4 floats of scale meta | bias table]
+      chain::PrepJobs jobs;
+      jobs.n = 0;
+      auto add = [&](const float* W, int64_t ldw, const float* bias, int N, int K, int transposed, const float* meta, uint16_t* im,
+                     float* bias_tab, int split) {
+        jobs.j[jobs.n++] = chain::PrepJob{W, bias, meta, im, bias_tab, (int)ldw, N, K, transposed, split};
+      };
+      chain::ScaleJobs sj;
+      sj.n = p.n_lin;
       for (int l = 0; l < p.n_lin; ++l) {
         float* meta = tab + p.sb_off[l];
         const float* W = wfold + p.w_off[l];
-        chain::chain_layer_scale_kernel<<<1, 256, 0, st>>>(W, p.w_ld[l], p.out_dim[l], p.in_dim[l], meta);
-        NUDF_LAUNCH_OK();
-        chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.out_dim[l]), 64, 0, st>>>(
-            W, p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], 0, meta, img + p.img_chain[l], meta + 4);
-        NUDF_LAUNCH_OK();
-        // R / T / B chains: split-bf16 images (gradient quantities: 2^-16 relative is far inside their tolerance; 3 products)
+        sj.j[l] = chain::ScaleJob{W, meta, (int)p.w_ld[l], p.out_dim[l], p.in_dim[l]};
+        add(W, p.w_ld[l], d->bias[l], p.out_dim[l], p.in_dim[l], 0, meta, img + p.img_chain[l], meta + 4, 0);
         if (l < last) {
-          chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.in_dim[l]), 64, 0, st>>>(
-              W, p.w_ld[l], nullptr, p.in_dim[l], p.out_dim[l], 1, meta, img + p.img_chain_nn[l], nullptr, 1);
-          NUDF_LAUNCH_OK();
-          chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.out_dim[l]), 64, 0, st>>>(
-              W, p.w_ld[l], nullptr, p.out_dim[l], p.in_dim[l], 0, meta, img + p.img_chain_t[l], nullptr, 1);
-          NUDF_LAUNCH_OK();
+          add(W, p.w_ld[l], nullptr, p.in_dim[l], p.out_dim[l], 1, meta, img + p.img_chain_nn[l], nullptr, 1);
+          add(W, p.w_ld[l], nullptr, p.out_dim[l], p.in_dim[l], 0, meta, img + p.img_chain_t[l], nullptr, 1);
         } else if (p.d_out > 1) {
-          chain::chain_prep_kernel<<<chain::CH_NT * chain::ch_n_tiles(p.in_dim[l]), 64, 0, st>>>(
-              W + p.w_ld[l], p.w_ld[l], nullptr, p.in_dim[l], p.d_out - 1, 1, meta, img + p.img_chain_nn1, nullptr, 1);
-          NUDF_LAUNCH_OK();
+          add(W + p.w_ld[l], p.w_ld[l], nullptr, p.in_dim[l], p.d_out - 1, 1, meta, img + p.img_chain_nn1, nullptr, 1);
         }
       }
+      if (int rc = chain::run_prep_jobs(sj, jobs, st)) return rc;
     }
   }
   return 0;
@@ -1059,12 +1061,11 @@ int nudf_udf_unfold_grads(const nudf_udf_desc* d, const float* dwfold, float* co
   UdfPlan p;
   if (int rc = make_plan(d, &p)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int l = 0; l < p.n_lin; ++l) {
-    unfold_kernel<<<p.out_dim[l], 128, 0, st>>>(d->weight_g[l], d->weight_v[l], dwfold + p.w_off[l], p.out_dim[l],
-                                                 p.in_dim[l], p.w_ld[l], dg[l], dv[l]);
-    NUDF_LAUNCH_OK();
-  }
-  return 0;
+  FoldJobs jobs;
+  jobs.n = p.n_lin;
+  for (int l = 0; l < p.n_lin; ++l)
+    jobs.j[l] = FoldJob{d->weight_g[l], d->weight_v[l], dwfold + p.w_off[l], dg[l], dv[l], nullptr, p.out_dim[l], p.in_dim[l], (int)p.w_ld[l]};
+  return run_fold_jobs(jobs, true, st);
 }
 
 }  // extern "C"
