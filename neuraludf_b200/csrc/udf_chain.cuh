@@ -1144,6 +1144,7 @@ static inline int launch_chain(const ChainParams& p, int family, cudaStream_t st
   }
   int64_t grid = (p.P + 127) / 128;
   if (grid > sm_count()) grid = sm_count();
+  if (grid > CH_MAX_GRID) grid = CH_MAX_GRID;                // the per-CTA encoding stash is sized for CH_MAX_GRID tiles
   static int trace_mode = -1;
   if (trace_mode < 0) { const char* e = getenv("NUDF_CHAIN_TRACE"); trace_mode = (e && atoi(e) > 0) ? atoi(e) : 0; }
   if (trace_mode > 0 && p.P >= 128 * 148) {              // profiling aid: synchronous, prints CTA 0's pipeline stamps
