@@ -1187,23 +1187,50 @@ gemm_tn2_kernel(TnPair p0, TnPair p1, int n_pairs, int M, int N, int64_t K, int6
     const int col0 = (is_a ? m0 : n0) + r0;                     // first operand column of this warp
     // k_chunk is a multiple of 128 (launcher): slice i of a pair starts at point kb + 32 i, 4 slices per 128-point block of the
     // T128 layout; inside a block consecutive points are 4 floats apart, the next block is (ld / 4) * 512 floats further
+    // per-pair, per-lane source bases, computed once: the copy loop only adds slice / half offsets.
+    //   T128:       src(isl, half, q) = xb + (isl >> 2) * bs + (isl & 3) * 128 + half * 2048 + q * 512      (kb is a multiple of 128)
+    //   row-major:  src(isl, gr, i)   = xb + (isl * 32 + 16 gr + 4 i) * ld                                  (lane = (point l >> 3, quad l & 7))
+    const float* xb[2];
+    int64_t bs[2];
+    int nq0[2];
+    int lane_row;                                               // point offset of this lane inside a granule
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+      const TnPair& pr = pi == 0 ? p0 : p1;
+      const float* X = is_a ? pr.A : pr.B;
+      const int64_t ld = is_a ? pr.lda : pr.ldb;
+      if (RM) {
+        xb[pi] = X + (kb + (lane >> 3)) * ld + col0 + 4 * (lane & 7);
+        bs[pi] = ld;
+        nq0[pi] = (col0 + 4 * (lane & 7) < ld) ? 1 : 0;         // this lane's column quad exists
+      } else {
+        xb[pi] = X + ((kb >> 7) * (ld >> 2) + (col0 >> 2)) * 512 + lane * 4;
+        bs[pi] = (ld >> 2) * 512;
+        nq0[pi] = (int)(ld >> 2) - (col0 >> 2);                 // column quads of this warp's block that exist
+      }
+    }
+    lane_row = RM ? (lane >> 3) : lane;
+    const float* any = is_a ? p0.A : p0.B;
     auto issue = [&](int h) {                                   // granule h = (slice h >> 1, half h & 1); always commits a group
       if (active && h < n_gran) {
-        const int i = h >> 1;
-        const TnPair& pr = pair_of(i);
+        const int i = h >> 1, half = h & 1;
+        const int pi = i < n_sl ? 0 : 1;
         const int isl = i < n_sl ? i : i - n_sl;
-        const float* X = is_a ? pr.A : pr.B;
-        const int64_t ld = is_a ? pr.lda : pr.ldb;
-        if (RM) {                                               // granule = points [16 (h & 1), +16) of the slice, all 32 columns
-          t2_issue_rm(X, ld, col0, kb + (int64_t)isl * T2_BK + 16 * (h & 1), ke, raw_warp_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
-          cp_async_commit();
-          return;
+        const uint32_t dst = raw_warp_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN;
+        const int64_t row0 = kb + (int64_t)isl * T2_BK;         // first point of the slice
+        if (RM) {                                               // granule = points [16 half, +16) of the slice, all 32 columns
+          const float* src = xb[pi] + ((int64_t)isl * T2_BK + 16 * half) * bs[pi];
+          const int c = lane & 7;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int pl = 4 * k + (lane >> 3);
+            const bool v = nq0[pi] != 0 && row0 + 16 * half + pl < ke;
+            cp_async16(dst + (uint32_t)pl * 128u + (uint32_t)((c ^ (pl >> 1)) & 7) * 16u, v ? src + (int64_t)(4 * k) * bs[pi] : any, v ? 16u : 0u);
+          }
+        } else {
+          const float* src = xb[pi] + (int64_t)(isl >> 2) * bs[pi] + (isl & 3) * 128 + half * 2048;
+          t2_issue(src, any, nq0[pi] - 4 * half, row0 + lane_row < ke, dst, lane);
         }
-        const int64_t row = kb + (int64_t)isl * T2_BK + lane;
-        const int cq0 = (col0 >> 2) + 4 * (h & 1);              // first quad of this half
-        int nq = (int)(ld >> 2) - cq0;                          // quads of this half that exist
-        const float* src = X + ((row >> 7) * (ld >> 2) + cq0) * 512 + (row & 127) * 4;
-        t2_issue(src, X, nq, row < ke, raw_warp_s + (uint32_t)(h % T2_RING) * T2_RAW_GRAN, lane);
       }
       cp_async_commit();
     };
