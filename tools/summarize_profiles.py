@@ -104,5 +104,7 @@ if __name__ == "__main__":
         path, name = spec.rsplit(":", 1)
         hdr = {"chain": "# udf_chain_kernel: launch 0 = F + R (value chain + reverse sweep), launch 1 = T + B (tangent + backward chains) of a C2 step,\n"
                         "# 65 536 points = 512 tiles of 128 points on 148 persistent CTAs.  Algorithmic MACs: F+R 2 x 524 544 per point, T+B 2 x 524 544.\n",
-               "wgrad": "# gemm_tn2_kernel: dW_l += D_l^T Adot_l + Zbar_l^T A_l (two operand pairs, 4 x [65 536 x 256] fp32 = 268 MB algorithmic read)\n"}.get(name, "")
+               "wgrad": "# gemm_tn2_kernel<.., 0> (T128 operands): dW_l += D_l^T Adot_l + Zbar_l^T A_l (two operand pairs, 4 x [65 536 x 256] fp32 = 268 MB\n"
+                        "# algorithmic read).  Captured before the last round of address hoisting (73 us per launch in the final launch list).\n",
+               "wgrad_rm": "# gemm_tn2_kernel<.., 1> (row-major operands, colour network): dW += dZ^T X, [65 536 x 128] x [65 536 x 128] fp32 = 67 MB read\n"}.get(name, "")
         report(path, name, "profiles/%s_%s_kernel.txt" % (a.tag, name), hdr)
