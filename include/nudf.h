@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 #define NUDF_MAX_LAYERS 16
-#define NUDF_ABI_VERSION 2
+#define NUDF_ABI_VERSION 3
 /* bits of the device-side status word (nudf_render_out.status, `status` of the sampling entry points): set by the kernels,
  * never cleared by the library; the caller reads it at a host synchronisation point of its choice */
 #define NUDF_STATUS_NONFINITE_SAMPLES 1   /* sample_pdf / up_sample produced a non-finite sample position (:97-101, 265-269) */
@@ -130,6 +130,14 @@ int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts,
 int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* out_bar,
                       int64_t ld_ob, const float* grad_bar, const float* ctx, float* scratch, float* dwfold,
                       float* dbias, void* stream);
+/* The same pair with the value and the feature part as SEPARATE tensors (udf [P], feat [P, ld_feat]; udf_bar [P], feat_bar
+ * [P, ld_fb], each may be NULL = zero): what render_core consumes (udf_renderer_blending.py:364-366 slices udf_nn_output[:, :1]
+ * and [:, 1:]) without an odd-width [P, 257] tensor in between and without re-assembling its gradient. */
+int nudf_udf_forward_split(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* udf, float* feat,
+                           int64_t ld_feat, float* grad, float* ctx, void* stream);
+int nudf_udf_backward_split(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* udf_bar,
+                            const float* feat_bar, int64_t ld_fb, const float* grad_bar, const float* ctx, float* scratch,
+                            float* dwfold, float* dbias, void* stream);
 /* weight-norm backward: dwfold -> (dg[l] [out,1], dv[l] [out,in]) for every layer (overwrites) */
 int nudf_udf_unfold_grads(const nudf_udf_desc* d, const float* dwfold, float* const* dg, float* const* dv, void* stream);
 

@@ -111,6 +111,10 @@ _SIGNATURES = {
     "nudf_udf_scratch_floats": (ctypes.c_int64, [c_void_p, ctypes.c_int64]),
     "nudf_udf_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64,
                                         c_void_p, c_void_p, c_void_p]),
+    "nudf_udf_forward_split": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int64,
+                                              c_void_p, c_void_p, c_void_p]),
+    "nudf_udf_backward_split": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int64,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nudf_udf_value": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p]),
     "nudf_udf_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -170,7 +174,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.nudf_abi_version() != 2:
+        if L.nudf_abi_version() != 3:
             raise RuntimeError("libnudf.so ABI version mismatch")
         _lib = L
     return _lib

@@ -249,8 +249,10 @@ __global__ void pe_forward_kernel(const float* __restrict__ pts, int64_t P, int 
 }
 
 // out = cat(|y0|/scale, y[1:]); sgn = sign(y0)
+// y [P, y_ld] -> udf[row * ld_u] = |y0| / scale, feat[row * ld_f + j] = y[1 + j]  (the classic [P, 1 + F] tensor is udf = out,
+// feat = out + 1, ld_u = ld_f = ld_out); sgn <- sign(y0)
 __global__ void udf_finalize_kernel(const float* __restrict__ y, int y_ld, int d_out, int64_t P, float inv_scale,
-                                    float* __restrict__ out, int64_t ld_out, float* __restrict__ sgn, int t128) {
+                                    float* __restrict__ udf, int64_t ld_u, float* __restrict__ feat, int64_t ld_f, float* __restrict__ sgn, int t128) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t row = idx / d_out;
   int c = (int)(idx - row * d_out);
@@ -258,9 +260,10 @@ __global__ void udf_finalize_kernel(const float* __restrict__ y, int y_ld, int d
   float v = y[mat_off(t128 != 0, row, c, y_ld)];
   if (c == 0) {
     if (sgn) sgn[row] = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
-    v = fabsf(v) * inv_scale;
+    if (udf) udf[row * ld_u] = fabsf(v) * inv_scale;
+  } else if (feat) {
+    feat[row * ld_f + c - 1] = v;
   }
-  if (out) out[row * ld_out + c] = v;
 }
 __global__ void udf_value_only_kernel(const float* __restrict__ y, int y_ld, int64_t P, float inv_scale, float* __restrict__ udf) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,38 +382,38 @@ int colsum(const float* X, int64_t ldx, const float* w, float wscale, int64_t P,
 }
 
 // Zlast[:,0] = sgn * ob[:,0] / scale ; Zlast[:,1:] = ob[:,1:]
-__global__ void zlast_kernel(const float* __restrict__ ob, int64_t ld_ob, const float* __restrict__ sgn, float inv_scale,
-                             int d_out, int y_ld, int64_t P, float* __restrict__ z) {
+__global__ void zlast_kernel(const float* __restrict__ ub, int64_t ld_ub, const float* __restrict__ fb, int64_t ld_fb,
+                             const float* __restrict__ sgn, float inv_scale, int d_out, int y_ld, int64_t P, float* __restrict__ z) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t row = idx / y_ld;
   int c = (int)(idx - row * y_ld);
   if (row >= P) return;
   float v = 0.f;
-  if (c < d_out) {
-    v = ob[row * ld_ob + c];
-    if (c == 0) v *= sgn[row] * inv_scale;
-  }
+  if (c == 0) v = ub ? ub[row * ld_ub] * sgn[row] * inv_scale : 0.f;
+  else if (c < d_out) v = fb ? fb[row * ld_fb + c - 1] : 0.f;
   z[row * y_ld + c] = v;
 }
 
-// Same, split: zf[:, j] = ob[:, 1 + j] (features, ld = F) and z0 = sgn * ob[:, 0] / scale (udf head)
-__global__ void zlast_split_kernel(const float* __restrict__ ob, int64_t ld_ob, const float* __restrict__ sgn, float inv_scale,
-                                   int F, int64_t P, float* __restrict__ zf, float* __restrict__ z0, int t128 = 0) {
+// Upstream gradient of the last layer, split: zf[:, j] = feat_bar[:, j] (features, ld = F) and z0 = sgn * udf_bar / scale (udf head);
+// a null pointer stands for a zero gradient
+__global__ void zlast_split_kernel(const float* __restrict__ ub, int64_t ld_ub, const float* __restrict__ fb, int64_t ld_fb,
+                                   const float* __restrict__ sgn, float inv_scale, int F, int64_t P, float* __restrict__ zf,
+                                   float* __restrict__ z0, int t128 = 0) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t row = idx / (F + 1);
   int c = (int)(idx - row * (F + 1));
   if (row >= P) return;
-  float v = ob[row * ld_ob + c];
-  if (c == 0) z0[row] = v * sgn[row] * inv_scale;
-  else zf[mat_off(t128 != 0, row, c - 1, F)] = v;
+  if (c == 0) z0[row] = ub ? ub[row * ld_ub] * sgn[row] * inv_scale : 0.f;
+  else zf[mat_off(t128 != 0, row, c - 1, F)] = fb ? fb[row * ld_fb + c - 1] : 0.f;
 }
 
 // Tiled versions for the T128 layout (fused chains): a CTA moves a 128-point x 32-column tile through shared memory so that
 // BOTH sides are coalesced -- 16-byte accesses with the points innermost on the T128 side, 128-byte column runs on the row-major
 // side (the torch-facing [P, 257] tensors: odd width, no vector access possible).  grid = (point tiles, column tiles).
-// out[P, ld_out] <- cat(|y0| / scale, y[1:]);  sgn <- sign(y0)
+// udf <- |y0| / scale, feat <- y[1:]  (separate leading dimensions);  sgn <- sign(y0)
 __global__ void __launch_bounds__(256) udf_finalize_t128_kernel(const float* __restrict__ y, int y_ld, int d_out, int64_t P, float inv_scale,
-                                                               float* __restrict__ out, int64_t ld_out, float* __restrict__ sgn) {
+                                                               float* __restrict__ udf, int64_t ld_u, float* __restrict__ feat, int64_t ld_f,
+                                                               float* __restrict__ sgn) {
   __shared__ float tile[128][33];
   const int64_t r0 = (int64_t)blockIdx.x * 128;
   const int c0 = blockIdx.y * 32;
@@ -437,15 +440,17 @@ __global__ void __launch_bounds__(256) udf_finalize_t128_kernel(const float* __r
       float v = tile[r][cc];
       if (c == 0) {
         if (sgn) sgn[row] = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
-        v = fabsf(v) * inv_scale;
+        if (udf) udf[row * ld_u] = fabsf(v) * inv_scale;
+      } else if (feat) {
+        feat[row * ld_f + c - 1] = v;
       }
-      if (out) out[row * ld_out + c] = v;
     }
   }
 }
-// zf[:, j] (T128, ld F) <- ob[:, 1 + j];  z0 <- sgn * ob[:, 0] / scale
-__global__ void __launch_bounds__(256) zlast_split_t128_kernel(const float* __restrict__ ob, int64_t ld_ob, const float* __restrict__ sgn,
-                                                              float inv_scale, int F, int64_t P, float* __restrict__ zf, float* __restrict__ z0) {
+// zf[:, j] (T128, ld F) <- feat_bar[:, j];  z0 <- sgn * udf_bar / scale  (null = zero gradient)
+__global__ void __launch_bounds__(256) zlast_split_t128_kernel(const float* __restrict__ ub, int64_t ld_ub, const float* __restrict__ fb,
+                                                              int64_t ld_fb, const float* __restrict__ sgn, float inv_scale, int F, int64_t P,
+                                                              float* __restrict__ zf, float* __restrict__ z0) {
   __shared__ float tile[128][33];
   const int64_t r0 = (int64_t)blockIdx.x * 128;
   const int c0 = blockIdx.y * 32;                           // feature columns [c0, c0 + 32) of zf = columns 1 + c0 .. of ob
@@ -456,9 +461,9 @@ __global__ void __launch_bounds__(256) zlast_split_t128_kernel(const float* __re
     const int r = (t >> 5) + 8 * k;
     const int64_t row = r0 + r;
     float v = 0.f;
-    if (row < P && c0 + cc < F) v = ob[row * ld_ob + 1 + c0 + cc];
+    if (fb != nullptr && row < P && c0 + cc < F) v = fb[row * ld_fb + c0 + cc];
     tile[r][cc] = v;
-    if (blockIdx.y == 0 && cc == 0 && row < P) z0[row] = ob[row * ld_ob] * sgn[row] * inv_scale;
+    if (blockIdx.y == 0 && cc == 0 && row < P) z0[row] = ub ? ub[row * ld_ub] * sgn[row] * inv_scale : 0.f;
   }
   __syncthreads();
   const int r = t & 127;
@@ -810,13 +815,12 @@ int64_t nudf_udf_scratch_floats(const nudf_udf_desc* d, int64_t P) {
   return s.total;
 }
 
-int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* out, int64_t ld_out,
-                     float* grad, float* ctx, void* stream) {
+static int udf_forward_impl(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* udf, int64_t ld_u, float* feat,
+                            int64_t ld_f, float* grad, float* ctx, void* stream) {
   UdfPlan p;
   if (int rc = make_plan(d, &p)) return rc;
   if (P <= 0) return 0;
   NUDF_REQUIRE(wfold && pts && ctx, "null pointer");
-  NUDF_REQUIRE(out == nullptr || ld_out >= p.d_out, "ld_out too small");
   cudaStream_t st = (cudaStream_t)stream;
   UdfCtx c;
   ctx_layout(p, P, grad != nullptr, &c);
@@ -825,8 +829,8 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
     chain::ChainParams cp;
     build_forward(p, wfold, pts, P, ctx, &c, nullptr, true, &cp);
     if (int rc = chain::launch_chain(cp, FAM_UDF_FWD_CHAIN, st)) return rc;
-    udf_finalize_t128_kernel<<<dim3(nblk(P, 128), nblk(p.d_out, 32)), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
-                                                                                    ctx + c.sgn);
+    udf_finalize_t128_kernel<<<dim3(nblk(P, 128), nblk(p.d_out, 32)), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, udf, ld_u,
+                                                                                    feat, ld_f, ctx + c.sgn);
     NUDF_LAUNCH_OK();
     pe_vjp_kernel<<<nblk(P, 128), 128, 0, st>>>(pts, ctx + c.ge, p.pe_ld, P, p.L, p.scale, grad, 1, p.skip >= 1 ? ctx + c.gpe : nullptr,
                                                 p.stash_ld, p.skip >= 1 ? (p.out_dim[p.skip - 1] & 7) : 0);
@@ -834,11 +838,25 @@ int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pt
     return 0;
   }
   if (int rc = value_chain(p, d, wfold, pts, P, ctx, c, st)) return rc;
-  udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, out, ld_out,
+  udf_finalize_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ctx + c.y, p.y_ld, p.d_out, P, 1.0f / p.scale, udf, ld_u, feat, ld_f,
                                                               ctx + c.sgn, fused_on(p) ? 1 : 0);
   NUDF_LAUNCH_OK();
   if (grad) return reverse_chain(p, wfold, pts, P, ctx, c, grad, st);
   return 0;
+}
+
+int nudf_udf_forward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* out, int64_t ld_out,
+                     float* grad, float* ctx, void* stream) {
+  NUDF_REQUIRE(d != nullptr, "null descriptor");
+  NUDF_REQUIRE(out == nullptr || ld_out >= d->d_out, "ld_out too small");
+  return udf_forward_impl(d, wfold, pts, P, out, ld_out, out ? out + 1 : nullptr, ld_out, grad, ctx, stream);
+}
+
+int nudf_udf_forward_split(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* udf, float* feat,
+                           int64_t ld_feat, float* grad, float* ctx, void* stream) {
+  NUDF_REQUIRE(d != nullptr, "null descriptor");
+  NUDF_REQUIRE(feat == nullptr || ld_feat >= d->d_out - 1, "ld_feat too small");
+  return udf_forward_impl(d, wfold, pts, P, udf, 1, feat, ld_feat, grad, ctx, stream);
 }
 
 int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, float* udf, float* work,
@@ -866,9 +884,27 @@ int nudf_udf_value(const nudf_udf_desc* d, const float* wfold, const float* pts,
   return 0;
 }
 
+static int udf_backward_impl(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* ub, int64_t ld_ub,
+                             const float* fb, int64_t ld_fb, const float* grad_bar, const float* ctx_c, float* scratch, float* dwfold,
+                             float* dbias, void* stream);
+
 int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* out_bar,
                       int64_t ld_ob, const float* grad_bar, const float* ctx_c, float* scratch, float* dwfold,
                       float* dbias, void* stream) {
+  return udf_backward_impl(d, wfold, pts, P, out_bar, ld_ob, out_bar ? out_bar + 1 : nullptr, ld_ob, grad_bar, ctx_c, scratch, dwfold, dbias,
+                           stream);
+}
+
+int nudf_udf_backward_split(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* udf_bar,
+                            const float* feat_bar, int64_t ld_fb, const float* grad_bar, const float* ctx_c, float* scratch,
+                            float* dwfold, float* dbias, void* stream) {
+  return udf_backward_impl(d, wfold, pts, P, udf_bar, 1, feat_bar, ld_fb, grad_bar, ctx_c, scratch, dwfold, dbias, stream);
+}
+
+static int udf_backward_impl(const nudf_udf_desc* d, const float* wfold, const float* pts, int64_t P, const float* ub, int64_t ld_ub,
+                             const float* fb, int64_t ld_fb, const float* grad_bar, const float* ctx_c, float* scratch, float* dwfold,
+                             float* dbias, void* stream) {
+  const bool out_bar = ub != nullptr || fb != nullptr;      // some upstream gradient of the value / feature outputs
   UdfPlan p;
   if (int rc = make_plan(d, &p)) return rc;
   NUDF_REQUIRE(wfold && dwfold && dbias, "null pointer");
@@ -891,7 +927,7 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
     float* zf = scratch + s.zlast;                  // [P, F] feature part of the upstream gradient of the last layer
     float* z0 = zf + ctx_rows(p, P) * F;            // [P]    udf-head part, times sgn / scale
     if (out_bar) {
-      zlast_split_t128_kernel<<<dim3(nblk(P, 128), nblk(F, 32)), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
+      zlast_split_t128_kernel<<<dim3(nblk(P, 128), nblk(F, 32)), 256, 0, st>>>(ub, ld_ub, fb, ld_fb, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
       NUDF_LAUNCH_OK();
     } else {
       NUDF_CUDA_OK(cudaMemsetAsync(zf, 0, sizeof(float) * (ctx_rows(p, P) * F + P), st));
@@ -1001,13 +1037,13 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
       NUDF_CUDA_OK(cudaMemsetAsync(scratch + s.q[l], 0, sizeof(float) * P * p.o_ld[l], st));
   float* zl = scratch + s.zlast;
   const int F = p.d_out - 1;
-  const bool split_head = out_bar != nullptr && tc_on(TC_BWD) && F >= 64 && (F % 4) == 0 && tc::pad64(F) <= 64 * tc::WR_MAX_SLICES;
+  const bool split_head = out_bar && tc_on(TC_BWD) && F >= 64 && (F % 4) == 0 && tc::pad64(F) <= 64 * tc::WR_MAX_SLICES;
   if (split_head) {
     // 257 = 1 udf-head row + 256 feature rows: the feature block is a K = 256 contraction for the weights-resident tensor
     // kernel, the head row a rank-1 update in its epilogue (and a weighted column sum for its weight gradient).
     float* zf = zl;
     float* z0 = zl + P * F;
-    zlast_split_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
+    zlast_split_kernel<<<nblk(P * p.d_out, 256), 256, 0, st>>>(ub, ld_ub, fb, ld_fb, ctx + c.sgn, 1.0f / p.scale, F, P, zf, z0);
     NUDF_LAUNCH_OK();
     const float* Wl = wfold + p.w_off[last];
     float* dWl = dwfold + p.w_off[last];
@@ -1024,7 +1060,7 @@ int nudf_udf_backward(const nudf_udf_desc* d, const float* wfold, const float* p
     if (int rc = gemm_nn(zf, F, Wl + p.w_ld[last], p.w_ld[last], P, p.in_dim[last], F, eb, st, img_base(p, wfold) + p.img_nn1, TC_BWD))
       return rc;
   } else if (out_bar) {
-    zlast_kernel<<<nblk(P * p.y_ld, 256), 256, 0, st>>>(out_bar, ld_ob, ctx + c.sgn, 1.0f / p.scale, p.d_out, p.y_ld, P, zl);
+    zlast_kernel<<<nblk(P * p.y_ld, 256), 256, 0, st>>>(ub, ld_ub, fb, ld_fb, ctx + c.sgn, 1.0f / p.scale, p.d_out, p.y_ld, P, zl);
     NUDF_LAUNCH_OK();
     EpiAtomicAdd ew{dwfold + p.w_off[last], p.w_ld[last]};
     if (int rc = gemm_tn(zl, p.y_ld, ctx + c.a[last], p.a_ld[last], p.out_dim[last], p.in_dim[last], P, ew, st, split, TC_WGRAD,

@@ -111,6 +111,10 @@ class UDFNetwork(nn.Module):
         twice for this, udf_renderer_blending.py:364 and :368)."""
         return ops.udf_forward(self._handle, x.reshape(-1, 3), True)
 
+    def value_feature_gradient(self, x):
+        """(udf [P,1], feature [P,d_out-1], d udf/d x [P,3]) as separate tensors from ONE fused evaluation: render_core's form."""
+        return ops.udf_forward_split(self._handle, x.reshape(-1, 3), True)
+
     def forward(self, inputs):
         out, _ = ops.udf_forward(self._handle, inputs.reshape(-1, 3), False)
         return out

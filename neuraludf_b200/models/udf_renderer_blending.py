@@ -206,9 +206,8 @@ class UDFRendererBlending:
         rays_d = rays_d.float().contiguous()
         pts, mid_z_vals, dists = ops.ray_points(rays_o, rays_d, z_vals, sample_dist)
 
-        out, gradients = udf_network.value_and_gradient(pts)        # [P, 1+F], [P, 3]  (:364-368)
-        udf = out[:, 0]
-        feature_vector = out[:, 1:]
+        udf, feature_vector, gradients = udf_network.value_feature_gradient(pts)        # [P,1], [P,F], [P,3]  (:364-368)
+        udf = udf[:, 0]
 
         inv_s = deviation_network(torch.zeros([1, 3], device=device))[:, :1].clip(1e-6, 1e6)     # :373
         beta = beta_network.get_beta().clip(1e-6, 1e6)

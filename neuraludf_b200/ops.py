@@ -140,28 +140,37 @@ class UdfHandle:
 
 class _UdfFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pts, handle, with_grad, *params):
+    def forward(ctx, pts, handle, with_grad, split, *params):
+        """split = False: (out [P, d_out], empty, grad);  split = True: (udf [P, 1], feat [P, d_out - 1], grad) as SEPARATE tensors
+        (the renderer's form: no slicing of an odd-width [P, 257] tensor and no zero-fill / copy / add to reassemble its gradient)"""
         lib = L.lib()
         handle.refresh()
         pts = _f32c(pts)
         _require_cuda(pts)
         P = pts.shape[0]
         d_out = handle.meta[2]
-        out = torch.empty(P, d_out, dtype=torch.float32, device=pts.device)
-        grad = torch.empty(P, 3, dtype=torch.float32, device=pts.device) if with_grad else None
+        dev = pts.device
+        grad = torch.empty(P, 3, dtype=torch.float32, device=dev) if with_grad else None
         nctx = lib.nudf_udf_ctx_floats(ctypes.byref(handle.desc), P, 1 if with_grad else 0)
-        buf = torch.empty(max(nctx, 1), dtype=torch.float32, device=pts.device)
-        L.check(lib.nudf_udf_forward(ctypes.byref(handle.desc), L.ptr(handle.wfold), L.ptr(pts), P, L.ptr(out), d_out,
-                                     L.ptr(grad), L.ptr(buf), L.stream_ptr()), "nudf_udf_forward")
-        ctx.handle, ctx.with_grad, ctx.P = handle, with_grad, P
+        buf = torch.empty(max(nctx, 1), dtype=torch.float32, device=dev)
+        if split:
+            a = torch.empty(P, 1, dtype=torch.float32, device=dev)
+            b = torch.empty(P, d_out - 1, dtype=torch.float32, device=dev)
+            L.check(lib.nudf_udf_forward_split(ctypes.byref(handle.desc), L.ptr(handle.wfold), L.ptr(pts), P, L.ptr(a), L.ptr(b), d_out - 1,
+                                               L.ptr(grad), L.ptr(buf), L.stream_ptr()), "nudf_udf_forward_split")
+        else:
+            a = torch.empty(P, d_out, dtype=torch.float32, device=dev)
+            b = torch.empty(0, device=dev)
+            L.check(lib.nudf_udf_forward(ctypes.byref(handle.desc), L.ptr(handle.wfold), L.ptr(pts), P, L.ptr(a), d_out,
+                                         L.ptr(grad), L.ptr(buf), L.stream_ptr()), "nudf_udf_forward")
+        ctx.handle, ctx.with_grad, ctx.P, ctx.split = handle, with_grad, P, split
         ctx.save_for_backward(pts, buf)
         ctx.key = handle._key
-        if with_grad:
-            return out, grad
-        return out, torch.empty(0, device=pts.device)
+        ctx.set_materialize_grads(False)            # unused outputs arrive as None: a null pointer = zero gradient for the kernels
+        return a, b, (grad if with_grad else torch.empty(0, device=dev))
 
     @staticmethod
-    def backward(ctx, out_bar, grad_bar):
+    def backward(ctx, a_bar, b_bar, grad_bar):
         lib = L.lib()
         h = ctx.handle
         pts, buf = ctx.saved_tensors
@@ -170,7 +179,8 @@ class _UdfFunction(torch.autograd.Function):
         P = ctx.P
         if not ctx.with_grad:
             grad_bar = None
-        out_bar = _f32c(out_bar)
+        a_bar = _f32c(a_bar)
+        b_bar = _f32c(b_bar) if ctx.split else None
         grad_bar = _f32c(grad_bar)
         dev = pts.device
         nscr = lib.nudf_udf_scratch_floats(ctypes.byref(h.desc), P)
@@ -192,9 +202,14 @@ class _UdfFunction(torch.autograd.Function):
                 n = m.bias.numel()
                 dbs.append(db[off:off + n])
                 off += n
-        L.check(lib.nudf_udf_backward(ctypes.byref(h.desc), L.ptr(h.wfold), L.ptr(pts), P, L.ptr(out_bar),
-                                      out_bar.shape[1] if out_bar is not None else 0, L.ptr(grad_bar), L.ptr(buf),
-                                      L.ptr(scratch), L.ptr(dw), L.ptr(db), L.stream_ptr()), "nudf_udf_backward")
+        if ctx.split:
+            L.check(lib.nudf_udf_backward_split(ctypes.byref(h.desc), L.ptr(h.wfold), L.ptr(pts), P, L.ptr(a_bar), L.ptr(b_bar),
+                                                b_bar.shape[1] if b_bar is not None else 0, L.ptr(grad_bar), L.ptr(buf),
+                                                L.ptr(scratch), L.ptr(dw), L.ptr(db), L.stream_ptr()), "nudf_udf_backward_split")
+        else:
+            L.check(lib.nudf_udf_backward(ctypes.byref(h.desc), L.ptr(h.wfold), L.ptr(pts), P, L.ptr(a_bar),
+                                          a_bar.shape[1] if a_bar is not None else 0, L.ptr(grad_bar), L.ptr(buf),
+                                          L.ptr(scratch), L.ptr(dw), L.ptr(db), L.stream_ptr()), "nudf_udf_backward")
         L.check(lib.nudf_udf_unfold_grads(ctypes.byref(h.desc), L.ptr(dw), _ptr_array(dgs), _ptr_array(dvs),
                                           L.stream_ptr()), "nudf_udf_unfold_grads")
         if sink is not None:
@@ -202,13 +217,19 @@ class _UdfFunction(torch.autograd.Function):
         grads = []
         for l in range(len(h.layers)):
             grads += [dgs[l], dvs[l], dbs[l]]
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 def udf_forward(handle, pts, with_grad):
     """(out [P,d_out], grad [P,3] or None); differentiable w.r.t. the module parameters (not w.r.t. pts)."""
-    out, grad = _UdfFunction.apply(pts, handle, with_grad, *handle.params())
+    out, _, grad = _UdfFunction.apply(pts, handle, with_grad, False, *handle.params())
     return out, (grad if with_grad else None)
+
+
+def udf_forward_split(handle, pts, with_grad=True):
+    """(udf [P,1], feature [P,d_out-1], grad [P,3] or None) as separate tensors -- what render_core consumes."""
+    udf, feat, grad = _UdfFunction.apply(pts, handle, with_grad, True, *handle.params())
+    return udf, feat, (grad if with_grad else None)
 
 
 def udf_value(handle, pts):

@@ -107,3 +107,36 @@ def test_chain_large_batch_throughput_report(golden):
     rep["value_only_algorithmic_tflops"] = 65536 * 918016 / (rep["value_only_us"] * 1e-6) / 1e12
     report("chain.throughput_65536", **rep)
     assert rep["value_only_us"] > 0
+
+
+def test_split_outputs_match_the_packed_form(golden):
+    """value_feature_gradient (separate udf / feature tensors, what render_core consumes) == value_and_gradient ([P, 1+F])
+    in the outputs and in every parameter gradient, with upstream gradients on all three outputs or on a subset."""
+    g = golden
+    x = _points(2500, 11).float().to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    ob = torch.randn(2500, 257, generator=gen).to(DEV)
+    gb = torch.randn(2500, 3, generator=gen).to(DEV)
+    for use in ((1, 1, 1), (0, 1, 0), (1, 0, 1)):
+        res = []
+        for split in (False, True):
+            udf = build_modules(g, DEV, "udf")[0]
+            if split:
+                u, f, grad = udf.value_feature_gradient(x)
+                out = torch.cat([u, f], dim=1)
+            else:
+                out, grad = udf.value_and_gradient(x)
+                u, f = out[:, :1], out[:, 1:]
+            loss = 0.0
+            if use[0]:
+                loss = loss + (u * ob[:, :1]).sum()
+            if use[1]:
+                loss = loss + (f * ob[:, 1:]).sum()
+            if use[2]:
+                loss = loss + (grad * gb).sum()
+            loss.backward()
+            res.append((out.detach(), grad.detach(), {k: v.grad.clone() for k, v in udf.named_parameters()}))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        for k in res[0][2]:
+            a, b = res[1][2][k], res[0][2][k]
+            assert err_inf(a, b) <= 1e-5 * scale_inf(b) + 1e-12, (use, k)
