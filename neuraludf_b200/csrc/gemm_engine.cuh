@@ -12,10 +12,11 @@
 
 namespace nudf {
 
-// TC_FWD: UDF value chain (3 planes); TC_REV/TAN/BWD: UDF gradient, tangent and backward chains; TC_WGRAD: weight gradients;
-// TC_COLOR / TC_NERF: BACKWARD data GEMMs of the ReLU networks; TC_RELU_FWD: their forward passes.  The default mask
-// (capi.cu) leaves both forward bits off: a 4e-6 perturbation of a pre-activation flips ~60x more ReLU gates than the
-// reference's own fp32 rounding does, which shows up as O(1/batch) jumps in the parameter gradients.
+// TC_FWD: UDF value chain (fused exact fp16-slice kernel); TC_REV/TAN/BWD: UDF gradient, tangent and backward chains; TC_WGRAD:
+// weight gradients; TC_COLOR / TC_NERF: BACKWARD data GEMMs of the ReLU networks (2 planes); TC_RELU_FWD: their forward passes,
+// with 3 planes / 6 products (gemm_w<3>, per-K-slice accumulators summed in fp32): a 4e-6 perturbation of a pre-activation (the
+// 2-plane split) flips ~60x more ReLU gates than the reference's own fp32 rounding does, which shows up as O(1/batch) jumps in
+// the parameter gradients and fails test_color_network_vs_reference_and_grads; the 3-plane product (3.5e-7 per layer) passes.
 enum TcChain { TC_FWD = 1, TC_REV = 2, TC_TAN = 4, TC_BWD = 8, TC_WGRAD = 16, TC_COLOR = 32, TC_NERF = 64, TC_RELU_FWD = 128 };
 
 int get_engine();

@@ -195,9 +195,9 @@ static int color_plan(const nudf_color_desc* d, ColorPlan* p) {
   p->w_total = off; p->b_total = boff;
   int64_t ioff = 0;
   for (int l = 0; l < p->n_lin; ++l) {
-    p->ib_nt[l] = ioff; ioff += tc::image_elems(p->dims_b[l + 1], p->dims_b[l], 2);
+    p->ib_nt[l] = ioff; ioff += tc::image_elems(p->dims_b[l + 1], p->dims_b[l], 3);    // forward images: 3 planes (6 products)
     p->ib_nn[l] = ioff; ioff += tc::image_elems(p->dims_b[l], p->dims_b[l + 1], 2);
-    p->im_nt[l] = ioff; ioff += tc::image_elems(p->dims_m[l + 1], p->dims_m[l], 2);
+    p->im_nt[l] = ioff; ioff += tc::image_elems(p->dims_m[l + 1], p->dims_m[l], 3);
     p->im_nn[l] = ioff; ioff += tc::image_elems(p->dims_m[l], p->dims_m[l + 1], 2);
   }
   p->img_total = round_up(ioff, 8);
@@ -316,9 +316,9 @@ int nudf_color_fold_weights(const nudf_color_desc* d, float* wfold, void* stream
     tc::PrepWJobs pj;
     pj.n = 0;
     for (int l = 0; l < p.n_lin; ++l) {
-      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wb_off[l], img + p.ib_nt[l], (int)p.wb_ld[l], p.dims_b[l + 1], p.dims_b[l], 0, 2};
+      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wb_off[l], img + p.ib_nt[l], (int)p.wb_ld[l], p.dims_b[l + 1], p.dims_b[l], 0, 3};
       pj.j[pj.n++] = tc::PrepWJob{wfold + p.wb_off[l], img + p.ib_nn[l], (int)p.wb_ld[l], p.dims_b[l], p.dims_b[l + 1], 1, 2};
-      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wm_off[l], img + p.im_nt[l], (int)p.wm_ld[l], p.dims_m[l + 1], p.dims_m[l], 0, 2};
+      pj.j[pj.n++] = tc::PrepWJob{wfold + p.wm_off[l], img + p.im_nt[l], (int)p.wm_ld[l], p.dims_m[l + 1], p.dims_m[l], 0, 3};
       pj.j[pj.n++] = tc::PrepWJob{wfold + p.wm_off[l], img + p.im_nn[l], (int)p.wm_ld[l], p.dims_m[l], p.dims_m[l + 1], 1, 2};
     }
     if (int rc = tc::prep_weights_jobs(pj, st)) return rc;
@@ -371,7 +371,7 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     else if (l == nl - 2) { e.C = xm + p.c_hid; e.ldc = p.ld_xm; e.act = ACT_RELU; }      // x_hidden (fields.py:472-473)
     else { e.C = xm + p.c_cb; e.ldc = p.ld_xm; e.act = ACT_SIGMOID; }                      // color_base (:475-476)
     if (int rc = gemm_nt(X, ldx, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l + 1], p.dims_b[l], e, st,
-                         cimg + p.ib_nt[l], TC_RELU_FWD)) return rc;
+                         cimg + p.ib_nt[l], TC_RELU_FWD, 3)) return rc;
   }
   if (color_base) {
     ew_copy_cols_kernel<<<ew_blocks(P * p.d_out, 256), 256, 0, st>>>(xm + p.c_cb, p.ld_xm, color_base, p.d_out, 0, p.d_out, P, 1.f);
@@ -386,7 +386,7 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     if (l < nl - 1) { e.C = ctx + c.hm[l + 1]; e.ldc = p.H; e.act = ACT_RELU; }
     else { e.C = ctx + c.ym; e.ldc = p.ld_ym; e.act = ACT_NONE; }
     if (int rc = gemm_nt(X, ldx, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l + 1], p.dims_m[l], e, st,
-                         cimg + p.im_nt[l], TC_RELU_FWD)) return rc;
+                         cimg + p.im_nt[l], TC_RELU_FWD, 3)) return rc;
   }
   color_head_kernel<<<ew_blocks(P * (p.d_out + p.n_blend), 256), 256, 0, st>>>(ctx + c.ym, p.ld_ym, p.d_out, p.n_blend, P,
                                                                               color, ctx + c.cs, 4, blend);
@@ -510,12 +510,12 @@ static int nerf_plan(const nudf_nerf_desc* d, NerfPlan* p) {
   p->ld_x5 = (int)round_up(p->W + p->ch, 4);
   int64_t io = 0;
   for (int i = 0; i < p->D; ++i) {
-    p->ipts_nt[i] = io; io += tc::image_elems(p->W, p->in_dim[i], 2);
+    p->ipts_nt[i] = io; io += tc::image_elems(p->W, p->in_dim[i], 3);    // forward images: 3 planes (6 products)
     p->ipts_nn[i] = io; io += tc::image_elems(p->in_dim[i], p->W, 2);
   }
-  p->ifeat_nt = io; io += tc::image_elems(p->W, p->W, 2);
+  p->ifeat_nt = io; io += tc::image_elems(p->W, p->W, 3);
   p->ifeat_nn = io; io += tc::image_elems(p->W, p->W, 2);
-  p->iviews_nt = io; io += tc::image_elems(p->W / 2, p->W + p->chv, 2);
+  p->iviews_nt = io; io += tc::image_elems(p->W / 2, p->W + p->chv, 3);
   p->iviews_nn = io; io += tc::image_elems(p->W + p->chv, p->W / 2, 2);
   p->img_total = round_up(io, 8);
   return 0;
@@ -566,15 +566,17 @@ int nudf_nerf_prepare(const nudf_nerf_desc* d, float* wimg, void* stream) {
   NUDF_REQUIRE(wimg != nullptr, "null wimg");
   cudaStream_t st = (cudaStream_t)stream;
   uint16_t* img = reinterpret_cast<uint16_t*>(wimg);
+  tc::PrepWJobs pj;                                        // all images in one launch; forward (X W^T) images with 3 planes
+  pj.n = 0;
   for (int i = 0; i < p.D; ++i) {
-    if (int rc = tc::prep_weights(d->pts_w[i], p.in_dim[i], p.W, p.in_dim[i], 0, 2, img + p.ipts_nt[i], st)) return rc;
-    if (int rc = tc::prep_weights(d->pts_w[i], p.in_dim[i], p.in_dim[i], p.W, 1, 2, img + p.ipts_nn[i], st)) return rc;
+    pj.j[pj.n++] = tc::PrepWJob{d->pts_w[i], img + p.ipts_nt[i], p.in_dim[i], p.W, p.in_dim[i], 0, 3};
+    pj.j[pj.n++] = tc::PrepWJob{d->pts_w[i], img + p.ipts_nn[i], p.in_dim[i], p.in_dim[i], p.W, 1, 2};
   }
-  if (int rc = tc::prep_weights(d->feature_w, p.W, p.W, p.W, 0, 2, img + p.ifeat_nt, st)) return rc;
-  if (int rc = tc::prep_weights(d->feature_w, p.W, p.W, p.W, 1, 2, img + p.ifeat_nn, st)) return rc;
-  if (int rc = tc::prep_weights(d->views_w, p.W + p.chv, p.W / 2, p.W + p.chv, 0, 2, img + p.iviews_nt, st)) return rc;
-  if (int rc = tc::prep_weights(d->views_w, p.W + p.chv, p.W + p.chv, p.W / 2, 1, 2, img + p.iviews_nn, st)) return rc;
-  return 0;
+  pj.j[pj.n++] = tc::PrepWJob{d->feature_w, img + p.ifeat_nt, p.W, p.W, p.W, 0, 3};
+  pj.j[pj.n++] = tc::PrepWJob{d->feature_w, img + p.ifeat_nn, p.W, p.W, p.W, 1, 2};
+  pj.j[pj.n++] = tc::PrepWJob{d->views_w, img + p.iviews_nt, p.W + p.chv, p.W / 2, p.W + p.chv, 0, 3};
+  pj.j[pj.n++] = tc::PrepWJob{d->views_w, img + p.iviews_nn, p.W + p.chv, p.W + p.chv, p.W / 2, 1, 2};
+  return tc::prep_weights_jobs(pj, st);
 }
 
 int64_t nudf_nerf_ctx_floats(const nudf_nerf_desc* d, int64_t P) {
@@ -614,7 +616,7 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* wimg, const float* p
     const float* X = nerf_x(p, ctx, c, i, &ldx);
     float* Hh = nerf_h(p, ctx, c, i, &ldh);
     EpiAct e{Hh, ldh, d->pts_b[i], ACT_RELU, 1.0f};
-    if (int rc = gemm_nt(X, ldx, d->pts_w[i], p.in_dim[i], P, p.W, p.in_dim[i], e, st, img ? img + p.ipts_nt[i] : nullptr, TC_RELU_FWD)) return rc;
+    if (int rc = gemm_nt(X, ldx, d->pts_w[i], p.in_dim[i], P, p.W, p.in_dim[i], e, st, img ? img + p.ipts_nt[i] : nullptr, TC_RELU_FWD, 3)) return rc;
   }
   int64_t ldl;
   const float* Hl = nerf_h(p, ctx, c, p.D - 1, &ldl);
@@ -624,11 +626,11 @@ int nudf_nerf_forward(const nudf_nerf_desc* d, const float* wimg, const float* p
   }
   {
     EpiAct e{ctx + c.f, p.ld_f, d->feature_b, ACT_NONE, 1.0f};
-    if (int rc = gemm_nt(Hl, ldl, d->feature_w, p.W, P, p.W, p.W, e, st, img ? img + p.ifeat_nt : nullptr, TC_RELU_FWD)) return rc;
+    if (int rc = gemm_nt(Hl, ldl, d->feature_w, p.W, P, p.W, p.W, e, st, img ? img + p.ifeat_nt : nullptr, TC_RELU_FWD, 3)) return rc;
   }
   {
     EpiAct e{ctx + c.hv, p.W / 2, d->views_b, ACT_RELU, 1.0f};
-    if (int rc = gemm_nt(ctx + c.f, p.ld_f, d->views_w, p.W + p.chv, P, p.W / 2, p.W + p.chv, e, st, img ? img + p.iviews_nt : nullptr, TC_RELU_FWD)) return rc;
+    if (int rc = gemm_nt(ctx + c.f, p.ld_f, d->views_w, p.W + p.chv, P, p.W / 2, p.W + p.chv, e, st, img ? img + p.iviews_nt : nullptr, TC_RELU_FWD, 3)) return rc;
   }
   {
     EpiAct e{rgb, 3, d->rgb_b, ACT_NONE, 1.0f};
