@@ -96,6 +96,55 @@ __global__ void pack_pts_feat_kernel(const float* __restrict__ pts, const float*
   *reinterpret_cast<float4*>(xb + row * ld_xb + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// Forward of a narrow head (N <= 16 outputs, K <= 128: colour_base, the colour / blending-logit head): Y[p, n] = act(<X[p, :], W[n, :]> + b[n]).
+// One warp per point, lanes along K (coalesced 128-byte reads of X, which may be an unaligned column window of a wider tensor); the
+// weights live in registers.  Streams X once (HBM-bound) instead of padding 3..13 output columns to a 128-wide GEMM tile.
+template <int MAXN>
+__global__ void __launch_bounds__(256) dense_small_forward_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw,
+                                                                 const float* __restrict__ bias, int N, int K, int act, float post_scale,
+                                                                 float* __restrict__ C, int64_t ldc, int64_t P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float w[MAXN][4];
+#pragma unroll
+  for (int n = 0; n < MAXN; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[n][i] = (n < N && lane + 32 * i < K) ? W[(int64_t)n * ldw + lane + 32 * i] : 0.f;
+  const float b = (bias != nullptr && lane < N) ? bias[lane] : 0.f;
+  for (int64_t row = gwarp; row < P; row += nwarps) {
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = (lane + 32 * i < K) ? X[row * ldx + lane + 32 * i] : 0.f;
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < MAXN; ++n) {
+      if (n < N) {
+        float t = x[0] * w[n][0] + x[1] * w[n][1] + x[2] * w[n][2] + x[3] * w[n][3];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == n) mine = t;
+      }
+    }
+    if (lane < N) {
+      float t = mine + b;
+      if (act == ACT_RELU) t = fmaxf(t, 0.f);
+      else if (act == ACT_SOFTPLUS100) t = softplus100(t);
+      else if (act == ACT_SIGMOID) t = sigmoidf_(t);
+      C[row * ldc + lane] = t * post_scale;
+    }
+  }
+}
+static inline int dense_small_forward(const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t P, int N, int K, const EpiAct& e,
+                                      cudaStream_t st) {
+  int blocks = (int)cdiv(P, 8 * 16);                         // ~16 points per warp
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  dense_small_forward_kernel<16><<<blocks, 256, 0, st>>>(X, ldx, W, ldw, e.bias, N, K, e.act, e.post_scale, e.C, e.ldc, P);
+  NUDF_LAUNCH_OK();
+  return 0;
+}
+
 // Weight gradient of a narrow head (n_out <= 16: colour / density heads): dW[m, n] += sum_p dZ[p, m] X[p, n], db[m] += sum_p dZ[p, m].
 // Streams X once (HBM-bound) instead of padding the 3..13 output rows to a 128-wide GEMM tile.  CTA = 128 input columns x 4
 // point lanes over a 256-point chunk; the lanes' partial sums meet in shared memory, then one atomic per (m, n) per CTA.
@@ -370,8 +419,10 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     if (l < nl - 2) { e.C = ctx + c.hb[l + 1]; e.ldc = p.H; e.act = ACT_RELU; }
     else if (l == nl - 2) { e.C = xm + p.c_hid; e.ldc = p.ld_xm; e.act = ACT_RELU; }      // x_hidden (fields.py:472-473)
     else { e.C = xm + p.c_cb; e.ldc = p.ld_xm; e.act = ACT_SIGMOID; }                      // color_base (:475-476)
-    if (int rc = gemm_nt(X, ldx, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l + 1], p.dims_b[l], e, st,
-                         cimg + p.ib_nt[l], TC_RELU_FWD, 3)) return rc;
+    if (p.dims_b[l + 1] <= 16 && p.dims_b[l] <= 128) {
+      if (int rc = dense_small_forward(X, ldx, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l + 1], p.dims_b[l], e, st)) return rc;
+    } else if (int rc = gemm_nt(X, ldx, wfold + p.wb_off[l], p.wb_ld[l], P, p.dims_b[l + 1], p.dims_b[l], e, st,
+                                cimg + p.ib_nt[l], TC_RELU_FWD, 3)) return rc;
   }
   if (color_base) {
     ew_copy_cols_kernel<<<ew_blocks(P * p.d_out, 256), 256, 0, st>>>(xm + p.c_cb, p.ld_xm, color_base, p.d_out, 0, p.d_out, P, 1.f);
@@ -385,8 +436,10 @@ int nudf_color_forward(const nudf_color_desc* d, const float* wfold, const float
     e.bias = d->main_b[l]; e.post_scale = 1.0f;
     if (l < nl - 1) { e.C = ctx + c.hm[l + 1]; e.ldc = p.H; e.act = ACT_RELU; }
     else { e.C = ctx + c.ym; e.ldc = p.ld_ym; e.act = ACT_NONE; }
-    if (int rc = gemm_nt(X, ldx, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l + 1], p.dims_m[l], e, st,
-                         cimg + p.im_nt[l], TC_RELU_FWD, 3)) return rc;
+    if (p.dims_m[l + 1] <= 16 && p.dims_m[l] <= 128) {
+      if (int rc = dense_small_forward(X, ldx, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l + 1], p.dims_m[l], e, st)) return rc;
+    } else if (int rc = gemm_nt(X, ldx, wfold + p.wm_off[l], p.wm_ld[l], P, p.dims_m[l + 1], p.dims_m[l], e, st,
+                                cimg + p.im_nt[l], TC_RELU_FWD, 3)) return rc;
   }
   color_head_kernel<<<ew_blocks(P * (p.d_out + p.n_blend), 256), 256, 0, st>>>(ctx + c.ym, p.ld_ym, p.d_out, p.n_blend, P,
                                                                               color, ctx + c.cs, 4, blend);
