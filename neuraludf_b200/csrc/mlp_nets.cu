@@ -112,26 +112,42 @@ __global__ void __launch_bounds__(256) dense_small_forward_kernel(const float* _
 #pragma unroll
     for (int i = 0; i < 4; ++i) w[n][i] = (n < N && lane + 32 * i < K) ? W[(int64_t)n * ldw + lane + 32 * i] : 0.f;
   const float b = (bias != nullptr && lane < N) ? bias[lane] : 0.f;
-  for (int64_t row = gwarp; row < P; row += nwarps) {
-    float x[4];
+  constexpr int R = 4;                                     // points per warp iteration: 16 independent loads in flight per lane
+  for (int64_t row0 = gwarp * R; row0 < P; row0 += nwarps * R) {
+    float x[R][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = (lane + 32 * i < K) ? X[row * ldx + lane + 32 * i] : 0.f;
-    float mine = 0.f;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[r][i] = (row0 + r < P && lane + 32 * i < K) ? X[(row0 + r) * ldx + lane + 32 * i] : 0.f;
+    float mine[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mine[r] = 0.f;
 #pragma unroll
     for (int n = 0; n < MAXN; ++n) {
       if (n < N) {
-        float t = x[0] * w[n][0] + x[1] * w[n][1] + x[2] * w[n][2] + x[3] * w[n][3];
+        float t[R];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == n) mine = t;
+        for (int r = 0; r < R; ++r) t[r] = x[r][0] * w[n][0] + x[r][1] * w[n][1] + x[r][2] * w[n][2] + x[r][3] * w[n][3];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int r = 0; r < R; ++r) t[r] += __shfl_xor_sync(0xffffffffu, t[r], o);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (lane == n) mine[r] = t[r];
       }
     }
     if (lane < N) {
-      float t = mine + b;
-      if (act == ACT_RELU) t = fmaxf(t, 0.f);
-      else if (act == ACT_SOFTPLUS100) t = softplus100(t);
-      else if (act == ACT_SIGMOID) t = sigmoidf_(t);
-      C[row * ldc + lane] = t * post_scale;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (row0 + r < P) {
+          float t = mine[r] + b;
+          if (act == ACT_RELU) t = fmaxf(t, 0.f);
+          else if (act == ACT_SOFTPLUS100) t = softplus100(t);
+          else if (act == ACT_SIGMOID) t = sigmoidf_(t);
+          C[(row0 + r) * ldc + lane] = t * post_scale;
+        }
+      }
     }
   }
 }
