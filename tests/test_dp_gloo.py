@@ -127,3 +127,46 @@ def test_gradient_sinks_allreduce_world2():
             assert torch.allclose(ga, torch.full((3, 2), 15.0))                  # mean of 10 and 20
             assert torch.allclose(gb, torch.full((2,), 1.5 + step))              # mean of (1 + step) and (2 + step)
             assert torch.allclose(gl, torch.full((1,), 0.5))
+
+
+def _replay_worker(rank, world, port, out):
+    """the CUDA-graph arrangement of bench.py at N > 1: forward + backward are replayed (the kernels write the flat bucket and the
+    static loose gradients, no Python bookkeeping runs), then allreduce_replayed() + the optimiser follow eagerly"""
+    sys.path.insert(0, ROOT)
+    from neuraludf_b200 import dp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))]
+    loose = torch.nn.Parameter(torch.zeros(2))
+    ha = _FakeHandle(a)
+    bucket = dp.GradBucket(a + [loose], modules=[_FakeModule(ha)], overlap=False)
+    # "capture": one ordinary step establishes the static gradient tensors (views of the flat bucket + the loose gradient)
+    ha.backward([torch.full_like(p, 1.0) for p in a])
+    loose.grad = torch.zeros(2)
+    static = [p.grad for p in a] + [loose.grad]
+    res = []
+    for step in range(2):
+        # "replay": the kernels overwrite the static tensors in place; begin() / ready() do not run
+        for g in static[:-1]:
+            g.fill_(float((rank + 1) * (step + 1)))
+        static[-1].fill_(float(rank + 10 * step))
+        bucket.allreduce_replayed()
+        assert all(p.grad is g for p, g in zip(a + [loose], static))             # nothing was re-allocated or zeroed
+        res.append((a[0].grad.clone(), a[2].grad.clone(), loose.grad.clone()))
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_allreduce_after_graph_replay_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_replay_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        for step in range(2):
+            ga, gc, gl = out[r][step]
+            assert torch.allclose(ga, torch.full((3, 2), 1.5 * (step + 1)))      # mean of (step+1) and 2 (step+1)
+            assert torch.allclose(gc, torch.full((3,), 1.5 * (step + 1)))
+            assert torch.allclose(gl, torch.full((2,), 0.5 + 10.0 * step))       # mean of 10 step and 1 + 10 step
